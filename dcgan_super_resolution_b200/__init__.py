@@ -1,0 +1,10 @@
+"""dcgan_super_resolution_b200 -- B200-native (sm_100a) DCGAN super-resolution training step.
+
+The product is ``libdcgansr.so`` (C ABI in ``include/dcgansr.h``; CUDA sources in ``csrc/``).  This
+package is the thin Python host above it: a ctypes binding (``_lib``), the Torch7-shaped surface the
+reference's ``train*.lua`` scripts use (``nn``), the reference's net graphs as data (``models``) and the
+data-parallel plumbing (``parallel``).  Nothing here computes on the CPU.
+"""
+from . import _lib, init, models, nn, parallel  # noqa: F401
+from ._lib import DcgansrError  # noqa: F401
+from .nn import Context, Sequential, make_step_cfg, stage_batch, train_step, train_step_staged  # noqa: F401

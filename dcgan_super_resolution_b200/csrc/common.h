@@ -1,0 +1,135 @@
+// common.h -- internal declarations shared by the translation units of libdcgansr.so.
+// Nothing here is part of the C ABI (include/dcgansr.h is).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#define DSR_MAX_TAPS 32
+
+// Stream handle + launch accounting (gpu_launches in bench.py is read from here) + the optional
+// per-launch event profiler (dcgansr_profile_begin/end): every launcher reports its kernel name and
+// the ALGORITHMIC work of the launch (flops for the convolution GEMMs, bytes for bandwidth kernels).
+#include <vector>
+enum { WORK_FLOPS = 0, WORK_BYTES = 1 };
+struct ProfRec { const char* name; double work; int kind; };
+struct Prof {
+  bool on = false;
+  std::vector<cudaEvent_t> pool;     // pool[0] = begin marker, pool[i+1] recorded after launch i
+  std::vector<ProfRec> recs;
+};
+struct St {
+  cudaStream_t s;
+  int64_t* launches;
+  Prof* prof;
+};
+static inline void dsr_launched(const St& st, const char* name, double work, int kind) {
+  if (st.launches) ++*st.launches;
+  if (st.prof && st.prof->on) {
+    Prof* p = st.prof;
+    size_t i = p->recs.size() + 1;
+    if (i >= p->pool.size()) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) return;
+      p->pool.push_back(e);
+    }
+    cudaEventRecord(p->pool[i], st.s);
+    p->recs.push_back(ProfRec{name, work, kind});
+  }
+}
+#define DSR_LAUNCHED(st, name, work, kind) dsr_launched((st), (name), (double)(work), (kind))
+
+enum { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2, ACT_TANH = 3, ACT_SIGMOID = 4 };
+enum { LOSS_BCE = 0, LOSS_MSE = 1 };
+
+// ---------------------------------------------------------------------------------------
+// Generic "tap-list" convolution geometry (one sub-pixel class per launch).
+//
+//   out[n, gy*so + oy0, gx*so + ox0, co] = act( sum_t sum_ci in[n, gy*si + dy[t], gx*si + dx[t], ci] * W[t][ci][co] )
+//
+// for (gy,gx) in [0,Hg)x[0,Wg); reads outside the input are zero.  It covers
+//   conv fwd            (si = stride, so = 1, taps = k*k,          dy = ky - p)
+//   full-conv dgrad     (same form with dy as the input)
+//   full-conv fwd       (si = 1, so = stride, one launch per output parity class)
+//   conv dgrad          (same sub-pixel form with dy as the input)
+// ---------------------------------------------------------------------------------------
+struct TapGeom {
+  int N, Hi, Wi, Ci;        // input tensor NHWC
+  int Ho, Wo, Co;           // output tensor NHWC (full dims)
+  int Hg, Wg;               // iterated grid for this class
+  int si, so, oy0, ox0;
+  int ntaps;
+  int dy[DSR_MAX_TAPS], dx[DSR_MAX_TAPS];
+};
+
+// ---------------------------------------------------------------------------------------
+// Generic weight-gradient geometry:
+//   acc[t][cp][cq] = sum_{n,gy,gx} P[n,gy,gx,cp] * Q[n, gy*s + dy[t], gx*s + dx[t], cq]
+// conv:      P = dy (Cp = cout), Q = x  (Cq = cin), master index cp*(Cq*T) + cq*T + t = w[co][ci][ky][kx]
+// full-conv: P = x  (Cp = cin),  Q = dy (Cq = cout),                              = w[ci][co][ky][kx]
+// ---------------------------------------------------------------------------------------
+struct WgradGeom {
+  int N, Hp, Wp, Cp;        // grid tensor
+  int Hq, Wq, Cq;           // shifted tensor
+  int s;
+  int ntaps;
+  int dy[DSR_MAX_TAPS], dx[DSR_MAX_TAPS];
+};
+
+// ---- kernels_bw.cu : bandwidth kernels ----------------------------------------------------
+void k_nchw_to_nhwc(St st, const float* in, float* out, int N, int C, int H, int W);
+void k_nhwc_to_nchw(St st, const float* in, float* out, int N, int C, int H, int W);
+// BN forward statistics.  partials: bn_partial_rows(P,C) x 2C doubles; sums[2C] = (sum x, sum x^2).
+int  bn_partial_rows(int64_t P, int C);
+void k_bn_stats(St st, const float* x, int64_t P, int C, double* partials, double* sums);
+void k_bn_finalize(St st, const double* sums, int C, double n_total, float eps, float momentum,
+                   float* save_mean, float* save_invstd, float* running_mean, float* running_var);
+void k_bn_apply_act(St st, const float* x, float* y, int64_t P, int C, const float* gamma, const float* beta,
+                    const float* mean, const float* invstd, int act, float negval);
+void k_act(St st, const float* x, float* y, int64_t count, int act, float negval);
+void k_act_bwd(St st, const float* y, const float* dy, float* dx, int64_t count, int act, float negval);
+// BN backward: g = dy*act'(y) written to g_out (y may be null when act == ACT_NONE);
+// sums[2C] = (sum g, sum g*xhat)
+void k_bn_bwd_reduce(St st, const float* dy, const float* y, const float* x, float* g_out, int64_t P, int C,
+                     const float* mean, const float* invstd, int act, float negval,
+                     double* partials, double* sums);
+// dbeta += sums_local[0..C), dgamma += sums_local[C..2C)   (either pointer may be null)
+void k_bn_bwd_param(St st, const double* sums_local, int C, float* dgamma, float* dbeta);
+void k_bn_bwd_apply(St st, const float* g, const float* x, float* dx, int64_t P, int C, const float* gamma,
+                    const float* mean, const float* invstd, const double* sums_total, double n_total);
+void k_upnearest_fwd(St st, const float* x, float* y, int N, int H, int W, int C, int scale);
+void k_upnearest_bwd(St st, const float* dy, float* dx, int N, int H, int W, int C, int scale);
+void k_avgpool2(St st, const float* x, float* y, int N, int H, int W, int C);
+// criterion forward+backward fused.  label_vec (per-sample, `per` outputs each) or constant.
+// loss_out[0] = sum/n_total ; dx = dL/dx with 1/n_total scaling.  dx may be null.
+void k_loss(St st, int kind, const float* x, int64_t count, const float* label_vec, int64_t per, float label_const,
+            double n_total, float* loss_out, float* dx);
+void k_pixel_mse(St st, const float* real, const float* fake, float* out, int n, int64_t per_sample, float div);
+// Adam: step size is read from dev_step[0] (written by k_adam_prep) so the launch is graph-replayable.
+void k_adam_prep(St st, int64_t* dev_t, float* dev_step, double lr, double beta1, double beta2);
+void k_adam(St st, float* p, const float* g, float* m, float* v, int64_t count, const float* dev_step,
+            double beta1, double beta2, double eps);
+void k_fill(St st, float* p, int64_t count, float v);
+void k_scale(St st, float* p, int64_t count, float s);
+void k_flush(St st, float* buf, int64_t count);
+
+// ---- kernels_simt.cu : strict fp32 FFMA convolutions -----------------------------------------
+// Packed weights for the tap-list kernels: Wp[t][a][b] = master[a*sa + b*sb + tapidx[t]]
+void k_pack_taps(St st, const float* master, float* wp, int ntaps, const int* tapidx_dev, int A, int B,
+                 int64_t sa, int64_t sb);
+void k_tapconv_simt(St st, const TapGeom& g, const float* in, const float* wp, float* out, int act, float negval);
+// wgrad: accumulates into grad_master (+=) through a deterministic split-K reduction in `scratch`
+size_t wgrad_simt_scratch_bytes(const WgradGeom& g);
+void k_wgrad_simt(St st, const WgradGeom& g, const float* P, const float* Q, float* grad_master,
+                  float* scratch, size_t scratch_bytes);
+
+// ---- kernels_tc.cu : tcgen05 / TMA / TMEM implicit-GEMM convolutions (FAST_TF32) --------------
+bool tc_init(std::string* err);                       // resolves cuTensorMapEncodeTiled
+bool tc_tapconv_supported(const TapGeom& g);
+// K-major packed weights for the tensor-core path: Bp[b (N, padded)][t*A + a] (tf32-rounded)
+size_t tc_packed_elems(int ntaps, int A, int B);
+void k_pack_taps_tc(St st, const float* master, float* bp, int ntaps, const int* tapidx_dev, int A, int B,
+                    int64_t sa, int64_t sb);
+// returns false (with err) if the launch could not be configured
+bool k_tapconv_tc(St st, const TapGeom& g, const float* in, const float* bp, float* out, int act, float negval,
+                  std::string* err);

@@ -1,0 +1,1322 @@
+// dcgansr.cu -- context, convolution plans, the nn.Sequential executor, the fused training step
+// and the C ABI of libdcgansr.so (include/dcgansr.h).
+//
+// What is restated from the reference (file:line under /root/reference):
+//   netG / netD builders        train.lua:97-139, train-gray.lua:102-137, train-gray-patch.lua:54-109
+//   Module:getParameters order  train.lua:202-203
+//   fDx / fGx / loop order      train.lua:208-283   (stale-activation G step, two D passes per step)
+//   optim.adam                  train.lua:280,283
+// Design: activations NHWC fp32 in HBM, parameters / gradients / Adam state in one flat master
+// vector per net in the Torch7 layout (export/import is a memcpy, Adam is one fused pass), packed
+// per-tap weight copies refreshed after every update.  One CUDA stream per context; no host
+// synchronisation inside a step unless the caller asks for the loss values.
+#pragma GCC visibility push(default)
+#include "../../include/dcgansr.h"
+#pragma GCC visibility pop
+#include "common.h"
+
+#include <dlfcn.h>
+#include <nccl.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------
+static thread_local std::string t_err;
+
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+};
+
+struct GraphEntry {
+  cudaGraphExec_t exec = nullptr;
+  const void *G = nullptr, *D = nullptr, *real = nullptr;
+  int batch = 0;
+  dcgansr_step_cfg cfg;
+  int64_t launches = 0;
+};
+
+struct dcgansr_ctx {
+  dcgansr_cfg cfg;
+  cudaStream_t stream = nullptr, comm_stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_c2m = nullptr, ev_m2c = nullptr;
+  int64_t launches = 0;
+  std::string err;
+  float* flush_buf = nullptr;
+  int64_t flush_count = 0;
+  float* d_losses = nullptr;   // errD_real, errD_fake, errG, spare
+  float* h_losses = nullptr;   // pinned mirror
+  std::vector<float*> slots;   // staged batches (NHWC)
+  std::vector<size_t> slot_bytes;
+  float* tmp = nullptr;        // device scratch for layout import/export
+  size_t tmp_bytes = 0;
+  float* label_vec = nullptr;  // per-sample pixel MSE (train.lua:237-245)
+  size_t label_cap = 0;
+  float* lr_buf = nullptr;     // 2x2 box down-sampled batch (train.lua:225-230)
+  size_t lr_cap = 0;
+  NcclApi nccl;
+  ncclComm_t comm = nullptr;
+  // CUDA graphs of the step (cfg.use_graph), one per (nets, staged batch, batch size, step cfg)
+  std::vector<GraphEntry> graphs;
+  Prof prof;
+  St st() { return St{stream, &launches, &prof}; }
+  int world() const { return cfg.world_size > 1 && comm ? cfg.world_size : 1; }
+};
+
+static int fail(dcgansr_ctx* ctx, int code, const std::string& msg) {
+  t_err = msg;
+  if (ctx) ctx->err = msg;
+  return code;
+}
+#define CK(ctx, call)                                                                                     \
+  do {                                                                                                    \
+    cudaError_t e_ = (call);                                                                              \
+    if (e_ != cudaSuccess)                                                                                \
+      return fail(ctx, DCGANSR_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+  } while (0)
+#define CKLAST(ctx)                                                                                       \
+  do {                                                                                                    \
+    cudaError_t e_ = cudaGetLastError();                                                                  \
+    if (e_ != cudaSuccess)                                                                                \
+      return fail(ctx, DCGANSR_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_));        \
+  } while (0)
+#define CKN(ctx, call)                                                                                    \
+  do {                                                                                                    \
+    ncclResult_t r_ = (call);                                                                             \
+    if (r_ != ncclSuccess)                                                                                \
+      return fail(ctx, DCGANSR_ERR_NCCL, std::string(#call) + ": " + (ctx)->nccl.GetErrorString(r_));     \
+  } while (0)
+
+struct Arena {
+  std::vector<void*> ptrs;
+  ~Arena() { for (void* p : ptrs) cudaFree(p); }
+  float* f(int64_t n) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, (size_t)std::max<int64_t>(n, 4) * sizeof(float)) != cudaSuccess) return nullptr;
+    ptrs.push_back(p);
+    return (float*)p;
+  }
+  void* bytes(size_t n) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, std::max<size_t>(n, 16)) != cudaSuccess) return nullptr;
+    ptrs.push_back(p);
+    return p;
+  }
+};
+
+static int ensure(dcgansr_ctx* ctx, float** buf, size_t* cap, size_t bytes) {
+  if (*cap >= bytes) return 0;
+  if (*buf) { cudaStreamSynchronize(ctx->stream); cudaFree(*buf); *buf = nullptr; *cap = 0; }
+  CK(ctx, cudaMalloc((void**)buf, bytes));
+  *cap = bytes;
+  return 0;
+}
+
+// host NCHW -> device NHWC (dst); uses ctx->tmp for the transpose source
+static int upload_nchw(dcgansr_ctx* ctx, const float* host, int N, int C, int H, int W, float* dst) {
+  size_t bytes = (size_t)N * C * H * W * sizeof(float);
+  if (bytes == 0) return 0;
+  if (C == 1 || H * W == 1) {
+    CK(ctx, cudaMemcpyAsync(dst, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return 0;
+  }
+  if (int rc = ensure(ctx, &ctx->tmp, &ctx->tmp_bytes, bytes)) return rc;
+  CK(ctx, cudaMemcpyAsync(ctx->tmp, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  k_nchw_to_nhwc(ctx->st(), ctx->tmp, dst, N, C, H, W);
+  return 0;
+}
+// device NHWC (src) -> host NCHW; synchronises the stream
+static int download_nchw(dcgansr_ctx* ctx, const float* src, int N, int C, int H, int W, float* host) {
+  size_t bytes = (size_t)N * C * H * W * sizeof(float);
+  if (bytes == 0) return 0;
+  if (C == 1 || H * W == 1) {
+    CK(ctx, cudaMemcpyAsync(host, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  } else {
+    if (int rc = ensure(ctx, &ctx->tmp, &ctx->tmp_bytes, bytes)) return rc;
+    k_nhwc_to_nchw(ctx->st(), src, ctx->tmp, N, C, H, W);
+    CK(ctx, cudaMemcpyAsync(host, ctx->tmp, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  CKLAST(ctx);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// convolution plan: geometry classes + packed weights of one conv / full-conv module
+// ------------------------------------------------------------------------------------------
+struct TapClass {
+  TapGeom g;
+  std::vector<int> tapidx;
+  int* tapidx_dev = nullptr;
+  float* wp = nullptr;       // SIMT pack  [t][A][B]
+  float* bp = nullptr;       // tensor-core pack (K-major, tf32)
+  int A = 0, B = 0;
+  int64_t sa = 0, sb = 0;
+};
+
+struct ConvPlan {
+  bool full = false;
+  int cin = 0, cout = 0, k = 0, s = 1, p = 0, adj = 0;
+  int Hin = 0, Win = 0, Hout = 0, Wout = 0, T = 0;
+  std::vector<TapClass> fwd, dgrad;
+  WgradGeom wg;
+  bool device = false;
+
+  int64_t weight_count() const { return (int64_t)cin * cout * k * k; }
+
+  // classes of the "transposed" form: out[gy*s+ry] = sum over ky with (ry+p-ky) % s == 0 of in[gy + (ry+p-ky)/s]
+  static void sub_pixel_classes(std::vector<TapClass>& v, int k, int s, int p, int Hi, int Wi, int Ci, int Ho, int Wo, int Co) {
+    for (int ry = 0; ry < s; ++ry)
+      for (int rx = 0; rx < s; ++rx) {
+        TapClass c;
+        memset(&c.g, 0, sizeof(c.g));
+        c.g.Hi = Hi; c.g.Wi = Wi; c.g.Ci = Ci; c.g.Ho = Ho; c.g.Wo = Wo; c.g.Co = Co;
+        c.g.si = 1; c.g.so = s; c.g.oy0 = ry; c.g.ox0 = rx;
+        c.g.Hg = Ho > ry ? (Ho - ry + s - 1) / s : 0;
+        c.g.Wg = Wo > rx ? (Wo - rx + s - 1) / s : 0;
+        int nt = 0;
+        for (int ky = 0; ky < k; ++ky) {
+          int vy = ry + p - ky;
+          if (((vy % s) + s) % s != 0) continue;
+          for (int kx = 0; kx < k; ++kx) {
+            int vx = rx + p - kx;
+            if (((vx % s) + s) % s != 0) continue;
+            c.g.dy[nt] = vy / s; c.g.dx[nt] = vx / s;     // exact (divisible)
+            c.tapidx.push_back(ky * k + kx);
+            ++nt;
+          }
+        }
+        c.g.ntaps = nt;
+        v.push_back(c);
+      }
+  }
+  static void direct_class(std::vector<TapClass>& v, int k, int s, int p, int Hi, int Wi, int Ci, int Ho, int Wo, int Co) {
+    TapClass c;
+    memset(&c.g, 0, sizeof(c.g));
+    c.g.Hi = Hi; c.g.Wi = Wi; c.g.Ci = Ci; c.g.Ho = Ho; c.g.Wo = Wo; c.g.Co = Co;
+    c.g.si = s; c.g.so = 1; c.g.oy0 = 0; c.g.ox0 = 0; c.g.Hg = Ho; c.g.Wg = Wo;
+    int nt = 0;
+    for (int ky = 0; ky < k; ++ky)
+      for (int kx = 0; kx < k; ++kx) {
+        c.g.dy[nt] = ky - p; c.g.dx[nt] = kx - p;
+        c.tapidx.push_back(ky * k + kx);
+        ++nt;
+      }
+    c.g.ntaps = nt;
+    v.push_back(c);
+  }
+
+  // returns "" or an error text
+  std::string build(bool full_, int cin_, int cout_, int k_, int s_, int p_, int adj_, int Hin_, int Win_) {
+    full = full_; cin = cin_; cout = cout_; k = k_; s = s_; p = p_; adj = adj_; Hin = Hin_; Win = Win_;
+    T = k * k;
+    if (cin <= 0 || cout <= 0 || k <= 0 || s <= 0 || p < 0) return "bad convolution parameters";
+    if (T > DSR_MAX_TAPS) return "kernel larger than 5x5 is not supported";
+    if (full) { Hout = (Hin - 1) * s - 2 * p + k + adj; Wout = (Win - 1) * s - 2 * p + k + adj; }
+    else {
+      if (Hin + 2 * p < k || Win + 2 * p < k) return "input smaller than kernel";
+      Hout = (Hin + 2 * p - k) / s + 1; Wout = (Win + 2 * p - k) / s + 1;
+    }
+    if (Hout <= 0 || Wout <= 0) return "empty convolution output";
+    const int64_t Ti = T;
+    if (!full) {
+      direct_class(fwd, k, s, p, Hin, Win, cin, Hout, Wout, cout);
+      for (auto& c : fwd) { c.A = cin; c.B = cout; c.sa = Ti; c.sb = (int64_t)cin * Ti; }       // w[co][ci][t]
+      sub_pixel_classes(dgrad, k, s, p, Hout, Wout, cout, Hin, Win, cin);
+      for (auto& c : dgrad) { c.A = cout; c.B = cin; c.sa = (int64_t)cin * Ti; c.sb = Ti; }
+      memset(&wg, 0, sizeof(wg));
+      wg.Hp = Hout; wg.Wp = Wout; wg.Cp = cout; wg.Hq = Hin; wg.Wq = Win; wg.Cq = cin; wg.s = s; wg.ntaps = T;
+    } else {
+      sub_pixel_classes(fwd, k, s, p, Hin, Win, cin, Hout, Wout, cout);
+      for (auto& c : fwd) { c.A = cin; c.B = cout; c.sa = (int64_t)cout * Ti; c.sb = Ti; }     // w[ci][co][t]
+      direct_class(dgrad, k, s, p, Hout, Wout, cout, Hin, Win, cin);
+      for (auto& c : dgrad) { c.A = cout; c.B = cin; c.sa = Ti; c.sb = (int64_t)cout * Ti; }
+      memset(&wg, 0, sizeof(wg));
+      wg.Hp = Hin; wg.Wp = Win; wg.Cp = cin; wg.Hq = Hout; wg.Wq = Wout; wg.Cq = cout; wg.s = s; wg.ntaps = T;
+    }
+    for (int ky = 0; ky < k; ++ky)
+      for (int kx = 0; kx < k; ++kx) { wg.dy[ky * k + kx] = ky - p; wg.dx[ky * k + kx] = kx - p; }
+    return "";
+  }
+
+  int alloc_device(dcgansr_ctx* ctx) {
+    for (auto* v : {&fwd, &dgrad})
+      for (auto& c : *v) {
+        size_t n = std::max<size_t>(c.tapidx.size(), 1);
+        CK(ctx, cudaMalloc((void**)&c.tapidx_dev, n * sizeof(int)));
+        if (!c.tapidx.empty())
+          CK(ctx, cudaMemcpy(c.tapidx_dev, c.tapidx.data(), c.tapidx.size() * sizeof(int), cudaMemcpyHostToDevice));
+        CK(ctx, cudaMalloc((void**)&c.wp, std::max<size_t>((size_t)c.g.ntaps * c.A * c.B, 4) * sizeof(float)));
+      }
+    device = true;
+    return 0;
+  }
+  void free_device() {
+    for (auto* v : {&fwd, &dgrad})
+      for (auto& c : *v) {
+        if (c.tapidx_dev) cudaFree(c.tapidx_dev);
+        if (c.wp) cudaFree(c.wp);
+        if (c.bp) cudaFree(c.bp);
+        c.tapidx_dev = nullptr; c.wp = nullptr; c.bp = nullptr;
+      }
+    device = false;
+  }
+  void pack(St st, const float* master) {
+    for (auto* v : {&fwd, &dgrad})
+      for (auto& c : *v)
+        if (c.g.ntaps > 0) k_pack_taps(st, master, c.wp, c.g.ntaps, c.tapidx_dev, c.A, c.B, c.sa, c.sb);
+  }
+  static void run_classes(dcgansr_ctx* ctx, std::vector<TapClass>& v, const float* in, float* out, int N, int act, float neg) {
+    for (auto& c : v) {
+      if (c.g.Hg <= 0 || c.g.Wg <= 0) continue;
+      TapGeom g = c.g;
+      g.N = N;
+      k_tapconv_simt(ctx->st(), g, in, c.wp, out, act, neg);
+    }
+  }
+  void forward(dcgansr_ctx* ctx, const float* in, float* out, int N, int act, float neg) { run_classes(ctx, fwd, in, out, N, act, neg); }
+  void dgrad_run(dcgansr_ctx* ctx, const float* dy, float* dx, int N) { run_classes(ctx, dgrad, dy, dx, N, ACT_NONE, 0.f); }
+  size_t wscratch_bytes(int N) const {
+    WgradGeom g = wg;
+    g.N = N;
+    return wgrad_simt_scratch_bytes(g);
+  }
+  // x: module input, dy: gradient w.r.t. module output
+  void wgrad_run(dcgansr_ctx* ctx, const float* x, const float* dy, float* grad_master, int N, float* scratch, size_t scratch_bytes) {
+    WgradGeom g = wg;
+    g.N = N;
+    if (!full) k_wgrad_simt(ctx->st(), g, dy, x, grad_master, scratch, scratch_bytes);
+    else k_wgrad_simt(ctx->st(), g, x, dy, grad_master, scratch, scratch_bytes);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// nn.Sequential
+// ------------------------------------------------------------------------------------------
+struct Mod {
+  int kind = 0;
+  dcgansr_layer L;
+  int cin = 0, hin = 0, win = 0, cout = 0, hout = 0, wout = 0;
+  ConvPlan* conv = nullptr;
+  int64_t p_off = -1, p_cnt = 0;
+  int64_t bn_off = -1;
+  float* out = nullptr;
+  bool owns_out = false;
+  int fused_act = ACT_NONE;      // activation fused into this CONV / BN module
+  float fused_neg = 0.f;
+  bool fused_into_prev = false;  // ACT module executed by its producer
+  int act = ACT_NONE;            // ACT modules: own kind
+  float *save_mean = nullptr, *save_invstd = nullptr;
+};
+
+struct dcgansr_net {
+  dcgansr_ctx* ctx = nullptr;
+  std::vector<Mod> mods;
+  int in_c = 0, in_h = 0, in_w = 0, max_batch = 0;
+  int64_t nparams = 0, nbn = 0;
+  float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+  int64_t* adam_t = nullptr;
+  float* adam_step = nullptr;
+  float *bn_rmean = nullptr, *bn_rvar = nullptr, *bn_save = nullptr;
+  float* in_buf = nullptr;
+  float* gbuf[2] = {nullptr, nullptr};
+  int64_t gelems = 0;
+  double *bn_partials = nullptr, *bn_sums = nullptr, *bn_sums_total = nullptr;
+  float* wscratch = nullptr;
+  size_t wscratch_bytes = 0;
+  int first_param_mod = -1;
+  int last_batch = 0;
+  const float* last_out = nullptr;
+  int out_c = 0, out_h = 0, out_w = 0;
+  std::vector<std::pair<int64_t, int64_t>> buckets;   // gradient buckets (offset, count), forward order
+
+  float* own(const float* cur) { return (cur == gbuf[0] || cur == gbuf[1]) ? const_cast<float*>(cur) : gbuf[0]; }
+  float* other(const float* cur) { return cur == gbuf[0] ? gbuf[1] : gbuf[0]; }
+};
+
+static int act_of_kind(int kind) {
+  switch (kind) {
+    case DCGANSR_RELU: return ACT_RELU;
+    case DCGANSR_LRELU: return ACT_LRELU;
+    case DCGANSR_TANH: return ACT_TANH;
+    case DCGANSR_SIGMOID: return ACT_SIGMOID;
+    default: return ACT_NONE;
+  }
+}
+
+static int nccl_allreduce(dcgansr_ctx* ctx, void* buf, size_t count, ncclDataType_t dt, cudaStream_t s) {
+  if (ctx->world() <= 1) return 0;
+  CKN(ctx, ctx->nccl.AllReduce(buf, buf, count, dt, ncclSum, ctx->comm, s));
+  ++ctx->launches;
+  return 0;
+}
+
+static void net_pack_all(dcgansr_net* net) {
+  for (auto& m : net->mods)
+    if (m.conv) m.conv->pack(net->ctx->st(), net->params + m.p_off);
+}
+
+// forward on device buffers (in: NHWC).  Caches every module output: last forward wins.
+static int net_forward_dev(dcgansr_net* net, const float* in, int B) {
+  dcgansr_ctx* ctx = net->ctx;
+  St st = ctx->st();
+  const float* cur = in;
+  const bool sync = ctx->cfg.sync_bn && ctx->world() > 1;
+  for (auto& m : net->mods) {
+    switch (m.kind) {
+      case DCGANSR_UPNEAREST:
+        k_upnearest_fwd(st, cur, m.out, B, m.hin, m.win, m.cin, m.L.scale);
+        cur = m.out;
+        break;
+      case DCGANSR_CONV:
+      case DCGANSR_FULLCONV:
+        m.conv->forward(ctx, cur, m.out, B, m.fused_act, m.fused_neg);
+        cur = m.out;
+        break;
+      case DCGANSR_BN: {
+        int64_t P = (int64_t)B * m.hin * m.win;
+        int C = m.cin;
+        k_bn_stats(st, cur, P, C, net->bn_partials, net->bn_sums);
+        double n_total = (double)P;
+        if (sync) {
+          if (int rc = nccl_allreduce(ctx, net->bn_sums, 2 * C, ncclDouble, ctx->stream)) return rc;
+          n_total *= ctx->world();
+        }
+        k_bn_finalize(st, net->bn_sums, C, n_total, m.L.eps, m.L.momentum, m.save_mean, m.save_invstd,
+                      net->bn_rmean + m.bn_off, net->bn_rvar + m.bn_off);
+        k_bn_apply_act(st, cur, m.out, P, C, net->params + m.p_off, net->params + m.p_off + C, m.save_mean, m.save_invstd,
+                       m.fused_act, m.fused_neg);
+        cur = m.out;
+        break;
+      }
+      case DCGANSR_RELU: case DCGANSR_LRELU: case DCGANSR_TANH: case DCGANSR_SIGMOID:
+        if (!m.fused_into_prev) {
+          k_act(st, cur, m.out, (int64_t)B * m.cin * m.hin * m.win, m.act, m.L.negval);
+          cur = m.out;
+        }
+        break;
+      default: break;   // VIEW
+    }
+  }
+  net->last_out = cur;
+  net->last_batch = B;
+  CKLAST(ctx);
+  return 0;
+}
+
+// backward walk.  acc: accumulate parameter gradients (net:backward) or not (net:updateGradInput).
+// Returns the gradient w.r.t. the net input in *dx_out (nullptr when need_dx is false).
+static int net_backward_dev(dcgansr_net* net, const float* in, const float* dy, int B, bool acc, bool need_dx,
+                            const float** dx_out) {
+  dcgansr_ctx* ctx = net->ctx;
+  St st = ctx->st();
+  const bool sync = ctx->cfg.sync_bn && ctx->world() > 1;
+  const float* cur = dy;
+  if (dx_out) *dx_out = nullptr;
+  for (int i = (int)net->mods.size() - 1; i >= 0; --i) {
+    Mod& m = net->mods[i];
+    const float* inp = i > 0 ? net->mods[i - 1].out : in;
+    switch (m.kind) {
+      case DCGANSR_UPNEAREST: {
+        float* t = net->other(cur);
+        k_upnearest_bwd(st, cur, t, B, m.hin, m.win, m.cin, m.L.scale);
+        cur = t;
+        break;
+      }
+      case DCGANSR_CONV:
+      case DCGANSR_FULLCONV: {
+        if (m.fused_act != ACT_NONE) {
+          float* t = net->own(cur);
+          k_act_bwd(st, m.out, cur, t, (int64_t)B * m.cout * m.hout * m.wout, m.fused_act, m.fused_neg);
+          cur = t;
+        }
+        if (acc) m.conv->wgrad_run(ctx, inp, cur, net->grads + m.p_off, B, net->wscratch, net->wscratch_bytes);
+        if (i == net->first_param_mod && !need_dx) { CKLAST(ctx); return 0; }
+        float* t = net->other(cur);
+        m.conv->dgrad_run(ctx, cur, t, B);
+        cur = t;
+        break;
+      }
+      case DCGANSR_BN: {
+        int64_t P = (int64_t)B * m.hin * m.win;
+        int C = m.cin;
+        float* g = net->own(cur);
+        k_bn_bwd_reduce(st, cur, m.fused_act != ACT_NONE ? m.out : nullptr, inp, g, P, C, m.save_mean, m.save_invstd,
+                        m.fused_act, m.fused_neg, net->bn_partials, net->bn_sums);
+        if (acc) k_bn_bwd_param(st, net->bn_sums, C, net->grads + m.p_off, net->grads + m.p_off + C);
+        const double* tot = net->bn_sums;
+        double n_total = (double)P;
+        if (sync) {
+          CK(ctx, cudaMemcpyAsync(net->bn_sums_total, net->bn_sums, 2 * C * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+          if (int rc = nccl_allreduce(ctx, net->bn_sums_total, 2 * C, ncclDouble, ctx->stream)) return rc;
+          tot = net->bn_sums_total;
+          n_total *= ctx->world();
+        }
+        k_bn_bwd_apply(st, g, inp, g, P, C, net->params + m.p_off, m.save_mean, m.save_invstd, tot, n_total);
+        cur = g;
+        break;
+      }
+      case DCGANSR_RELU: case DCGANSR_LRELU: case DCGANSR_TANH: case DCGANSR_SIGMOID:
+        if (!m.fused_into_prev) {
+          float* t = net->own(cur);
+          k_act_bwd(st, m.out, cur, t, (int64_t)B * m.cin * m.hin * m.win, m.act, m.L.negval);
+          cur = t;
+        }
+        break;
+      default: break;   // VIEW
+    }
+  }
+  if (dx_out) *dx_out = cur;
+  CKLAST(ctx);
+  return 0;
+}
+
+static int net_adam_dev(dcgansr_net* net, double lr, double b1, double b2, double eps) {
+  dcgansr_ctx* ctx = net->ctx;
+  St st = ctx->st();
+  k_adam_prep(st, net->adam_t, net->adam_step, lr, b1, b2);
+  k_adam(st, net->params, net->grads, net->adam_m, net->adam_v, net->nparams, net->adam_step, b1, b2, eps);
+  net_pack_all(net);
+  CKLAST(ctx);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// C ABI: lifecycle
+// ------------------------------------------------------------------------------------------
+#pragma GCC visibility push(default)
+extern "C" {
+
+int dcgansr_version(void) { return 100; }
+
+const char* dcgansr_last_error(dcgansr_ctx* ctx) { return ctx ? ctx->err.c_str() : t_err.c_str(); }
+
+int dcgansr_ctx_create(const dcgansr_cfg* cfg, dcgansr_ctx** out) {
+  if (!cfg || !out) return fail(nullptr, DCGANSR_ERR_INVALID, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, DCGANSR_ERR_CUDA, std::string("no CUDA device: libdcgansr has no CPU fallback (") +
+                                               cudaGetErrorString(e) + ")");
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, DCGANSR_ERR_INVALID, "bad device ordinal");
+  if (cfg->precision != DCGANSR_STRICT_FP32 && cfg->precision != DCGANSR_FAST_TF32)
+    return fail(nullptr, DCGANSR_ERR_INVALID, "bad precision mode");
+  CK(nullptr, cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(nullptr, cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10)
+    return fail(nullptr, DCGANSR_ERR_UNSUPPORTED, std::string("libdcgansr is built for sm_100a only; device is ") + prop.name);
+  dcgansr_ctx* ctx = new dcgansr_ctx();
+  ctx->cfg = *cfg;
+  if (ctx->cfg.world_size < 1) ctx->cfg.world_size = 1;
+  CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CK(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+  CK(ctx, cudaEventCreate(&ctx->ev0));
+  CK(ctx, cudaEventCreate(&ctx->ev1));
+  CK(ctx, cudaEventCreateWithFlags(&ctx->ev_c2m, cudaEventDisableTiming));
+  CK(ctx, cudaEventCreateWithFlags(&ctx->ev_m2c, cudaEventDisableTiming));
+  CK(ctx, cudaMalloc((void**)&ctx->d_losses, 4 * sizeof(float)));
+  CK(ctx, cudaMemset(ctx->d_losses, 0, 4 * sizeof(float)));
+  CK(ctx, cudaMallocHost((void**)&ctx->h_losses, 4 * sizeof(float)));
+  *out = ctx;
+  return 0;
+}
+
+void dcgansr_ctx_destroy(dcgansr_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->cfg.device);
+  cudaDeviceSynchronize();
+  for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+  if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
+  for (float* p : ctx->slots) if (p) cudaFree(p);
+  if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+  if (ctx->tmp) cudaFree(ctx->tmp);
+  if (ctx->label_vec) cudaFree(ctx->label_vec);
+  if (ctx->lr_buf) cudaFree(ctx->lr_buf);
+  if (ctx->d_losses) cudaFree(ctx->d_losses);
+  if (ctx->h_losses) cudaFreeHost(ctx->h_losses);
+  for (cudaEvent_t e : ctx->prof.pool) cudaEventDestroy(e);
+  if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+  if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->ev_c2m) cudaEventDestroy(ctx->ev_c2m);
+  if (ctx->ev_m2c) cudaEventDestroy(ctx->ev_m2c);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
+  delete ctx;
+}
+
+int dcgansr_synchronize(dcgansr_ctx* ctx) {
+  if (!ctx) return fail(nullptr, DCGANSR_ERR_INVALID, "null ctx");
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  CKLAST(ctx);
+  return 0;
+}
+int dcgansr_timer_begin(dcgansr_ctx* ctx) {
+  if (!ctx) return fail(nullptr, DCGANSR_ERR_INVALID, "null ctx");
+  CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+  return 0;
+}
+int dcgansr_timer_end(dcgansr_ctx* ctx, float* ms_out) {
+  if (!ctx || !ms_out) return fail(ctx, DCGANSR_ERR_INVALID, "null argument");
+  CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(ctx, cudaEventSynchronize(ctx->ev1));
+  CK(ctx, cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
+  return 0;
+}
+int dcgansr_launch_count(dcgansr_ctx* ctx, int64_t* out) {
+  if (!ctx || !out) return fail(ctx, DCGANSR_ERR_INVALID, "null argument");
+  *out = ctx->launches;
+  return 0;
+}
+int dcgansr_flush_l2(dcgansr_ctx* ctx) {
+  if (!ctx) return fail(nullptr, DCGANSR_ERR_INVALID, "null ctx");
+  if (!ctx->flush_buf) {
+    ctx->flush_count = (int64_t)64 << 20;   // 256 MiB of floats > 126 MB L2
+    CK(ctx, cudaMalloc((void**)&ctx->flush_buf, ctx->flush_count * sizeof(float)));
+  }
+  k_flush(ctx->st(), ctx->flush_buf, ctx->flush_count);
+  CKLAST(ctx);
+  return 0;
+}
+
+// ---- per-launch event profiler (bench.py roofline leg) ------------------------------------------
+int dcgansr_profile_begin(dcgansr_ctx* ctx) {
+  if (!ctx) return fail(nullptr, DCGANSR_ERR_INVALID, "null ctx");
+  CK(ctx, cudaSetDevice(ctx->cfg.device));
+  Prof& p = ctx->prof;
+  if (p.pool.empty()) {
+    cudaEvent_t e;
+    CK(ctx, cudaEventCreate(&e));
+    p.pool.push_back(e);
+  }
+  p.recs.clear();
+  CK(ctx, cudaEventRecord(p.pool[0], ctx->stream));
+  p.on = true;
+  return 0;
+}
+int dcgansr_profile_end(dcgansr_ctx* ctx, char* json_out, int64_t cap) {
+  if (!ctx || !json_out || cap < 64) return fail(ctx, DCGANSR_ERR_INVALID, "bad argument");
+  Prof& p = ctx->prof;
+  p.on = false;
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  struct Agg { std::string name; double work; int kind; int64_t n; double ms; };
+  std::vector<Agg> aggs;
+  for (size_t i = 0; i < p.recs.size(); ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, p.pool[i], p.pool[i + 1]) != cudaSuccess) continue;
+    const ProfRec& r = p.recs[i];
+    Agg* a = nullptr;
+    for (auto& x : aggs)
+      if (x.name == r.name && x.work == r.work && x.kind == r.kind) { a = &x; break; }
+    if (!a) { aggs.push_back(Agg{r.name, r.work, r.kind, 0, 0.0}); a = &aggs.back(); }
+    a->n += 1; a->ms += ms;
+  }
+  std::sort(aggs.begin(), aggs.end(), [](const Agg& a, const Agg& b) { return a.ms > b.ms; });
+  std::string js = "[";
+  char buf[256];
+  for (size_t i = 0; i < aggs.size(); ++i) {
+    snprintf(buf, sizeof(buf), "%s{\"name\":\"%s\",\"work\":%.6e,\"kind\":\"%s\",\"launches\":%lld,\"ms\":%.6f}",
+             i ? "," : "", aggs[i].name.c_str(), aggs[i].work, aggs[i].kind == WORK_FLOPS ? "flops" : "bytes",
+             (long long)aggs[i].n, aggs[i].ms);
+    if ((int64_t)(js.size() + strlen(buf) + 2) >= cap) break;
+    js += buf;
+  }
+  js += "]";
+  memcpy(json_out, js.c_str(), js.size() + 1);
+  p.recs.clear();
+  return 0;
+}
+
+// ---- communicator ---------------------------------------------------------------------------
+static int nccl_load(dcgansr_ctx* ctx) {
+  if (ctx->nccl.h) return 0;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) return fail(ctx, DCGANSR_ERR_NCCL, std::string("cannot load libnccl: ") + dlerror());
+  NcclApi& a = ctx->nccl;
+  a.h = h;
+  a.GetUniqueId = (decltype(a.GetUniqueId))dlsym(h, "ncclGetUniqueId");
+  a.CommInitRank = (decltype(a.CommInitRank))dlsym(h, "ncclCommInitRank");
+  a.AllReduce = (decltype(a.AllReduce))dlsym(h, "ncclAllReduce");
+  a.CommDestroy = (decltype(a.CommDestroy))dlsym(h, "ncclCommDestroy");
+  a.GetErrorString = (decltype(a.GetErrorString))dlsym(h, "ncclGetErrorString");
+  a.GroupStart = (decltype(a.GroupStart))dlsym(h, "ncclGroupStart");
+  a.GroupEnd = (decltype(a.GroupEnd))dlsym(h, "ncclGroupEnd");
+  if (!a.GetUniqueId || !a.CommInitRank || !a.AllReduce || !a.CommDestroy || !a.GetErrorString)
+    return fail(ctx, DCGANSR_ERR_NCCL, "libnccl lacks required symbols");
+  return 0;
+}
+int dcgansr_comm_get_unique_id(dcgansr_ctx* ctx, void* unique_id_128) {
+  if (!ctx || !unique_id_128) return fail(ctx, DCGANSR_ERR_INVALID, "null argument");
+  if (int rc = nccl_load(ctx)) return rc;
+  ncclUniqueId id;
+  CKN(ctx, ctx->nccl.GetUniqueId(&id));
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(unique_id_128, &id, 128);
+  return 0;
+}
+int dcgansr_comm_init(dcgansr_ctx* ctx, const void* unique_id_128) {
+  if (!ctx || !unique_id_128) return fail(ctx, DCGANSR_ERR_INVALID, "null argument");
+  if (ctx->cfg.world_size <= 1) return 0;
+  if (int rc = nccl_load(ctx)) return rc;
+  CK(ctx, cudaSetDevice(ctx->cfg.device));
+  ncclUniqueId id;
+  memcpy(&id, unique_id_128, 128);
+  CKN(ctx, ctx->nccl.CommInitRank(&ctx->comm, ctx->cfg.world_size, id, ctx->cfg.rank));
+  return 0;
+}
+
+// ---- net description --------------------------------------------------------------------------
+void dcgansr_net_destroy(dcgansr_net* net) {
+  if (!net) return;
+  if (net->ctx) { cudaSetDevice(net->ctx->cfg.device); cudaStreamSynchronize(net->ctx->stream); }
+  for (auto& m : net->mods) {
+    if (m.conv) { m.conv->free_device(); delete m.conv; }
+    if (m.owns_out && m.out) cudaFree(m.out);
+  }
+  void* ptrs[] = {net->params, net->grads, net->adam_m, net->adam_v, net->adam_t, net->adam_step, net->bn_rmean,
+                  net->bn_rvar, net->bn_save, net->in_buf, net->gbuf[0], net->gbuf[1], net->bn_partials, net->bn_sums,
+                  net->bn_sums_total, net->wscratch};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete net;
+}
+
+int dcgansr_net_create(dcgansr_ctx* ctx, const dcgansr_layer* layers, int n_layers, int in_c, int in_h, int in_w,
+                       int max_batch, dcgansr_net** out) {
+  if (!layers || !out || n_layers <= 0 || in_c <= 0 || in_h <= 0 || in_w <= 0 || max_batch <= 0)
+    return fail(ctx, DCGANSR_ERR_INVALID, "bad net description");
+  *out = nullptr;
+  dcgansr_net* net = new dcgansr_net();
+  net->ctx = ctx;
+  net->in_c = in_c; net->in_h = in_h; net->in_w = in_w; net->max_batch = max_batch;
+  int c = in_c, h = in_h, w = in_w;
+  int64_t poff = 0, bnoff = 0;
+  std::string err;
+  for (int i = 0; i < n_layers && err.empty(); ++i) {
+    Mod m;
+    m.kind = layers[i].kind;
+    m.L = layers[i];
+    m.cin = c; m.hin = h; m.win = w;
+    switch (m.kind) {
+      case DCGANSR_CONV:
+      case DCGANSR_FULLCONV: {
+        const dcgansr_layer& L = layers[i];
+        if (L.cin != c) { err = "layer " + std::to_string(i) + ": cin does not match the incoming channel count"; break; }
+        if (L.kh != L.kw || L.sh != L.sw || L.ph != L.pw || L.adjh != L.adjw) { err = "only square kernels / strides / pads"; break; }
+        m.conv = new ConvPlan();
+        err = m.conv->build(m.kind == DCGANSR_FULLCONV, L.cin, L.cout, L.kh, L.sh > 0 ? L.sh : 1, L.ph, L.adjh, h, w);
+        if (!err.empty()) { delete m.conv; m.conv = nullptr; err = "layer " + std::to_string(i) + ": " + err; break; }
+        m.p_off = poff; m.p_cnt = m.conv->weight_count(); poff += m.p_cnt;
+        c = L.cout; h = m.conv->Hout; w = m.conv->Wout;
+        if (net->first_param_mod < 0) net->first_param_mod = i;
+        break;
+      }
+      case DCGANSR_BN:
+        if (layers[i].cout != c) { err = "layer " + std::to_string(i) + ": BN channel count mismatch"; break; }
+        m.p_off = poff; m.p_cnt = 2 * (int64_t)c; poff += m.p_cnt;
+        m.bn_off = bnoff; bnoff += c;
+        if (m.L.eps <= 0.f) m.L.eps = 1e-5f;
+        if (net->first_param_mod < 0) net->first_param_mod = i;
+        break;
+      case DCGANSR_RELU: case DCGANSR_LRELU: case DCGANSR_TANH: case DCGANSR_SIGMOID:
+        m.act = act_of_kind(m.kind);
+        break;
+      case DCGANSR_UPNEAREST:
+        if (m.L.scale <= 0) m.L.scale = 2;
+        h *= m.L.scale; w *= m.L.scale;
+        break;
+      case DCGANSR_VIEW: break;
+      default: err = "layer " + std::to_string(i) + ": unknown kind";
+    }
+    m.cout = c; m.hout = h; m.wout = w;
+    net->mods.push_back(m);
+  }
+  if (!err.empty()) { dcgansr_net_destroy(net); return fail(ctx, DCGANSR_ERR_INVALID, err); }
+  net->nparams = poff; net->nbn = bnoff;
+  net->out_c = c; net->out_h = h; net->out_w = w;
+  // activation fusion: an ACT right after CONV / BN runs in that module's epilogue
+  for (size_t i = 1; i < net->mods.size(); ++i) {
+    Mod& m = net->mods[i];
+    Mod& pm = net->mods[i - 1];
+    if (m.act != ACT_NONE && (pm.kind == DCGANSR_CONV || pm.kind == DCGANSR_FULLCONV || pm.kind == DCGANSR_BN) &&
+        pm.fused_act == ACT_NONE) {
+      pm.fused_act = m.act; pm.fused_neg = m.L.negval; m.fused_into_prev = true;
+    }
+  }
+  // gradient buckets: [conv, following BN ...) ranges
+  {
+    int64_t start = 0;
+    bool seen = false;
+    for (auto& m : net->mods) {
+      if (m.conv) {
+        if (seen) net->buckets.push_back({start, m.p_off - start});
+        start = m.p_off; seen = true;
+      }
+    }
+    if (net->nparams > start || !seen) net->buckets.push_back({start, net->nparams - start});
+  }
+  if (!ctx) { *out = net; return 0; }
+
+  // ---- device memory ----
+  CK(ctx, cudaSetDevice(ctx->cfg.device));
+  int64_t np4 = (net->nparams + 3) / 4 * 4 + 4;
+  auto dalloc = [&](float** p, int64_t n) -> cudaError_t {
+    cudaError_t e = cudaMalloc((void**)p, (size_t)std::max<int64_t>(n, 4) * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(*p, 0, (size_t)std::max<int64_t>(n, 4) * sizeof(float));
+    return e;
+  };
+  cudaError_t e = cudaSuccess;
+  auto A = [&](float** p, int64_t n) { if (e == cudaSuccess) e = dalloc(p, n); };
+  A(&net->params, np4); A(&net->grads, np4); A(&net->adam_m, np4); A(&net->adam_v, np4);
+  A(&net->adam_step, 4);
+  A(&net->bn_rmean, net->nbn); A(&net->bn_rvar, net->nbn); A(&net->bn_save, 2 * net->nbn);
+  if (e == cudaSuccess) e = cudaMalloc((void**)&net->adam_t, sizeof(int64_t));
+  if (e == cudaSuccess) e = cudaMemset(net->adam_t, 0, sizeof(int64_t));
+  int64_t B = max_batch;
+  int64_t gmax = B * in_c * in_h * in_w;
+  int maxC = 1;
+  int64_t maxP = 1;
+  size_t wsc = 0;
+  for (auto& m : net->mods) {
+    int64_t oe = B * m.cout * m.hout * m.wout;
+    gmax = std::max(gmax, std::max(oe, B * m.cin * m.hin * m.win));
+    bool needs_buf = m.kind == DCGANSR_CONV || m.kind == DCGANSR_FULLCONV || m.kind == DCGANSR_BN ||
+                     m.kind == DCGANSR_UPNEAREST || (m.act != ACT_NONE && !m.fused_into_prev);
+    if (needs_buf) { A(&m.out, oe); m.owns_out = true; }
+    if (m.kind == DCGANSR_BN) {
+      maxC = std::max(maxC, m.cin);
+      maxP = std::max(maxP, B * m.hin * m.win);
+      m.save_mean = net->bn_save + m.bn_off;
+      m.save_invstd = net->bn_save + net->nbn + m.bn_off;
+    }
+    if (m.conv) {
+      if (e == cudaSuccess && m.conv->alloc_device(ctx) != 0) e = cudaErrorMemoryAllocation;
+      wsc = std::max(wsc, m.conv->wscratch_bytes((int)B));
+    }
+  }
+  // aliases for fused ACT / VIEW modules
+  for (size_t i = 0; i < net->mods.size(); ++i) {
+    Mod& m = net->mods[i];
+    if (!m.owns_out) m.out = i > 0 ? net->mods[i - 1].out : nullptr;
+  }
+  net->gelems = gmax;
+  A(&net->in_buf, B * in_c * in_h * in_w);
+  A(&net->gbuf[0], gmax); A(&net->gbuf[1], gmax);
+  {
+    int64_t rows = 0;
+    for (auto& m : net->mods)
+      if (m.kind == DCGANSR_BN) rows = std::max<int64_t>(rows, (int64_t)bn_partial_rows(B * m.hin * m.win, m.cin) * 2 * m.cin);
+    float* tmpf = nullptr;
+    A(&tmpf, std::max<int64_t>(rows, 2) * 2); net->bn_partials = (double*)tmpf; tmpf = nullptr;
+    A(&tmpf, (int64_t)maxC * 4 + 4); net->bn_sums = (double*)tmpf; tmpf = nullptr;
+    A(&tmpf, (int64_t)maxC * 4 + 4); net->bn_sums_total = (double*)tmpf;
+  }
+  net->wscratch_bytes = wsc;
+  A(&net->wscratch, (int64_t)(wsc / sizeof(float)) + 4);
+  if (e != cudaSuccess) {
+    std::string msg = std::string("device allocation failed: ") + cudaGetErrorString(e);
+    dcgansr_net_destroy(net);
+    return fail(ctx, DCGANSR_ERR_NOMEM, msg);
+  }
+  // BN running_var starts at 1 (Torch7 init)
+  if (net->nbn > 0) k_fill(ctx->st(), net->bn_rvar, net->nbn, 1.f);
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  *out = net;
+  return 0;
+}
+
+int dcgansr_net_out_shape(dcgansr_net* net, int* c, int* h, int* w) {
+  if (!net) return fail(nullptr, DCGANSR_ERR_INVALID, "null net");
+  if (c) *c = net->out_c;
+  if (h) *h = net->out_h;
+  if (w) *w = net->out_w;
+  return 0;
+}
+int dcgansr_net_num_params(dcgansr_net* net, int64_t* out) {
+  if (!net || !out) return fail(nullptr, DCGANSR_ERR_INVALID, "null argument");
+  *out = net->nparams;
+  return 0;
+}
+int dcgansr_net_num_bn_channels(dcgansr_net* net, int64_t* out) {
+  if (!net || !out) return fail(nullptr, DCGANSR_ERR_INVALID, "null argument");
+  *out = net->nbn;
+  return 0;
+}
+
+#define NEED_DEV(net)                                                                             \
+  if (!(net)) return fail(nullptr, DCGANSR_ERR_INVALID, "null net");                               \
+  if (!(net)->ctx) return fail(nullptr, DCGANSR_ERR_INVALID, "plan-only net: no CUDA context");     \
+  dcgansr_ctx* ctx = (net)->ctx;                                                                   \
+  CK(ctx, cudaSetDevice(ctx->cfg.device));
+
+int dcgansr_net_set_params(dcgansr_net* net, const float* host_flat) {
+  NEED_DEV(net);
+  if (!host_flat) return fail(ctx, DCGANSR_ERR_INVALID, "null params");
+  CK(ctx, cudaMemcpyAsync(net->params, host_flat, net->nparams * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  net_pack_all(net);
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  CKLAST(ctx);
+  return 0;
+}
+static int d2h(dcgansr_ctx* ctx, float* host, const float* dev, int64_t n) {
+  if (n <= 0 || !host) return 0;
+  CK(ctx, cudaMemcpyAsync(host, dev, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  CKLAST(ctx);
+  return 0;
+}
+static int h2d(dcgansr_ctx* ctx, float* dev, const float* host, int64_t n) {
+  if (n <= 0 || !host) return 0;
+  CK(ctx, cudaMemcpyAsync(dev, host, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int dcgansr_net_get_params(dcgansr_net* net, float* host_flat) { NEED_DEV(net); return d2h(ctx, host_flat, net->params, net->nparams); }
+int dcgansr_net_get_grads(dcgansr_net* net, float* host_flat) { NEED_DEV(net); return d2h(ctx, host_flat, net->grads, net->nparams); }
+int dcgansr_net_get_bn_running(dcgansr_net* net, float* mean, float* var) {
+  NEED_DEV(net);
+  if (int rc = d2h(ctx, mean, net->bn_rmean, net->nbn)) return rc;
+  return d2h(ctx, var, net->bn_rvar, net->nbn);
+}
+int dcgansr_net_set_bn_running(dcgansr_net* net, const float* mean, const float* var) {
+  NEED_DEV(net);
+  if (int rc = h2d(ctx, net->bn_rmean, mean, net->nbn)) return rc;
+  return h2d(ctx, net->bn_rvar, var, net->nbn);
+}
+int dcgansr_net_get_adam_state(dcgansr_net* net, float* m, float* v, int64_t* t) {
+  NEED_DEV(net);
+  if (int rc = d2h(ctx, m, net->adam_m, net->nparams)) return rc;
+  if (int rc = d2h(ctx, v, net->adam_v, net->nparams)) return rc;
+  if (t) {
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaMemcpy(t, net->adam_t, sizeof(int64_t), cudaMemcpyDeviceToHost));
+  }
+  return 0;
+}
+int dcgansr_net_set_adam_state(dcgansr_net* net, const float* m, const float* v, int64_t t) {
+  NEED_DEV(net);
+  if (int rc = h2d(ctx, net->adam_m, m, net->nparams)) return rc;
+  if (int rc = h2d(ctx, net->adam_v, v, net->nparams)) return rc;
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  CK(ctx, cudaMemcpy(net->adam_t, &t, sizeof(int64_t), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// ---- Torch7-shaped net ops -------------------------------------------------------------------
+int dcgansr_net_forward(dcgansr_net* net, const float* x, int batch, float* y) {
+  NEED_DEV(net);
+  if (!x || batch <= 0 || batch > net->max_batch) return fail(ctx, DCGANSR_ERR_INVALID, "bad batch / null input");
+  if (int rc = upload_nchw(ctx, x, batch, net->in_c, net->in_h, net->in_w, net->in_buf)) return rc;
+  if (int rc = net_forward_dev(net, net->in_buf, batch)) return rc;
+  if (y) return download_nchw(ctx, net->last_out, batch, net->out_c, net->out_h, net->out_w, y);
+  return 0;
+}
+
+static int net_backward_host(dcgansr_net* net, const float* x, const float* dy, int batch, float* dx, bool acc) {
+  NEED_DEV(net);
+  if (!dy || batch <= 0 || batch > net->max_batch) return fail(ctx, DCGANSR_ERR_INVALID, "bad batch / null gradOutput");
+  if (batch != net->last_batch) return fail(ctx, DCGANSR_ERR_INVALID, "backward batch differs from the cached forward");
+  if (x)
+    if (int rc = upload_nchw(ctx, x, batch, net->in_c, net->in_h, net->in_w, net->in_buf)) return rc;
+  if (int rc = upload_nchw(ctx, dy, batch, net->out_c, net->out_h, net->out_w, net->gbuf[0])) return rc;
+  const float* dxd = nullptr;
+  if (int rc = net_backward_dev(net, net->in_buf, net->gbuf[0], batch, acc, dx != nullptr, &dxd)) return rc;
+  if (dx) {
+    if (!dxd) return fail(ctx, DCGANSR_ERR_INVALID, "no input gradient produced");
+    return download_nchw(ctx, dxd, batch, net->in_c, net->in_h, net->in_w, dx);
+  }
+  CK(ctx, cudaStreamSynchronize(ctx->stream));
+  CKLAST(ctx);
+  return 0;
+}
+int dcgansr_net_backward(dcgansr_net* net, const float* x, const float* dy, int batch, float* dx) {
+  return net_backward_host(net, x, dy, batch, dx, true);
+}
+int dcgansr_net_update_grad_input(dcgansr_net* net, const float* x, const float* dy, int batch, float* dx) {
+  return net_backward_host(net, x, dy, batch, dx, false);
+}
+int dcgansr_net_zero_grads(dcgansr_net* net) {
+  NEED_DEV(net);
+  CK(ctx, cudaMemsetAsync(net->grads, 0, net->nparams * sizeof(float), ctx->stream));
+  return 0;
+}
+int dcgansr_net_adam(dcgansr_net* net, double lr, double beta1, double beta2, double eps) {
+  NEED_DEV(net);
+  return net_adam_dev(net, lr, beta1, beta2, eps);
+}
+
+// ---- the fused step ---------------------------------------------------------------------------
+static int allreduce_grads(dcgansr_ctx* ctx, dcgansr_net* net) {
+  if (ctx->world() <= 1) return 0;
+  if (int rc = nccl_allreduce(ctx, net->grads, net->nparams, ncclFloat, ctx->stream)) return rc;
+  if (!ctx->cfg.sync_bn && net->nbn > 0) {
+    // running statistics averaged at the gradient exchange point (local batch statistics mode)
+    if (int rc = nccl_allreduce(ctx, net->bn_rmean, net->nbn, ncclFloat, ctx->stream)) return rc;
+    if (int rc = nccl_allreduce(ctx, net->bn_rvar, net->nbn, ncclFloat, ctx->stream)) return rc;
+    k_scale(ctx->st(), net->bn_rmean, net->nbn, 1.f / ctx->world());
+    k_scale(ctx->st(), net->bn_rvar, net->nbn, 1.f / ctx->world());
+  }
+  return 0;
+}
+
+static int step_body(dcgansr_ctx* ctx, dcgansr_net* G, dcgansr_net* D, const dcgansr_step_cfg* cfg, const float* real, int B) {
+  St st = ctx->st();
+  const int world = ctx->world();
+  const int64_t dcount = (int64_t)B * D->out_c * D->out_h * D->out_w;   // nElement of D's output
+  const int64_t per = dcount / B;
+  const double n_total = (double)dcount * world;
+  const int lossk = cfg->loss == DCGANSR_LOSS_BCE ? LOSS_BCE : LOSS_MSE;
+  const float* dxd = nullptr;
+
+  // ---------------- fDx (train.lua:208-253) ----------------
+  CK(ctx, cudaMemsetAsync(D->grads, 0, D->nparams * sizeof(float), ctx->stream));
+  if (int rc = net_forward_dev(D, real, B)) return rc;
+  k_loss(st, lossk, D->last_out, dcount, nullptr, per, cfg->real_label, n_total, ctx->d_losses + 0, D->gbuf[0]);
+  if (int rc = net_backward_dev(D, real, D->gbuf[0], B, true, false, &dxd)) return rc;
+
+  k_avgpool2(st, real, ctx->lr_buf, B, D->in_h, D->in_w, D->in_c);                  // train.lua:225-230
+  if (int rc = net_forward_dev(G, ctx->lr_buf, B)) return rc;                       // :233-234
+  const float* fake = G->last_out;
+  const float* lvec = nullptr;
+  if (cfg->pixel_label) {                                                           // :237-239,245
+    k_pixel_mse(st, real, fake, ctx->label_vec, B, (int64_t)D->in_c * D->in_h * D->in_w, cfg->pixel_div);
+    lvec = ctx->label_vec;
+  }
+  if (int rc = net_forward_dev(D, fake, B)) return rc;                              // :242-243
+  k_loss(st, lossk, D->last_out, dcount, lvec, per, cfg->fake_label, n_total, ctx->d_losses + 1, D->gbuf[0]);
+  if (int rc = net_backward_dev(D, fake, D->gbuf[0], B, true, false, &dxd)) return rc;
+  if (int rc = allreduce_grads(ctx, D)) return rc;
+  if (int rc = net_adam_dev(D, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps)) return rc;   // optim.adam(fDx) :280
+
+  // ---------------- fGx (train.lua:256-272) ----------------
+  CK(ctx, cudaMemsetAsync(G->grads, 0, G->nparams * sizeof(float), ctx->stream));
+  // stale netD.output (pre-Adam forward on fake), post-Adam weights in the dgrad walk
+  k_loss(st, lossk, D->last_out, dcount, nullptr, per, cfg->gen_label, n_total, ctx->d_losses + 2, D->gbuf[0]);
+  if (int rc = net_backward_dev(D, fake, D->gbuf[0], B, false, true, &dxd)) return rc;  // netD:updateGradInput :268
+  const float* dummy = nullptr;
+  if (int rc = net_backward_dev(G, ctx->lr_buf, dxd, B, true, false, &dummy)) return rc; // netG:backward :270
+  if (int rc = allreduce_grads(ctx, G)) return rc;
+  if (int rc = net_adam_dev(G, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps)) return rc;   // optim.adam(fGx) :283
+  if (world > 1)
+    if (int rc = nccl_allreduce(ctx, ctx->d_losses, 3, ncclFloat, ctx->stream)) return rc;
+  return 0;
+}
+
+static int check_step_args(dcgansr_ctx* ctx, dcgansr_net* G, dcgansr_net* D, const dcgansr_step_cfg* cfg, int B) {
+  if (!ctx || !G || !D || !cfg) return fail(ctx, DCGANSR_ERR_INVALID, "null argument");
+  if (G->ctx != ctx || D->ctx != ctx) return fail(ctx, DCGANSR_ERR_INVALID, "nets belong to another context");
+  if (B <= 0 || B > G->max_batch || B > D->max_batch) return fail(ctx, DCGANSR_ERR_INVALID, "batch exceeds max_batch");
+  if (D->in_h % 2 || D->in_w % 2) return fail(ctx, DCGANSR_ERR_INVALID, "D input must have even spatial size");
+  if (G->in_c != D->in_c || G->in_h * 2 != D->in_h || G->in_w * 2 != D->in_w)
+    return fail(ctx, DCGANSR_ERR_INVALID, "G input must be the 2x2 down-sampled D input");
+  if (G->out_c != D->in_c || G->out_h != D->in_h || G->out_w != D->in_w)
+    return fail(ctx, DCGANSR_ERR_INVALID, "G output shape must equal D input shape");
+  if (cfg->loss != DCGANSR_LOSS_BCE && cfg->loss != DCGANSR_LOSS_MSE) return fail(ctx, DCGANSR_ERR_INVALID, "bad loss kind");
+  return 0;
+}
+
+static int step_run(dcgansr_ctx* ctx, dcgansr_net* G, dcgansr_net* D, const dcgansr_step_cfg* cfg, const float* real_dev, int B,
+                    float* out_losses) {
+  CK(ctx, cudaSetDevice(ctx->cfg.device));
+  size_t lr_bytes = (size_t)B * G->in_c * G->in_h * G->in_w * sizeof(float);
+  if (int rc = ensure(ctx, &ctx->lr_buf, &ctx->lr_cap, std::max<size_t>(lr_bytes, 16))) return rc;
+  if (int rc = ensure(ctx, &ctx->label_vec, &ctx->label_cap, std::max<size_t>((size_t)B * sizeof(float), 16))) return rc;
+  if (ctx->cfg.use_graph) {
+    GraphEntry* ge = nullptr;
+    for (auto& g : ctx->graphs)
+      if (g.G == G && g.D == D && g.real == real_dev && g.batch == B && memcmp(&g.cfg, cfg, sizeof(*cfg)) == 0) ge = &g;
+    if (!ge) {
+      if (ctx->graphs.size() >= 64) {
+        for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+        ctx->graphs.clear();
+      }
+      cudaGraph_t graph = nullptr;
+      int64_t before = ctx->launches;
+      CK(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+      int rc = step_body(ctx, G, D, cfg, real_dev, B);
+      cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+      int64_t nodes = ctx->launches - before;
+      ctx->launches = before;
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (e != cudaSuccess) return fail(ctx, DCGANSR_ERR_CUDA, std::string("graph capture: ") + cudaGetErrorString(e));
+      GraphEntry ne;
+      e = cudaGraphInstantiate(&ne.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) return fail(ctx, DCGANSR_ERR_CUDA, std::string("graph instantiate: ") + cudaGetErrorString(e));
+      ne.G = G; ne.D = D; ne.real = real_dev; ne.batch = B; ne.cfg = *cfg; ne.launches = nodes;
+      ctx->graphs.push_back(ne);
+      ge = &ctx->graphs.back();
+    }
+    CK(ctx, cudaGraphLaunch(ge->exec, ctx->stream));
+    ctx->launches += ge->launches;
+  } else {
+    if (int rc = step_body(ctx, G, D, cfg, real_dev, B)) return rc;
+  }
+  if (out_losses) {
+    CK(ctx, cudaMemcpyAsync(ctx->h_losses, ctx->d_losses, 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CKLAST(ctx);
+    out_losses[0] = ctx->h_losses[0]; out_losses[1] = ctx->h_losses[1]; out_losses[2] = ctx->h_losses[2];
+  }
+  return 0;
+}
+
+int dcgansr_stage_batch(dcgansr_ctx* ctx, dcgansr_net* netD, const float* real_host, int local_batch, int slot) {
+  if (!ctx || !netD || !real_host || local_batch <= 0 || slot < 0 || slot > 63)
+    return fail(ctx, DCGANSR_ERR_INVALID, "bad stage_batch argument");
+  CK(ctx, cudaSetDevice(ctx->cfg.device));
+  if ((int)ctx->slots.size() <= slot) { ctx->slots.resize(slot + 1, nullptr); ctx->slot_bytes.resize(slot + 1, 0); }
+  size_t bytes = (size_t)local_batch * netD->in_c * netD->in_h * netD->in_w * sizeof(float);
+  if (int rc = ensure(ctx, &ctx->slots[slot], &ctx->slot_bytes[slot], bytes)) return rc;
+  return upload_nchw(ctx, real_host, local_batch, netD->in_c, netD->in_h, netD->in_w, ctx->slots[slot]);
+}
+int dcgansr_train_step_staged(dcgansr_ctx* ctx, dcgansr_net* netG, dcgansr_net* netD, const dcgansr_step_cfg* cfg, int slot,
+                              int local_batch, float* out_losses) {
+  if (int rc = check_step_args(ctx, netG, netD, cfg, local_batch)) return rc;
+  if (slot < 0 || slot >= (int)ctx->slots.size() || !ctx->slots[slot]) return fail(ctx, DCGANSR_ERR_INVALID, "empty batch slot");
+  if (ctx->slot_bytes[slot] < (size_t)local_batch * netD->in_c * netD->in_h * netD->in_w * sizeof(float))
+    return fail(ctx, DCGANSR_ERR_INVALID, "staged batch smaller than local_batch");
+  return step_run(ctx, netG, netD, cfg, ctx->slots[slot], local_batch, out_losses);
+}
+int dcgansr_train_step(dcgansr_ctx* ctx, dcgansr_net* netG, dcgansr_net* netD, const dcgansr_step_cfg* cfg,
+                       const float* real_host, int local_batch, float* out_losses) {
+  if (int rc = check_step_args(ctx, netG, netD, cfg, local_batch)) return rc;
+  if (!real_host) return fail(ctx, DCGANSR_ERR_INVALID, "null batch");
+  CK(ctx, cudaSetDevice(ctx->cfg.device));
+  if (int rc = upload_nchw(ctx, real_host, local_batch, netD->in_c, netD->in_h, netD->in_w, netD->in_buf)) return rc;
+  return step_run(ctx, netG, netD, cfg, netD->in_buf, local_batch, out_losses);
+}
+int dcgansr_generate(dcgansr_ctx* ctx, dcgansr_net* netG, const float* lr_host, int batch, float* sr_host) {
+  if (!ctx || !netG || netG->ctx != ctx) return fail(ctx, DCGANSR_ERR_INVALID, "bad argument");
+  return dcgansr_net_forward(netG, lr_host, batch, sr_host);
+}
+
+// ---- layer-level ops (parity tests) -----------------------------------------------------------
+#define NEED_CTX(ctx)                                                          \
+  if (!(ctx)) return fail(nullptr, DCGANSR_ERR_INVALID, "null ctx");            \
+  CK(ctx, cudaSetDevice((ctx)->cfg.device));
+
+static int conv_op(dcgansr_ctx* ctx, bool full, int what, const float* a, const float* b, float* outp, int n, int cin, int h,
+                   int wd, int cout, int k, int s, int p) {
+  NEED_CTX(ctx);
+  if (!a || !b || !outp || n <= 0) return fail(ctx, DCGANSR_ERR_INVALID, "null argument");
+  ConvPlan plan;
+  std::string err = plan.build(full, cin, cout, k, s, p, 0, h, wd);
+  if (!err.empty()) return fail(ctx, DCGANSR_ERR_INVALID, err);
+  struct Guard { ConvPlan& p; ~Guard() { p.free_device(); } } guard{plan};
+  if (int rc = plan.alloc_device(ctx)) return rc;
+  Arena ar;
+  int64_t xin = (int64_t)n * cin * h * wd, yout = (int64_t)n * cout * plan.Hout * plan.Wout, wn = plan.weight_count();
+  float* dX = ar.f(xin);
+  float* dY = ar.f(yout);
+  float* dW = ar.f(wn);
+  if (!dX || !dY || !dW) return fail(ctx, DCGANSR_ERR_NOMEM, "device allocation failed");
+  int rc = 0;
+  if (what == 0) {          // fwd: a = x, b = w, out = y
+    if ((rc = upload_nchw(ctx, a, n, cin, h, wd, dX))) return rc;
+    CK(ctx, cudaMemcpyAsync(dW, b, wn * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    plan.pack(ctx->st(), dW);
+    plan.forward(ctx, dX, dY, n, ACT_NONE, 0.f);
+    return download_nchw(ctx, dY, n, cout, plan.Hout, plan.Wout, outp);
+  } else if (what == 1) {   // dgrad: a = dy, b = w, out = dx
+    if ((rc = upload_nchw(ctx, a, n, cout, plan.Hout, plan.Wout, dY))) return rc;
+    CK(ctx, cudaMemcpyAsync(dW, b, wn * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    plan.pack(ctx->st(), dW);
+    plan.dgrad_run(ctx, dY, dX, n);
+    return download_nchw(ctx, dX, n, cin, h, wd, outp);
+  } else {                  // wgrad: a = x, b = dy, out = dw
+    if ((rc = upload_nchw(ctx, a, n, cin, h, wd, dX))) return rc;
+    if ((rc = upload_nchw(ctx, b, n, cout, plan.Hout, plan.Wout, dY))) return rc;
+    CK(ctx, cudaMemsetAsync(dW, 0, wn * sizeof(float), ctx->stream));
+    size_t sb = plan.wscratch_bytes(n);
+    float* sc = (float*)ar.bytes(sb);
+    if (!sc) return fail(ctx, DCGANSR_ERR_NOMEM, "device allocation failed");
+    plan.wgrad_run(ctx, dX, dY, dW, n, sc, sb);
+    return d2h(ctx, outp, dW, wn);
+  }
+}
+int dcgansr_conv2d_fwd(dcgansr_ctx* ctx, const float* x, const float* w, float* y, int n, int cin, int h, int wd, int cout, int k, int s, int p) {
+  return conv_op(ctx, false, 0, x, w, y, n, cin, h, wd, cout, k, s, p);
+}
+int dcgansr_conv2d_dgrad(dcgansr_ctx* ctx, const float* dy, const float* w, float* dx, int n, int cin, int h, int wd, int cout, int k, int s, int p) {
+  return conv_op(ctx, false, 1, dy, w, dx, n, cin, h, wd, cout, k, s, p);
+}
+int dcgansr_conv2d_wgrad(dcgansr_ctx* ctx, const float* x, const float* dy, float* dw, int n, int cin, int h, int wd, int cout, int k, int s, int p) {
+  return conv_op(ctx, false, 2, x, dy, dw, n, cin, h, wd, cout, k, s, p);
+}
+int dcgansr_fullconv2d_fwd(dcgansr_ctx* ctx, const float* x, const float* w, float* y, int n, int cin, int h, int wd, int cout, int k, int s, int p) {
+  return conv_op(ctx, true, 0, x, w, y, n, cin, h, wd, cout, k, s, p);
+}
+int dcgansr_fullconv2d_dgrad(dcgansr_ctx* ctx, const float* dy, const float* w, float* dx, int n, int cin, int h, int wd, int cout, int k, int s, int p) {
+  return conv_op(ctx, true, 1, dy, w, dx, n, cin, h, wd, cout, k, s, p);
+}
+int dcgansr_fullconv2d_wgrad(dcgansr_ctx* ctx, const float* x, const float* dy, float* dw, int n, int cin, int h, int wd, int cout, int k, int s, int p) {
+  return conv_op(ctx, true, 2, x, dy, dw, n, cin, h, wd, cout, k, s, p);
+}
+
+int dcgansr_bn_fwd_train(dcgansr_ctx* ctx, const float* x, const float* gamma, const float* beta, float* running_mean,
+                         float* running_var, float* y, float* save_mean, float* save_invstd, int n, int c, int h, int wd,
+                         float eps, float momentum) {
+  NEED_CTX(ctx);
+  if (!x || !gamma || !beta || !y || n <= 0 || c <= 0) return fail(ctx, DCGANSR_ERR_INVALID, "null argument");
+  Arena ar;
+  int64_t E = (int64_t)n * c * h * wd, P = (int64_t)n * h * wd;
+  float *dX = ar.f(E), *dY = ar.f(E), *dG = ar.f(c), *dB = ar.f(c), *dM = ar.f(c), *dI = ar.f(c), *dRM = ar.f(c), *dRV = ar.f(c);
+  double* part = (double*)ar.bytes((size_t)bn_partial_rows(P, c) * 2 * c * sizeof(double));
+  double* sums = (double*)ar.bytes((size_t)2 * c * sizeof(double));
+  if (!dX || !dY || !dG || !dB || !dM || !dI || !dRM || !dRV || !part || !sums) return fail(ctx, DCGANSR_ERR_NOMEM, "device allocation failed");
+  if (int rc = upload_nchw(ctx, x, n, c, h, wd, dX)) return rc;
+  CK(ctx, cudaMemcpyAsync(dG, gamma, c * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(dB, beta, c * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  bool run = running_mean && running_var;
+  if (run) {
+    CK(ctx, cudaMemcpyAsync(dRM, running_mean, c * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(dRV, running_var, c * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  St st = ctx->st();
+  k_bn_stats(st, dX, P, c, part, sums);
+  k_bn_finalize(st, sums, c, (double)P, eps, momentum, dM, dI, run ? dRM : nullptr, run ? dRV : nullptr);
+  k_bn_apply_act(st, dX, dY, P, c, dG, dB, dM, dI, ACT_NONE, 0.f);
+  if (int rc = download_nchw(ctx, dY, n, c, h, wd, y)) return rc;
+  if (int rc = d2h(ctx, save_mean, dM, c)) return rc;
+  if (int rc = d2h(ctx, save_invstd, dI, c)) return rc;
+  if (run) {
+    if (int rc = d2h(ctx, running_mean, dRM, c)) return rc;
+    if (int rc = d2h(ctx, running_var, dRV, c)) return rc;
+  }
+  return 0;
+}
+
+int dcgansr_bn_bwd(dcgansr_ctx* ctx, const float* x, const float* dy, const float* gamma, const float* save_mean,
+                   const float* save_invstd, float* dx, float* dgamma, float* dbeta, int n, int c, int h, int wd) {
+  NEED_CTX(ctx);
+  if (!x || !dy || !gamma || !save_mean || !save_invstd || n <= 0 || c <= 0) return fail(ctx, DCGANSR_ERR_INVALID, "null argument");
+  Arena ar;
+  int64_t E = (int64_t)n * c * h * wd, P = (int64_t)n * h * wd;
+  float *dX = ar.f(E), *dDY = ar.f(E), *dGm = ar.f(E), *dG = ar.f(c), *dM = ar.f(c), *dI = ar.f(c), *dDG = ar.f(c), *dDB = ar.f(c);
+  double* part = (double*)ar.bytes((size_t)bn_partial_rows(P, c) * 2 * c * sizeof(double));
+  double* sums = (double*)ar.bytes((size_t)2 * c * sizeof(double));
+  if (!dX || !dDY || !dGm || !dG || !dM || !dI || !dDG || !dDB || !part || !sums) return fail(ctx, DCGANSR_ERR_NOMEM, "device allocation failed");
+  if (int rc = upload_nchw(ctx, x, n, c, h, wd, dX)) return rc;
+  if (int rc = upload_nchw(ctx, dy, n, c, h, wd, dDY)) return rc;
+  CK(ctx, cudaMemcpyAsync(dG, gamma, c * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(dM, save_mean, c * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(dI, save_invstd, c * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemsetAsync(dDG, 0, c * sizeof(float), ctx->stream));
+  CK(ctx, cudaMemsetAsync(dDB, 0, c * sizeof(float), ctx->stream));
+  St st = ctx->st();
+  k_bn_bwd_reduce(st, dDY, nullptr, dX, dGm, P, c, dM, dI, ACT_NONE, 0.f, part, sums);
+  k_bn_bwd_param(st, sums, c, dDG, dDB);
+  k_bn_bwd_apply(st, dGm, dX, dGm, P, c, dG, dM, dI, sums, (double)P);
+  if (dx) if (int rc = download_nchw(ctx, dGm, n, c, h, wd, dx)) return rc;
+  if (int rc = d2h(ctx, dgamma, dDG, c)) return rc;
+  return d2h(ctx, dbeta, dDB, c);
+}
+
+int dcgansr_act_fwd(dcgansr_ctx* ctx, const float* x, float* y, int64_t count, int kind, float negval) {
+  NEED_CTX(ctx);
+  if (!x || !y || count < 0) return fail(ctx, DCGANSR_ERR_INVALID, "null argument");
+  if (count == 0) return 0;
+  Arena ar;
+  float* d = ar.f(count);
+  if (!d) return fail(ctx, DCGANSR_ERR_NOMEM, "device allocation failed");
+  CK(ctx, cudaMemcpyAsync(d, x, count * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  k_act(ctx->st(), d, d, count, kind, negval);
+  return d2h(ctx, y, d, count);
+}
+int dcgansr_act_bwd(dcgansr_ctx* ctx, const float* y, const float* dy, float* dx, int64_t count, int kind, float negval) {
+  NEED_CTX(ctx);
+  if (!y || !dy || !dx || count < 0) return fail(ctx, DCGANSR_ERR_INVALID, "null argument");
+  if (count == 0) return 0;
+  Arena ar;
+  float *a = ar.f(count), *b = ar.f(count);
+  if (!a || !b) return fail(ctx, DCGANSR_ERR_NOMEM, "device allocation failed");
+  CK(ctx, cudaMemcpyAsync(a, y, count * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(b, dy, count * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  k_act_bwd(ctx->st(), a, b, b, count, kind, negval);
+  return d2h(ctx, dx, b, count);
+}
+
+static int resample_op(dcgansr_ctx* ctx, int what, const float* a, float* outp, int n, int c, int h, int wd) {
+  NEED_CTX(ctx);
+  if (!a || !outp || n <= 0 || c <= 0 || h <= 0 || wd <= 0) return fail(ctx, DCGANSR_ERR_INVALID, "null argument");
+  // what: 0 upnearest fwd (in h x wd -> 2h x 2wd), 1 upnearest bwd (in 2h x 2wd -> h x wd), 2 avgpool2 (in h x wd -> h/2 x wd/2)
+  int ih = what == 1 ? 2 * h : h, iw = what == 1 ? 2 * wd : wd;
+  int oh = what == 0 ? 2 * h : (what == 1 ? h : h / 2), ow = what == 0 ? 2 * wd : (what == 1 ? wd : wd / 2);
+  if (what == 2 && (h % 2 || wd % 2)) return fail(ctx, DCGANSR_ERR_INVALID, "avgpool2 needs even spatial dims");
+  Arena ar;
+  float *dI = ar.f((int64_t)n * c * ih * iw), *dO = ar.f((int64_t)n * c * oh * ow);
+  if (!dI || !dO) return fail(ctx, DCGANSR_ERR_NOMEM, "device allocation failed");
+  if (int rc = upload_nchw(ctx, a, n, c, ih, iw, dI)) return rc;
+  if (what == 0) k_upnearest_fwd(ctx->st(), dI, dO, n, h, wd, c, 2);
+  else if (what == 1) k_upnearest_bwd(ctx->st(), dI, dO, n, h, wd, c, 2);
+  else k_avgpool2(ctx->st(), dI, dO, n, h, wd, c);
+  return download_nchw(ctx, dO, n, c, oh, ow, outp);
+}
+int dcgansr_upnearest2_fwd(dcgansr_ctx* ctx, const float* x, float* y, int n, int c, int h, int wd) { return resample_op(ctx, 0, x, y, n, c, h, wd); }
+int dcgansr_upnearest2_bwd(dcgansr_ctx* ctx, const float* dy, float* dx, int n, int c, int h, int wd) { return resample_op(ctx, 1, dy, dx, n, c, h, wd); }
+int dcgansr_avgpool2_fwd(dcgansr_ctx* ctx, const float* x, float* y, int n, int c, int h, int wd) { return resample_op(ctx, 2, x, y, n, c, h, wd); }
+
+static int loss_op(dcgansr_ctx* ctx, int kind, const float* x, const float* label, int64_t count, float* loss, float* dx) {
+  NEED_CTX(ctx);
+  if (!x || !label || count <= 0) return fail(ctx, DCGANSR_ERR_INVALID, "null argument");
+  Arena ar;
+  float *dX = ar.f(count), *dL = ar.f(count), *dD = ar.f(count), *dS = ar.f(4);
+  if (!dX || !dL || !dD || !dS) return fail(ctx, DCGANSR_ERR_NOMEM, "device allocation failed");
+  CK(ctx, cudaMemcpyAsync(dX, x, count * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(dL, label, count * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  k_loss(ctx->st(), kind, dX, count, dL, 1, 0.f, (double)count, dS, dD);
+  if (int rc = d2h(ctx, loss, dS, 1)) return rc;
+  return d2h(ctx, dx, dD, count);
+}
+int dcgansr_bce(dcgansr_ctx* ctx, const float* x, const float* label, int64_t count, float* loss, float* dx) { return loss_op(ctx, LOSS_BCE, x, label, count, loss, dx); }
+int dcgansr_mse(dcgansr_ctx* ctx, const float* x, const float* label, int64_t count, float* loss, float* dx) { return loss_op(ctx, LOSS_MSE, x, label, count, loss, dx); }
+
+int dcgansr_pixel_mse_per_sample(dcgansr_ctx* ctx, const float* real, const float* fake, float* out, int n, int64_t per_sample, float div) {
+  NEED_CTX(ctx);
+  if (!real || !fake || !out || n <= 0 || per_sample <= 0) return fail(ctx, DCGANSR_ERR_INVALID, "null argument");
+  Arena ar;
+  float *a = ar.f(n * per_sample), *b = ar.f(n * per_sample), *o = ar.f(n);
+  if (!a || !b || !o) return fail(ctx, DCGANSR_ERR_NOMEM, "device allocation failed");
+  CK(ctx, cudaMemcpyAsync(a, real, n * per_sample * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(b, fake, n * per_sample * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  k_pixel_mse(ctx->st(), a, b, o, n, per_sample, div);
+  return d2h(ctx, out, o, n);
+}
+
+int dcgansr_adam_step(dcgansr_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t count, int64_t t, double lr,
+                      double beta1, double beta2, double eps) {
+  NEED_CTX(ctx);
+  if (!p || !g || !m || !v || count <= 0) return fail(ctx, DCGANSR_ERR_INVALID, "null argument");
+  Arena ar;
+  float *dp = ar.f(count), *dg = ar.f(count), *dm = ar.f(count), *dv = ar.f(count), *ds = ar.f(4);
+  int64_t* dt = (int64_t*)ar.bytes(sizeof(int64_t));
+  if (!dp || !dg || !dm || !dv || !ds || !dt) return fail(ctx, DCGANSR_ERR_NOMEM, "device allocation failed");
+  size_t nb = count * sizeof(float);
+  CK(ctx, cudaMemcpyAsync(dp, p, nb, cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(dg, g, nb, cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(dm, m, nb, cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(dv, v, nb, cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(dt, &t, sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
+  k_adam_prep(ctx->st(), dt, ds, lr, beta1, beta2);
+  k_adam(ctx->st(), dp, dg, dm, dv, count, ds, beta1, beta2, eps);
+  if (int rc = d2h(ctx, p, dp, count)) return rc;
+  if (int rc = d2h(ctx, m, dm, count)) return rc;
+  return d2h(ctx, v, dv, count);
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,653 @@
+// kernels_bw.cu -- the HBM-bound kernels of the DCGAN-SR training step (sm_100a).
+//
+// Everything here is bandwidth work: layout import/export, BatchNorm statistics / apply /
+// backward, activations, nearest up-sampling, the 2x2 box down-sample, the criteria, the
+// per-sample pixel MSE and the fused Adam update.  Activations are NHWC fp32; the channel is
+// the fastest dimension so every kernel reads and writes 16-byte vectors when C % 4 == 0.
+// Reductions are deterministic: per-thread double accumulators -> shared-memory tree ->
+// one partial row per CTA -> fixed-order column sum (no atomics).
+//
+// Reference semantics restated:
+//   nn.SpatialBatchNormalization  train.lua:100        nn.ReLU/LeakyReLU/Tanh/Sigmoid  train.lua:100-134
+//   nn.SpatialUpSamplingNearest   train-gray.lua:104   2x2 box down-sample loop        train.lua:225-230
+//   nn.BCECriterion / MSECriterion train-gray-patch.lua:113 / train.lua:142
+//   calMSE loop                   train.lua:193-195,237-239     optim.adam   train.lua:280
+#include "common.h"
+#include <math.h>
+
+#define NSM 148
+
+static inline int cdiv64(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------
+// layout import / export: per image a [R][Cc] -> [Cc][R] transpose through shared memory
+// ------------------------------------------------------------------------------------------
+__global__ void transpose_kernel(const float* __restrict__ in, float* __restrict__ out, int R, int Cc, int N) {
+  __shared__ float tile[32][33];
+  int tiles_r = (R + 31) / 32;
+  for (int n = blockIdx.z; n < N; n += gridDim.z) {
+    const float* src = in + (int64_t)n * R * Cc;
+    float* dst = out + (int64_t)n * R * Cc;
+    for (int tr = blockIdx.y; tr < tiles_r; tr += gridDim.y) {
+      int c0 = blockIdx.x * 32, r0 = tr * 32;
+      for (int j = threadIdx.y; j < 32; j += 8) {
+        int r = r0 + j, c = c0 + threadIdx.x;
+        if (r < R && c < Cc) tile[j][threadIdx.x] = src[(int64_t)r * Cc + c];
+      }
+      __syncthreads();
+      for (int j = threadIdx.y; j < 32; j += 8) {
+        int c = c0 + j, r = r0 + threadIdx.x;
+        if (r < R && c < Cc) dst[(int64_t)c * R + r] = tile[threadIdx.x][j];
+      }
+      __syncthreads();
+    }
+  }
+}
+
+static void transpose_batched(St st, const float* in, float* out, int N, int R, int Cc) {
+  if (R == 1 || Cc == 1) {
+    cudaMemcpyAsync(out, in, (size_t)N * R * Cc * sizeof(float), cudaMemcpyDeviceToDevice, st.s);
+    return;
+  }
+  int gy = (R + 31) / 32;
+  if (gy > 4096) gy = 4096;
+  dim3 grid((Cc + 31) / 32, gy, N > 1024 ? 1024 : N);
+  transpose_kernel<<<grid, dim3(32, 8), 0, st.s>>>(in, out, R, Cc, N);
+  DSR_LAUNCHED(st, "transpose", 8.0 * N * R * Cc, WORK_BYTES);
+}
+
+// per image: [C][HW] -> [HW][C]
+void k_nchw_to_nhwc(St st, const float* in, float* out, int N, int C, int H, int W) {
+  transpose_batched(st, in, out, N, C, H * W);
+}
+// per image: [HW][C] -> [C][HW]
+void k_nhwc_to_nchw(St st, const float* in, float* out, int N, int C, int H, int W) {
+  transpose_batched(st, in, out, N, H * W, C);
+}
+
+// ------------------------------------------------------------------------------------------
+// activations
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float act_apply(float v, int act, float neg) {
+  switch (act) {
+    case ACT_RELU: return v > 0.f ? v : 0.f;
+    case ACT_LRELU: return v > 0.f ? v : v * neg;
+    case ACT_TANH: return tanhf(v);
+    case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    default: return v;
+  }
+}
+// gradient through the activation given its OUTPUT y (in-place Torch7 modules test the output)
+__device__ __forceinline__ float act_grad(float y, float dy, int act, float neg) {
+  switch (act) {
+    case ACT_RELU: return y > 0.f ? dy : 0.f;
+    case ACT_LRELU: return y > 0.f ? dy : dy * neg;
+    case ACT_TANH: return dy * (1.f - y * y);
+    case ACT_SIGMOID: return dy * y * (1.f - y);
+    default: return dy;
+  }
+}
+
+__global__ void act_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t count, int act, float neg) {
+  int64_t n4 = count >> 2;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  float4* y4 = reinterpret_cast<float4*>(y);
+  for (int64_t k = i; k < n4; k += stride) {
+    float4 v = x4[k];
+    v.x = act_apply(v.x, act, neg); v.y = act_apply(v.y, act, neg);
+    v.z = act_apply(v.z, act, neg); v.w = act_apply(v.w, act, neg);
+    y4[k] = v;
+  }
+  for (int64_t k = (n4 << 2) + i; k < count; k += stride) y[k] = act_apply(x[k], act, neg);
+}
+
+__global__ void act_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx,
+                               int64_t count, int act, float neg) {
+  int64_t n4 = count >> 2;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const float4* y4 = reinterpret_cast<const float4*>(y);
+  const float4* d4 = reinterpret_cast<const float4*>(dy);
+  float4* o4 = reinterpret_cast<float4*>(dx);
+  for (int64_t k = i; k < n4; k += stride) {
+    float4 a = y4[k], d = d4[k], o;
+    o.x = act_grad(a.x, d.x, act, neg); o.y = act_grad(a.y, d.y, act, neg);
+    o.z = act_grad(a.z, d.z, act, neg); o.w = act_grad(a.w, d.w, act, neg);
+    o4[k] = o;
+  }
+  for (int64_t k = (n4 << 2) + i; k < count; k += stride) dx[k] = act_grad(y[k], dy[k], act, neg);
+}
+
+static inline int ew_grid(int64_t count) {
+  int64_t want = (count / 4 + 255) / 256;
+  int64_t cap = NSM * 16;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+
+void k_act(St st, const float* x, float* y, int64_t count, int act, float negval) {
+  if (count <= 0) return;
+  act_kernel<<<ew_grid(count), 256, 0, st.s>>>(x, y, count, act, negval);
+  DSR_LAUNCHED(st, "act", 8.0 * count, WORK_BYTES);
+}
+void k_act_bwd(St st, const float* y, const float* dy, float* dx, int64_t count, int act, float negval) {
+  if (count <= 0) return;
+  act_bwd_kernel<<<ew_grid(count), 256, 0, st.s>>>(y, dy, dx, count, act, negval);
+  DSR_LAUNCHED(st, "act_bwd", 12.0 * count, WORK_BYTES);
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm.  x is [P][C] (P = N*H*W pixels).  Thread layout inside a 256-thread CTA:
+// tx in [0,TX) walks channel vectors, ty in [0,TY) walks pixels; a CTA owns a contiguous
+// pixel range, so each warp reads whole contiguous runs of the tensor.
+// ------------------------------------------------------------------------------------------
+struct BnCfg { int vec, CV, TX, TY, nb; int64_t ppb; };
+
+static BnCfg bn_cfg(int64_t P, int C) {
+  BnCfg c;
+  c.vec = (C % 4 == 0) ? 4 : 1;
+  c.CV = C / c.vec;
+  int tx = 1;
+  while (tx < c.CV && tx < 256) tx <<= 1;
+  c.TX = tx;
+  c.TY = 256 / tx;
+  int64_t min_ppb = (int64_t)c.TY * 8;                 // at least 8 pixels per thread row
+  int64_t nb = (P + min_ppb - 1) / min_ppb;
+  int64_t cap = NSM * 4;
+  if (nb > cap) nb = cap;
+  if (nb < 1) nb = 1;
+  c.ppb = (P + nb - 1) / nb;
+  c.nb = (int)((P + c.ppb - 1) / c.ppb);
+  if (c.nb < 1) c.nb = 1;
+  return c;
+}
+
+int bn_partial_rows(int64_t P, int C) { return bn_cfg(P, C).nb; }
+
+// Reduce per-thread accumulators a[2*VEC] over ty and write one partial row.
+template <int VEC>
+__device__ __forceinline__ void bn_block_reduce_store(double (&a)[2 * VEC], int tx, int ty, int TX, int TY, int cv, int CV,
+                                                      int C, double* __restrict__ prow) {
+  __shared__ double red[256 * 2 * VEC];
+  int tid = ty * TX + tx;
+#pragma unroll
+  for (int j = 0; j < 2 * VEC; ++j) red[j * 256 + tid] = a[j];
+  __syncthreads();
+  for (int off = TY >> 1; off > 0; off >>= 1) {
+    if (ty < off) {
+#pragma unroll
+      for (int j = 0; j < 2 * VEC; ++j) red[j * 256 + tid] += red[j * 256 + tid + off * TX];
+    }
+    __syncthreads();
+  }
+  if (ty == 0 && cv < CV) {
+#pragma unroll
+    for (int j = 0; j < VEC; ++j) {
+      prow[cv * VEC + j] = red[j * 256 + tid];
+      prow[C + cv * VEC + j] = red[(VEC + j) * 256 + tid];
+    }
+  }
+  __syncthreads();
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, int64_t P, int C, int TX, int TY,
+                                                       int64_t ppb, double* __restrict__ partials) {
+  int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  int CV = C / VEC;
+  int64_t p0 = (int64_t)blockIdx.x * ppb;
+  int64_t p1 = p0 + ppb < P ? p0 + ppb : P;
+  double* prow = partials + (int64_t)blockIdx.x * 2 * C;
+  for (int cv0 = 0; cv0 < CV; cv0 += TX) {
+    int cv = cv0 + tx;
+    double a[2 * VEC];
+#pragma unroll
+    for (int j = 0; j < 2 * VEC; ++j) a[j] = 0.0;
+    if (cv < CV) {
+      for (int64_t p = p0 + ty; p < p1; p += TY) {
+        if (VEC == 4) {
+          float4 v = *reinterpret_cast<const float4*>(x + p * C + cv * 4);
+          double d0 = v.x, d1 = v.y, d2 = v.z, d3 = v.w;
+          a[0] += d0; a[1] += d1; a[2] += d2; a[3] += d3;
+          a[VEC + 0] += d0 * d0; a[VEC + 1] += d1 * d1; a[VEC + 2] += d2 * d2; a[VEC + 3] += d3 * d3;
+        } else {
+          double d0 = x[p * C + cv];
+          a[0] += d0; a[VEC] += d0 * d0;
+        }
+      }
+    }
+    bn_block_reduce_store<VEC>(a, tx, ty, TX, TY, cv, CV, C, prow);
+  }
+}
+
+// sums[j] = sum_b partials[b][j]   (fixed order: deterministic)
+__global__ void colsum_kernel(const double* __restrict__ partials, int nb, int ncol, double* __restrict__ sums) {
+  __shared__ double red[8][33];
+  int j = blockIdx.x * 32 + threadIdx.x;
+  double a = 0.0;
+  if (j < ncol)
+    for (int b = threadIdx.y; b < nb; b += 8) a += partials[(int64_t)b * ncol + j];
+  red[threadIdx.y][threadIdx.x] = a;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < ncol) {
+    double s = 0.0;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) s += red[r][threadIdx.x];
+    sums[j] = s;
+  }
+}
+
+void k_bn_stats(St st, const float* x, int64_t P, int C, double* partials, double* sums) {
+  BnCfg c = bn_cfg(P, C);
+  if (c.vec == 4) bn_stats_kernel<4><<<c.nb, 256, 0, st.s>>>(x, P, C, c.TX, c.TY, c.ppb, partials);
+  else bn_stats_kernel<1><<<c.nb, 256, 0, st.s>>>(x, P, C, c.TX, c.TY, c.ppb, partials);
+  DSR_LAUNCHED(st, "bn_stats", 4.0 * P * C, WORK_BYTES);
+  colsum_kernel<<<(2 * C + 31) / 32, dim3(32, 8), 0, st.s>>>(partials, c.nb, 2 * C, sums);
+  DSR_LAUNCHED(st, "bn_colsum", 16.0 * c.nb * C, WORK_BYTES);
+}
+
+// mean / invstd / running statistics (biased variance normalises, unbiased goes to running_var)
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, double n_total, float eps, float momentum,
+                                   float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double mean = sums[c] / n_total;
+  double var = sums[C + c] / n_total - mean * mean;
+  if (var < 0.0) var = 0.0;
+  double invstd = 1.0 / sqrt(var + (double)eps);
+  save_mean[c] = (float)mean;
+  save_invstd[c] = (float)invstd;
+  if (running_mean) {
+    double unb = n_total > 1.0 ? var * (n_total / (n_total - 1.0)) : var;
+    running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * mean);
+    running_var[c] = (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * unb);
+  }
+}
+
+void k_bn_finalize(St st, const double* sums, int C, double n_total, float eps, float momentum,
+                   float* save_mean, float* save_invstd, float* running_mean, float* running_var) {
+  bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st.s>>>(sums, C, n_total, eps, momentum, save_mean, save_invstd,
+                                                         running_mean, running_var);
+  DSR_LAUNCHED(st, "bn_finalize", 32.0 * C, WORK_BYTES);
+}
+
+// y = act(gamma * (x - mean) * invstd + beta)
+template <int VEC>
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t total_v, int CV,
+                                                       const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                       const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                       int act, float neg) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_v; i += stride) {
+    int cv = (int)(i % CV);
+    if (VEC == 4) {
+      float4 v = reinterpret_cast<const float4*>(x)[i];
+      float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + cv);
+      float4 b = __ldg(reinterpret_cast<const float4*>(beta) + cv);
+      float4 m = __ldg(reinterpret_cast<const float4*>(mean) + cv);
+      float4 s = __ldg(reinterpret_cast<const float4*>(invstd) + cv);
+      v.x = act_apply((v.x - m.x) * s.x * g.x + b.x, act, neg);
+      v.y = act_apply((v.y - m.y) * s.y * g.y + b.y, act, neg);
+      v.z = act_apply((v.z - m.z) * s.z * g.z + b.z, act, neg);
+      v.w = act_apply((v.w - m.w) * s.w * g.w + b.w, act, neg);
+      reinterpret_cast<float4*>(y)[i] = v;
+    } else {
+      float v = x[i];
+      y[i] = act_apply((v - __ldg(mean + cv)) * __ldg(invstd + cv) * __ldg(gamma + cv) + __ldg(beta + cv), act, neg);
+    }
+  }
+}
+
+void k_bn_apply_act(St st, const float* x, float* y, int64_t P, int C, const float* gamma, const float* beta,
+                    const float* mean, const float* invstd, int act, float negval) {
+  if (C % 4 == 0) {
+    int64_t tv = P * (C / 4);
+    bn_apply_kernel<4><<<ew_grid(tv * 4), 256, 0, st.s>>>(x, y, tv, C / 4, gamma, beta, mean, invstd, act, negval);
+  } else {
+    int64_t tv = P * C;
+    bn_apply_kernel<1><<<ew_grid(tv * 4), 256, 0, st.s>>>(x, y, tv, C, gamma, beta, mean, invstd, act, negval);
+  }
+  DSR_LAUNCHED(st, "bn_apply_act", 8.0 * P * C, WORK_BYTES);
+}
+
+// backward reductions: g = dy * act'(y) ; sum g, sum g * xhat
+template <int VEC>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                            const float* __restrict__ x, float* __restrict__ g_out, int64_t P,
+                                                            int C, int TX, int TY, int64_t ppb, const float* __restrict__ mean,
+                                                            const float* __restrict__ invstd, int act, float neg,
+                                                            double* __restrict__ partials) {
+  int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
+  int CV = C / VEC;
+  int64_t p0 = (int64_t)blockIdx.x * ppb;
+  int64_t p1 = p0 + ppb < P ? p0 + ppb : P;
+  double* prow = partials + (int64_t)blockIdx.x * 2 * C;
+  for (int cv0 = 0; cv0 < CV; cv0 += TX) {
+    int cv = cv0 + tx;
+    double a[2 * VEC];
+#pragma unroll
+    for (int j = 0; j < 2 * VEC; ++j) a[j] = 0.0;
+    if (cv < CV) {
+      if (VEC == 4) {
+        float4 m = __ldg(reinterpret_cast<const float4*>(mean) + cv);
+        float4 s = __ldg(reinterpret_cast<const float4*>(invstd) + cv);
+        for (int64_t p = p0 + ty; p < p1; p += TY) {
+          int64_t o = p * C + cv * 4;
+          float4 d = *reinterpret_cast<const float4*>(dy + o);
+          float4 xv = *reinterpret_cast<const float4*>(x + o);
+          float4 g = d;
+          if (act != ACT_NONE) {
+            float4 yv = *reinterpret_cast<const float4*>(y + o);
+            g.x = act_grad(yv.x, d.x, act, neg); g.y = act_grad(yv.y, d.y, act, neg);
+            g.z = act_grad(yv.z, d.z, act, neg); g.w = act_grad(yv.w, d.w, act, neg);
+          }
+          *reinterpret_cast<float4*>(g_out + o) = g;
+          double g0 = g.x, g1 = g.y, g2 = g.z, g3 = g.w;
+          a[0] += g0; a[1] += g1; a[2] += g2; a[3] += g3;
+          a[VEC + 0] += g0 * (double)((xv.x - m.x) * s.x);
+          a[VEC + 1] += g1 * (double)((xv.y - m.y) * s.y);
+          a[VEC + 2] += g2 * (double)((xv.z - m.z) * s.z);
+          a[VEC + 3] += g3 * (double)((xv.w - m.w) * s.w);
+        }
+      } else {
+        float m = __ldg(mean + cv), s = __ldg(invstd + cv);
+        for (int64_t p = p0 + ty; p < p1; p += TY) {
+          int64_t o = p * C + cv;
+          float d = dy[o];
+          float g = act != ACT_NONE ? act_grad(y[o], d, act, neg) : d;
+          g_out[o] = g;
+          a[0] += (double)g;
+          a[VEC] += (double)g * (double)((x[o] - m) * s);
+        }
+      }
+    }
+    bn_block_reduce_store<VEC>(a, tx, ty, TX, TY, cv, CV, C, prow);
+  }
+}
+
+void k_bn_bwd_reduce(St st, const float* dy, const float* y, const float* x, float* g_out, int64_t P, int C,
+                     const float* mean, const float* invstd, int act, float negval, double* partials, double* sums) {
+  BnCfg c = bn_cfg(P, C);
+  if (c.vec == 4)
+    bn_bwd_reduce_kernel<4><<<c.nb, 256, 0, st.s>>>(dy, y, x, g_out, P, C, c.TX, c.TY, c.ppb, mean, invstd, act, negval, partials);
+  else
+    bn_bwd_reduce_kernel<1><<<c.nb, 256, 0, st.s>>>(dy, y, x, g_out, P, C, c.TX, c.TY, c.ppb, mean, invstd, act, negval, partials);
+  DSR_LAUNCHED(st, "bn_bwd_reduce", (act != ACT_NONE ? 16.0 : 12.0) * P * C, WORK_BYTES);
+  colsum_kernel<<<(2 * C + 31) / 32, dim3(32, 8), 0, st.s>>>(partials, c.nb, 2 * C, sums);
+  DSR_LAUNCHED(st, "bn_colsum", 16.0 * c.nb * C, WORK_BYTES);
+}
+
+__global__ void bn_bwd_param_kernel(const double* __restrict__ sums, int C, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  if (dbeta) dbeta[c] += (float)sums[c];
+  if (dgamma) dgamma[c] += (float)sums[C + c];
+}
+void k_bn_bwd_param(St st, const double* sums_local, int C, float* dgamma, float* dbeta) {
+  bn_bwd_param_kernel<<<(C + 127) / 128, 128, 0, st.s>>>(sums_local, C, dgamma, dbeta);
+  DSR_LAUNCHED(st, "bn_bwd_param", 32.0 * C, WORK_BYTES);
+}
+
+// dx = (g - sum_g/n - xhat * sum_gxhat/n) * gamma * invstd      (in place on g allowed)
+template <int VEC>
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ x,
+                                                           float* __restrict__ dx, int64_t total_v, int CV, int C,
+                                                           const float* __restrict__ gamma, const float* __restrict__ mean,
+                                                           const float* __restrict__ invstd, const double* __restrict__ sums,
+                                                           double n_total) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_v; i += stride) {
+    int cv = (int)(i % CV);
+    if (VEC == 4) {
+      float4 gv = reinterpret_cast<const float4*>(g)[i];
+      float4 xv = reinterpret_cast<const float4*>(x)[i];
+      float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + cv);
+      float4 m = __ldg(reinterpret_cast<const float4*>(mean) + cv);
+      float4 s = __ldg(reinterpret_cast<const float4*>(invstd) + cv);
+      int c = cv * 4;
+      float mg0 = (float)(sums[c + 0] / n_total), mg1 = (float)(sums[c + 1] / n_total);
+      float mg2 = (float)(sums[c + 2] / n_total), mg3 = (float)(sums[c + 3] / n_total);
+      float mx0 = (float)(sums[C + c + 0] / n_total), mx1 = (float)(sums[C + c + 1] / n_total);
+      float mx2 = (float)(sums[C + c + 2] / n_total), mx3 = (float)(sums[C + c + 3] / n_total);
+      float4 o;
+      o.x = (gv.x - mg0 - (xv.x - m.x) * s.x * mx0) * (ga.x * s.x);
+      o.y = (gv.y - mg1 - (xv.y - m.y) * s.y * mx1) * (ga.y * s.y);
+      o.z = (gv.z - mg2 - (xv.z - m.z) * s.z * mx2) * (ga.z * s.z);
+      o.w = (gv.w - mg3 - (xv.w - m.w) * s.w * mx3) * (ga.w * s.w);
+      reinterpret_cast<float4*>(dx)[i] = o;
+    } else {
+      float mg = (float)(sums[cv] / n_total), mx = (float)(sums[C + cv] / n_total);
+      float s = __ldg(invstd + cv);
+      dx[i] = (g[i] - mg - (x[i] - __ldg(mean + cv)) * s * mx) * (__ldg(gamma + cv) * s);
+    }
+  }
+}
+
+void k_bn_bwd_apply(St st, const float* g, const float* x, float* dx, int64_t P, int C, const float* gamma,
+                    const float* mean, const float* invstd, const double* sums_total, double n_total) {
+  if (C % 4 == 0) {
+    int64_t tv = P * (C / 4);
+    bn_bwd_apply_kernel<4><<<ew_grid(tv * 4), 256, 0, st.s>>>(g, x, dx, tv, C / 4, C, gamma, mean, invstd, sums_total, n_total);
+  } else {
+    int64_t tv = P * C;
+    bn_bwd_apply_kernel<1><<<ew_grid(tv * 4), 256, 0, st.s>>>(g, x, dx, tv, C, C, gamma, mean, invstd, sums_total, n_total);
+  }
+  DSR_LAUNCHED(st, "bn_bwd_apply", 12.0 * P * C, WORK_BYTES);
+}
+
+// ------------------------------------------------------------------------------------------
+// nearest up-sampling, 2x2 box down-sample (NHWC, one thread per output element)
+// ------------------------------------------------------------------------------------------
+__global__ void upnearest_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C, int s) {
+  int Ho = H * s, Wo = W * s;
+  int64_t total = (int64_t)N * Ho * Wo * C;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int c = (int)(i % C);
+    int64_t p = i / C;
+    int ox = (int)(p % Wo); p /= Wo;
+    int oy = (int)(p % Ho);
+    int n = (int)(p / Ho);
+    y[i] = x[(((int64_t)n * H + oy / s) * W + ox / s) * C + c];
+  }
+}
+__global__ void upnearest_bwd_kernel(const float* __restrict__ dy, float* __restrict__ dx, int N, int H, int W, int C, int s) {
+  int Ho = H * s, Wo = W * s;
+  int64_t total = (int64_t)N * H * W * C;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int c = (int)(i % C);
+    int64_t p = i / C;
+    int ix = (int)(p % W); p /= W;
+    int iy = (int)(p % H);
+    int n = (int)(p / H);
+    float a = 0.f;
+    for (int u = 0; u < s; ++u)
+      for (int v = 0; v < s; ++v) a += dy[(((int64_t)n * Ho + iy * s + u) * Wo + ix * s + v) * C + c];
+    dx[i] = a;
+  }
+}
+// (a[2i,2j] + a[2i+1,2j] + a[2i,2j+1] + a[2i+1,2j+1]) / 4 -- the association order of train.lua:227-229
+__global__ void avgpool2_kernel(const float* __restrict__ x, float* __restrict__ y, int N, int H, int W, int C) {
+  int Ho = H / 2, Wo = W / 2;
+  int64_t total = (int64_t)N * Ho * Wo * C;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int c = (int)(i % C);
+    int64_t p = i / C;
+    int ox = (int)(p % Wo); p /= Wo;
+    int oy = (int)(p % Ho);
+    int n = (int)(p / Ho);
+    const float* b = x + (((int64_t)n * H + 2 * oy) * W + 2 * ox) * C + c;
+    float a00 = b[0], a10 = b[(int64_t)W * C], a01 = b[C], a11 = b[(int64_t)W * C + C];
+    y[i] = (((a00 + a10) + a01) + a11) / 4.f;
+  }
+}
+static inline int sc_grid(int64_t total) {
+  int64_t want = (total + 255) / 256;
+  int64_t cap = NSM * 16;
+  if (want < 1) want = 1;
+  return (int)(want < cap ? want : cap);
+}
+void k_upnearest_fwd(St st, const float* x, float* y, int N, int H, int W, int C, int scale) {
+  upnearest_fwd_kernel<<<sc_grid((int64_t)N * H * W * C * scale * scale), 256, 0, st.s>>>(x, y, N, H, W, C, scale);
+  DSR_LAUNCHED(st, "upnearest_fwd", 4.0 * N * H * W * C * (1 + scale * scale), WORK_BYTES);
+}
+void k_upnearest_bwd(St st, const float* dy, float* dx, int N, int H, int W, int C, int scale) {
+  upnearest_bwd_kernel<<<sc_grid((int64_t)N * H * W * C), 256, 0, st.s>>>(dy, dx, N, H, W, C, scale);
+  DSR_LAUNCHED(st, "upnearest_bwd", 4.0 * N * H * W * C * (1 + scale * scale), WORK_BYTES);
+}
+void k_avgpool2(St st, const float* x, float* y, int N, int H, int W, int C) {
+  avgpool2_kernel<<<sc_grid((int64_t)N * (H / 2) * (W / 2) * C), 256, 0, st.s>>>(x, y, N, H, W, C);
+  DSR_LAUNCHED(st, "avgpool2", 5.0 * N * H * W * C, WORK_BYTES);
+}
+
+// ------------------------------------------------------------------------------------------
+// criteria (count = nElement of D's output: small) -- one CTA, deterministic, evaluated in double
+// like THNN's BCECriterion (eps 1e-12) / MSECriterion with sizeAverage = true.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) loss_kernel(int kind, const float* __restrict__ x, int64_t count,
+                                                    const float* __restrict__ label_vec, int64_t per, float label_const,
+                                                    double n_total, float* __restrict__ loss_out, float* __restrict__ dx) {
+  __shared__ double red[1024];
+  const double eps = 1e-12;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < count; i += 1024) {
+    double t = label_vec ? (double)label_vec[i / per] : (double)label_const;
+    double xd = (double)x[i];
+    double l, g;
+    if (kind == LOSS_BCE) {
+      l = -(t * log(xd + eps) + (1.0 - t) * log(1.0 - xd + eps));
+      g = -(t - xd) / ((1.0 - xd + eps) * (xd + eps)) / n_total;
+    } else {
+      double d = xd - t;
+      l = d * d;
+      g = 2.0 * d / n_total;
+    }
+    acc += l;
+    if (dx) dx[i] = (float)g;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 512; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) loss_out[0] = (float)(red[0] / n_total);
+}
+void k_loss(St st, int kind, const float* x, int64_t count, const float* label_vec, int64_t per, float label_const,
+            double n_total, float* loss_out, float* dx) {
+  loss_kernel<<<1, 1024, 0, st.s>>>(kind, x, count, label_vec, per > 0 ? per : 1, label_const, n_total, loss_out, dx);
+  DSR_LAUNCHED(st, "criterion", 8.0 * count, WORK_BYTES);
+}
+
+// per-sample sum((real - fake)^2) / div  -> becomes D's target on the fake pass (train.lua:237-245)
+__global__ void __launch_bounds__(256) pixel_mse_kernel(const float* __restrict__ real, const float* __restrict__ fake,
+                                                        float* __restrict__ out, int64_t per_sample, float div) {
+  __shared__ double red[256];
+  const float* r = real + (int64_t)blockIdx.x * per_sample;
+  const float* f = fake + (int64_t)blockIdx.x * per_sample;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < per_sample; i += 256) {
+    float d = r[i] - f[i];
+    acc += (double)d * (double)d;
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) {
+    if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[blockIdx.x] = (float)(red[0] / (double)div);
+}
+void k_pixel_mse(St st, const float* real, const float* fake, float* out, int n, int64_t per_sample, float div) {
+  pixel_mse_kernel<<<n, 256, 0, st.s>>>(real, fake, out, per_sample, div);
+  DSR_LAUNCHED(st, "pixel_mse", 8.0 * n * per_sample, WORK_BYTES);
+}
+
+// ------------------------------------------------------------------------------------------
+// optim.adam (Torch7 form): x -= lr*sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v) + eps)
+// 28 B/param: read p,g,m,v ; write p,m,v -- one pass (the reference issues 7 tensor ops).
+// ------------------------------------------------------------------------------------------
+__global__ void adam_prep_kernel(int64_t* t, float* step, double lr, double b1, double b2) {
+  int64_t tt = *t + 1;
+  *t = tt;
+  double bc1 = 1.0 - pow(b1, (double)tt);
+  double bc2 = 1.0 - pow(b2, (double)tt);
+  *step = (float)(lr * sqrt(bc2) / bc1);
+}
+void k_adam_prep(St st, int64_t* dev_t, float* dev_step, double lr, double beta1, double beta2) {
+  adam_prep_kernel<<<1, 1, 0, st.s>>>(dev_t, dev_step, lr, beta1, beta2);
+  DSR_LAUNCHED(st, "adam_prep", 16.0, WORK_BYTES);
+}
+
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, int64_t count, const float* __restrict__ step_p,
+                                                   float b1, float b2, float omb1, float omb2, float eps) {
+  const float step = __ldg(step_p);
+  int64_t n4 = count >> 2;
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i = i0; i < n4; i += stride) {
+    float4 pv = reinterpret_cast<float4*>(p)[i];
+    float4 gv = reinterpret_cast<const float4*>(g)[i];
+    float4 mv = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    mv.x = mv.x * b1 + omb1 * gv.x; mv.y = mv.y * b1 + omb1 * gv.y;
+    mv.z = mv.z * b1 + omb1 * gv.z; mv.w = mv.w * b1 + omb1 * gv.w;
+    vv.x = vv.x * b2 + omb2 * gv.x * gv.x; vv.y = vv.y * b2 + omb2 * gv.y * gv.y;
+    vv.z = vv.z * b2 + omb2 * gv.z * gv.z; vv.w = vv.w * b2 + omb2 * gv.w * gv.w;
+    pv.x -= step * (mv.x / (sqrtf(vv.x) + eps)); pv.y -= step * (mv.y / (sqrtf(vv.y) + eps));
+    pv.z -= step * (mv.z / (sqrtf(vv.z) + eps)); pv.w -= step * (mv.w / (sqrtf(vv.w) + eps));
+    reinterpret_cast<float4*>(p)[i] = pv;
+    reinterpret_cast<float4*>(m)[i] = mv;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+  for (int64_t i = (n4 << 2) + i0; i < count; i += stride) {
+    float gg = g[i];
+    float mm = m[i] * b1 + omb1 * gg;
+    float vv = v[i] * b2 + omb2 * gg * gg;
+    p[i] -= step * (mm / (sqrtf(vv) + eps));
+    m[i] = mm;
+    v[i] = vv;
+  }
+}
+void k_adam(St st, float* p, const float* g, float* m, float* v, int64_t count, const float* dev_step,
+              double beta1, double beta2, double eps) {
+  if (count <= 0) return;
+  adam_kernel<<<ew_grid(count), 256, 0, st.s>>>(p, g, m, v, count, dev_step, (float)beta1, (float)beta2,
+                                                 (float)(1.0 - beta1), (float)(1.0 - beta2), (float)eps);
+  DSR_LAUNCHED(st, "adam", 28.0 * count, WORK_BYTES);
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void fill_kernel(float* __restrict__ p, int64_t count, float v) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) p[i] = v;
+}
+void k_fill(St st, float* p, int64_t count, float v) {
+  if (count <= 0) return;
+  fill_kernel<<<sc_grid(count), 256, 0, st.s>>>(p, count, v);
+  DSR_LAUNCHED(st, "fill", 4.0 * count, WORK_BYTES);
+}
+__global__ void scale_kernel(float* __restrict__ p, int64_t count, float s) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) p[i] *= s;
+}
+void k_scale(St st, float* p, int64_t count, float s) {
+  if (count <= 0) return;
+  scale_kernel<<<sc_grid(count), 256, 0, st.s>>>(p, count, s);
+  DSR_LAUNCHED(st, "scale", 8.0 * count, WORK_BYTES);
+}
+// L2 flush: write a buffer larger than L2 (bench hygiene)
+__global__ void flush_kernel(float4* __restrict__ p, int64_t n4) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) p[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+void k_flush(St st, float* buf, int64_t count) {
+  flush_kernel<<<NSM * 8, 256, 0, st.s>>>(reinterpret_cast<float4*>(buf), count / 4);
+  DSR_LAUNCHED(st, "l2_flush", 4.0 * count, WORK_BYTES);
+}
