@@ -239,6 +239,20 @@ class Sequential:
     def update_grad_input(self, x, dy):
         return self._walk_back(x, dy, acc=False)
 
+    def kink_margin(self):
+        """Conditioning probe for the parity tests: the smallest |pre-activation| / max|pre-activation| over all
+        ReLU / LeakyReLU inputs of the last forward.  An element within float32 rounding (~1e-7) of the kink may
+        take the other branch in ANY float32 implementation (Torch7 included), which changes the gradients at the
+        1e-3 level -- a property of the network, not of an implementation."""
+        m = float("inf")
+        for mod in self.modules:
+            if isinstance(mod, Act) and mod.akind in (ops.ACT_RELU, ops.ACT_LRELU) and mod.input is not None:
+                a = mod.input.abs()
+                mx = float(a.max())
+                if mx > 0:
+                    m = min(m, float(a.min()) / mx)
+        return m
+
 
 def weights_init(net: Sequential, seed: int):
     """weights_init (train.lua:42-51): conv ~N(0,.02) bias-free, BN gamma~N(1,.02), beta=0.

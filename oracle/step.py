@@ -81,16 +81,23 @@ def train_step(netG: Sequential, netD: Sequential, stG: AdamState, stD: AdamStat
     """One iteration of the reference loop.  Returns (errD_real, errD_fake, errG)."""
     B = real.shape[0]
     real = real.to(netD.dtype)
+    margin = [float("inf")]
+
+    def probe(net):
+        if trace is not None:
+            margin[0] = min(margin[0], net.kink_margin())
 
     # ---------------- fDx (train.lua:208-253) ----------------
     netD.zero_grad_parameters()
     out = netD.forward(real)
+    probe(netD)
     lab = _labels_like(out, cfg.real_label, B)
     errD_real, df_do = _crit(cfg.family, out, lab)
     netD.backward(real, df_do)
 
     lr_img = ops.avgpool2_fwd(real)                      # train.lua:225-230
     fake = netG.forward(lr_img)                          # :233-234
+    probe(netG)
 
     if cfg.pixel_label:
         pm = ops.pixel_mse_per_sample(real, fake, cfg.pixel_div)   # :237-239
@@ -99,6 +106,7 @@ def train_step(netG: Sequential, netD: Sequential, stG: AdamState, stD: AdamStat
         fake_target = cfg.fake_label
 
     out = netD.forward(fake)                             # :242-243 (cached acts = FAKE pass)
+    probe(netD)
     lab = _labels_like(out, fake_target, B)
     errD_fake, df_do = _crit(cfg.family, out, lab)
     netD.backward(fake, df_do)                           # grads accumulate (F6)
@@ -120,6 +128,7 @@ def train_step(netG: Sequential, netD: Sequential, stG: AdamState, stD: AdamStat
     if trace is not None:
         trace["gradG"] = netG.get_flat_grads().clone()
         trace["df_dg"] = df_dg.clone()
+        trace["kink_margin"] = margin[0]
 
     adam_apply(netG, stG, cfg)                           # optim.adam(fGx, ...) :283
     return errD_real, errD_fake, errG

@@ -1,0 +1,101 @@
+"""CPU tests of the drop-in boundary: libdcgansr.so loads, exports every symbol include/dcgansr.h declares,
+plan-only nets (no GPU) reproduce the reference's shapes and parameter counts, and compute entry points fail
+loudly without a device (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import dcgan_super_resolution_b200 as dsr
+from dcgan_super_resolution_b200 import _lib as L
+from dcgan_super_resolution_b200 import init, models
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "dcgansr.h")
+
+
+def header_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dcgansr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_parses_as_plain_c():
+    r = subprocess.run(["gcc", "-std=c99", "-fsyntax-only", "-Wall", "-Werror", "-x", "c", HEADER], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_library_exports_every_declared_symbol():
+    lib = L.load()
+    names = header_functions()
+    assert len(names) >= 45
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in dcgansr.h but not exported"
+    assert sorted(L.symbols()) == names, "ctypes binding and header disagree"
+    assert lib.dcgansr_version() >= 100
+
+
+def test_struct_layouts_match_header():
+    # sizes the C compiler gives the three boundary structs
+    code = '#include <stdio.h>\n#include "dcgansr.h"\nint main(){printf("%zu %zu %zu", sizeof(dcgansr_cfg), sizeof(dcgansr_layer), sizeof(dcgansr_step_cfg));return 0;}'
+    exe = "/tmp/_dsr_sizes"
+    r = subprocess.run(["gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe], input=code, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    sizes = list(map(int, subprocess.run([exe], capture_output=True, text=True).stdout.split()))
+    assert sizes == [C.sizeof(L.Cfg), C.sizeof(L.Layer), C.sizeof(L.StepCfg)]
+
+
+@pytest.mark.parametrize("name,gparams,dparams", [("C3a", 102312, 2765568), ("C1a", 84384, 371008), ("C2", 42240, 2763520),
+                                                  ("C1b", 1320576, 371008), ("C5", 11069184, 11036160)])
+def test_plan_only_nets_match_survey_counts(name, gparams, dparams):
+    cfg = models.config(name)
+    hr, nc = cfg["hr"], cfg["nc"]
+    G = dsr.Sequential.from_specs(cfg["G"]).cuda(None, (nc, hr // 2, hr // 2), 4)
+    D = dsr.Sequential.from_specs(cfg["D"]).cuda(None, (nc, hr, hr), 4)
+    assert G.num_params() == gparams and D.num_params() == dparams
+    assert G.out_shape() == (nc, hr, hr)
+    assert init.weights_init(cfg["G"], 1).size == gparams
+    G.close(); D.close()
+
+
+def test_d_output_shapes_at_baseline_sizes():
+    # at BASELINE sizes D no longer ends at 1x1
+    for name, want in (("C1a", (1, 1, 1)), ("C1b", (1, 25, 25)), ("C3a", (1, 1, 1)), ("C3b", (1, 5, 5)), ("C5", (1, 13, 13))):
+        cfg = models.config(name)
+        D = dsr.Sequential.from_specs(cfg["D"]).cuda(None, (cfg["nc"], cfg["hr"], cfg["hr"]), 2)
+        assert D.out_shape() == want, name
+        D.close()
+
+
+def test_bad_descriptions_are_rejected():
+    bad = [dict(kind="conv", cin=3, cout=8, k=4, s=2, p=1), dict(kind="bn", c=16)]           # BN channel mismatch
+    with pytest.raises(dsr.DcgansrError):
+        dsr.Sequential.from_specs(bad).cuda(None, (3, 8, 8), 2)
+    with pytest.raises(dsr.DcgansrError):
+        dsr.Sequential.from_specs([dict(kind="conv", cin=3, cout=8, k=9, s=1, p=0)]).cuda(None, (3, 16, 16), 2)   # 9x9 kernel
+    with pytest.raises(dsr.DcgansrError):
+        dsr.Sequential.from_specs([dict(kind="conv", cin=4, cout=8, k=3, s=1, p=0)]).cuda(None, (3, 16, 16), 2)   # cin mismatch
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present: this checks the no-GPU behaviour")
+    with pytest.raises(dsr.DcgansrError, match="no CPU fallback"):
+        dsr.Context(device=0)
+    net = dsr.Sequential.from_specs(models.patch_D(8)).cuda(None, (1, 8, 8), 2)
+    with pytest.raises(dsr.DcgansrError):
+        net.forward(np.zeros((2, 1, 8, 8), np.float32))       # plan-only net cannot compute
+    net.close()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "dcgan_super_resolution_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
