@@ -70,6 +70,7 @@ struct dcgansr_ctx {
   ncclComm_t comm = nullptr;
   // CUDA graphs of the step (cfg.use_graph), one per (nets, staged batch, batch size, step cfg)
   std::vector<GraphEntry> graphs;
+  bool tc_failed = false;
   Prof prof;
   St st() { return St{stream, &launches, &prof}; }
   int world() const { return cfg.world_size > 1 && comm ? cfg.world_size : 1; }
@@ -88,6 +89,7 @@ static int fail(dcgansr_ctx* ctx, int code, const std::string& msg) {
   } while (0)
 #define CKLAST(ctx)                                                                                       \
   do {                                                                                                    \
+    if ((ctx) && (ctx)->tc_failed) { (ctx)->tc_failed = false; t_err = (ctx)->err; return DCGANSR_ERR_CUDA; } \
     cudaError_t e_ = cudaGetLastError();                                                                  \
     if (e_ != cudaSuccess)                                                                                \
       return fail(ctx, DCGANSR_ERR_CUDA, std::string("kernel launch: ") + cudaGetErrorString(e_));        \
@@ -252,8 +254,15 @@ struct ConvPlan {
   }
 
   int alloc_device(dcgansr_ctx* ctx) {
+    const bool fast = ctx->cfg.precision == DCGANSR_FAST_TF32;
     for (auto* v : {&fwd, &dgrad})
       for (auto& c : *v) {
+        if (fast) {
+          TapGeom g = c.g;
+          g.N = 1;
+          if (tc_tapconv_supported(g))
+            CK(ctx, cudaMalloc((void**)&c.bp, std::max<size_t>(tc_packed_elems(c.g.ntaps, c.A, c.B), 4) * sizeof(float)));
+        }
         size_t n = std::max<size_t>(c.tapidx.size(), 1);
         CK(ctx, cudaMalloc((void**)&c.tapidx_dev, n * sizeof(int)));
         if (!c.tapidx.empty())
@@ -276,13 +285,23 @@ struct ConvPlan {
   void pack(St st, const float* master) {
     for (auto* v : {&fwd, &dgrad})
       for (auto& c : *v)
-        if (c.g.ntaps > 0) k_pack_taps(st, master, c.wp, c.g.ntaps, c.tapidx_dev, c.A, c.B, c.sa, c.sb);
+        if (c.g.ntaps > 0) {
+          if (c.bp) k_pack_taps_tc(st, master, c.bp, c.g.ntaps, c.tapidx_dev, c.A, c.B, c.sa, c.sb);
+          else k_pack_taps(st, master, c.wp, c.g.ntaps, c.tapidx_dev, c.A, c.B, c.sa, c.sb);
+        }
   }
   static void run_classes(dcgansr_ctx* ctx, std::vector<TapClass>& v, const float* in, float* out, int N, int act, float neg) {
     for (auto& c : v) {
       if (c.g.Hg <= 0 || c.g.Wg <= 0) continue;
       TapGeom g = c.g;
       g.N = N;
+      if (c.bp) {
+        std::string e;
+        if (k_tapconv_tc(ctx->st(), g, in, c.bp, out, act, neg, &e)) continue;
+        ctx->err = "tcgen05 path: " + e;       // surfaced by the caller's CKLAST / status
+        ctx->tc_failed = true;
+        continue;
+      }
       k_tapconv_simt(ctx->st(), g, in, c.wp, out, act, neg);
     }
   }
@@ -519,6 +538,10 @@ int dcgansr_ctx_create(const dcgansr_cfg* cfg, dcgansr_ctx** out) {
   CK(nullptr, cudaGetDeviceProperties(&prop, cfg->device));
   if (prop.major != 10)
     return fail(nullptr, DCGANSR_ERR_UNSUPPORTED, std::string("libdcgansr is built for sm_100a only; device is ") + prop.name);
+  if (cfg->precision == DCGANSR_FAST_TF32) {
+    std::string e;
+    if (!tc_init(&e)) return fail(nullptr, DCGANSR_ERR_UNSUPPORTED, e);
+  }
   dcgansr_ctx* ctx = new dcgansr_ctx();
   ctx->cfg = *cfg;
   if (ctx->cfg.world_size < 1) ctx->cfg.world_size = 1;
