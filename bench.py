@@ -110,8 +110,7 @@ def oracle_step_rate(workload, sample_batch, min_seconds, max_steps, threads=Non
     from dcgan_super_resolution_b200 import models
     from oracle import nets as onets
     from oracle import step as ostep
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or os.cpu_count() or 1)      # torchrun pins OMP_NUM_THREADS=1: undo for the CPU arm
     cfg = models.config(workload)
     oG = onets.weights_init(onets.Sequential(cfg["G"], torch.float32), 4321)
     oD = onets.weights_init(onets.Sequential(cfg["D"], torch.float32), 8765)
@@ -141,6 +140,7 @@ def reference_arm(args):
     import torch
     from oracle import nets as onets
     from oracle import step as ostep
+    torch.set_num_threads(os.cpu_count() or 1)                  # all host threads (torchrun pins OMP_NUM_THREADS=1)
     oG = onets.weights_init(onets.Sequential(cfg["G"], torch.float32), 4321)
     oD = onets.weights_init(onets.Sequential(cfg["D"], torch.float32), 8765)
     stG, stD = ostep.new_adam_state(oG), ostep.new_adam_state(oD)
@@ -248,7 +248,7 @@ def main():
         dsr.train_step_staged(ctx, G, D, scfg, i % NPOOL, B)
     barrier()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if rank == 0 and not os.environ.get("DCGANSR_NO_SAMPLER"):
         sampler.start()
         time.sleep(0.25)
     l0 = ctx.launch_count()
@@ -287,10 +287,31 @@ def main():
         prof = ctx.profile_end()
     barrier()
 
+    if os.environ.get("DCGANSR_DEBUG_LEGS"):
+        for label, sync_each in (("staged-async", False), ("staged-sync-each-step", True)):
+            barrier()
+            ctx.timer_begin()
+            for i in range(args.steps):
+                dsr.train_step_staged(ctx, G, D, scfg, i % NPOOL, B, want_losses=sync_each)
+            t = ctx.timer_end()
+            barrier()
+            sys.stderr.write(f"[rank {rank}] {label}: {t / args.steps:.3f} ms/step\n")
+
+    def teardown():
+        # orderly: every rank destroys its communicator at the same point, then leaves without waiting for
+        # interpreter-exit destructors (a lingering NCCL / process-group thread must never hang the driver)
+        sys.stdout.flush()
+        sys.stderr.flush()
+        barrier()
+        try:
+            G.close()
+            D.close()
+            ctx.close()
+        finally:
+            os._exit(0)
+
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
-        return 0
+        teardown()
 
     peaks = load_peaks()
     total_ms = sum(p["ms"] for p in prof) or 1.0
@@ -368,11 +389,7 @@ def main():
         "cpu_baseline": cpu,
     }
     print(json.dumps(line))
-    G.close()
-    D.close()
-    ctx.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    teardown()
     return 0
 
 

@@ -122,6 +122,8 @@ void k_tapconv_simt(St st, const TapGeom& g, const float* in, const float* wp, f
 size_t wgrad_simt_scratch_bytes(const WgradGeom& g);
 void k_wgrad_simt(St st, const WgradGeom& g, const float* P, const float* Q, float* grad_master,
                   float* scratch, size_t scratch_bytes);
+// grad_master[cp*(Cq*T) + cq*T + t] += sum_s scratch[s][cp][t*Cq + cq]   (fixed order)
+void k_wgrad_reduce(St st, const float* scratch, int S, int Cp, int Cq, int T, float* grad_master);
 
 // ---- kernels_tc.cu : tcgen05 / TMA / TMEM implicit-GEMM convolutions (FAST_TF32) --------------
 bool tc_init(std::string* err);                       // resolves cuTensorMapEncodeTiled
@@ -133,3 +135,7 @@ void k_pack_taps_tc(St st, const float* master, float* bp, int ntaps, const int*
 // returns false (with err) if the launch could not be configured
 bool k_tapconv_tc(St st, const TapGeom& g, const float* in, const float* bp, float* out, int act, float negval,
                   std::string* err);
+bool tc_wgrad_supported(const WgradGeom& g);
+size_t wgrad_tc_scratch_bytes(const WgradGeom& g);
+bool k_wgrad_tc(St st, const WgradGeom& g, const float* P, const float* Q, float* grad_master, float* scratch, size_t scratch_bytes,
+                std::string* err);

@@ -255,6 +255,7 @@ struct ConvPlan {
 
   int alloc_device(dcgansr_ctx* ctx) {
     const bool fast = ctx->cfg.precision == DCGANSR_FAST_TF32;
+    this->fast = fast;
     for (auto* v : {&fwd, &dgrad})
       for (auto& c : *v) {
         if (fast) {
@@ -307,17 +308,28 @@ struct ConvPlan {
   }
   void forward(dcgansr_ctx* ctx, const float* in, float* out, int N, int act, float neg) { run_classes(ctx, fwd, in, out, N, act, neg); }
   void dgrad_run(dcgansr_ctx* ctx, const float* dy, float* dx, int N) { run_classes(ctx, dgrad, dy, dx, N, ACT_NONE, 0.f); }
+  bool fast = false;       // FAST_TF32: tensor-core wgrad when the geometry allows
   size_t wscratch_bytes(int N) const {
     WgradGeom g = wg;
     g.N = N;
-    return wgrad_simt_scratch_bytes(g);
+    size_t b = wgrad_simt_scratch_bytes(g);
+    if (fast && tc_wgrad_supported(g)) b = std::max(b, wgrad_tc_scratch_bytes(g));
+    return b;
   }
   // x: module input, dy: gradient w.r.t. module output
   void wgrad_run(dcgansr_ctx* ctx, const float* x, const float* dy, float* grad_master, int N, float* scratch, size_t scratch_bytes) {
     WgradGeom g = wg;
     g.N = N;
-    if (!full) k_wgrad_simt(ctx->st(), g, dy, x, grad_master, scratch, scratch_bytes);
-    else k_wgrad_simt(ctx->st(), g, x, dy, grad_master, scratch, scratch_bytes);
+    const float* Pp = full ? x : dy;
+    const float* Qp = full ? dy : x;
+    if (fast && tc_wgrad_supported(g)) {
+      std::string e;
+      if (k_wgrad_tc(ctx->st(), g, Pp, Qp, grad_master, scratch, scratch_bytes, &e)) return;
+      ctx->err = "tcgen05 wgrad: " + e;
+      ctx->tc_failed = true;
+      return;
+    }
+    k_wgrad_simt(ctx->st(), g, Pp, Qp, grad_master, scratch, scratch_bytes);
   }
 };
 

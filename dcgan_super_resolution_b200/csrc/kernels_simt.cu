@@ -385,9 +385,14 @@ void k_wgrad_simt(St st, const WgradGeom& g, const float* P, const float* Q, flo
   else if (vq) wgrad_simt_kernel<false, true><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
   else wgrad_simt_kernel<false, false><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
   DSR_LAUNCHED(st, "wgrad_simt", 2.0 * g.N * g.Hp * g.Wp * g.Cp * g.Cq * g.ntaps, WORK_FLOPS);
-  int64_t total = (int64_t)g.Cp * g.Cq * g.ntaps;
+  k_wgrad_reduce(st, scratch, c.S, g.Cp, g.Cq, g.ntaps, grad_master);
+}
+
+void k_wgrad_reduce(St st, const float* scratch, int S, int Cp, int Cq, int T, float* grad_master) {
+  int64_t total = (int64_t)Cp * Cq * T;
   int64_t blocks = (total + 255) / 256;
   if (blocks > NSM * 8) blocks = NSM * 8;
-  wgrad_reduce_kernel<<<(int)blocks, 256, 0, st.s>>>(scratch, c.S, g.Cp, g.Cq, g.ntaps, grad_master);
-  DSR_LAUNCHED(st, "wgrad_reduce", 4.0 * total * (c.S + 2), WORK_BYTES);
+  if (blocks < 1) blocks = 1;
+  wgrad_reduce_kernel<<<(int)blocks, 256, 0, st.s>>>(scratch, S, Cp, Cq, T, grad_master);
+  DSR_LAUNCHED(st, "wgrad_reduce", 4.0 * total * (S + 2), WORK_BYTES);
 }

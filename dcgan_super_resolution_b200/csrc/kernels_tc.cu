@@ -411,3 +411,291 @@ bool k_tapconv_tc(St st, const TapGeom& g, const float* in, const float* bp, flo
   DSR_LAUNCHED(st, "tapconv_tc", 2.0 * g.N * g.Hg * g.Wg * g.ntaps * g.Ci * g.Co, WORK_FLOPS);
   return true;
 }
+
+
+// ==========================================================================================
+// wgrad on tensor cores.
+//
+//   acc[t][cp][cq] = sum_pix P[pix][cp] * Q[shift_t(pix)][cq]
+//
+// per tap t a GEMM  D_t[M = 128 cp][N = cq] += A[K = pixels][M]^T * B_t[K = pixels][N]  with BOTH operands
+// MN-major in shared memory: the TMA boxes of the NHWC tensors ([pixels][channels], channels contiguous)
+// are used as they land, no transpose.  One CTA owns a 128-channel slice of cp, a slice of cq, a group of
+// TG taps (TG * N columns of TMEM, one accumulator per tap) and a range of pixel tiles (split-K); the P tile
+// of a pixel tile stays resident in smem while the TG shifted Q tiles stream through a second ring.
+// Partials go to scratch[split][cp][t*Cq + cq]; k_wgrad_reduce adds them into the Torch7-layout master
+// gradient in a fixed order (deterministic).
+// ==========================================================================================
+struct WgParams {
+  int Cp, Cq, ntaps, s;
+  int TW, TH, TB, tiles_x, tiles_y, ntiles, tiles_per_split;
+  int KPIX, kbp, kbq, atoms_p, atoms_q, n_mma, TG, tmem_cols;
+  int p_stage_bytes, q_stage_bytes, np_stage, nq_stage;
+  int q_tiles;                 // number of cq slices (blockIdx.z = mtile * q_tiles + qtile)
+  long long split_stride;      // Cp * ntaps * Cq
+  short oy[DSR_MAX_TAPS], ox[DSR_MAX_TAPS], py[DSR_MAX_TAPS], px[DSR_MAX_TAPS];
+};
+
+// MN-major TF32 shared-memory matrix descriptor.  The only layout the tensor core accepts for MN-major 32-bit
+// operands is SWIZZLE_128B_BASE32B (32-byte chunks swizzled inside 128-byte rows, period 4 rows) -- what
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B produces.  Rows (= K = pixels) are 128 B = 32 channels; 4-row groups
+// every SBO = 512 B; the next 32 channels (MN atom) every `lbo` bytes.
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t saddr, int kb, uint32_t lbo) {
+  (void)kb;
+  uint32_t sbo = 4u * 128u;
+  uint64_t layout = 1ull;                                                     // SWIZZLE_128B_BASE32B
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(sbo >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(TC_THREADS) wgrad_tc_kernel(const __grid_constant__ CUtensorMap mapP,
+                                                              const __grid_constant__ CUtensorMap mapQ, const WgParams p,
+                                                              float* __restrict__ scratch) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sP = smem;
+  uint8_t* sQ = smem + (size_t)p.np_stage * p.p_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sQ + (size_t)p.nq_stage * p.q_stage_bytes);
+  uint64_t* p_full = bars;
+  uint64_t* p_empty = p_full + p.np_stage;
+  uint64_t* q_full = p_empty + p.np_stage;
+  uint64_t* q_empty = q_full + p.nq_stage;
+  uint64_t* tmem_full = q_empty + p.nq_stage;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int split = blockIdx.x;
+  const int t0 = blockIdx.y * p.TG;
+  const int tg_n = min(p.TG, p.ntaps - t0);
+  const int mtile = blockIdx.z / p.q_tiles, qtile = blockIdx.z % p.q_tiles;
+  const int m0 = mtile * 128, q0 = qtile * p.n_mma;
+  const int tile_beg = split * p.tiles_per_split;
+  const int tile_end = min(p.ntiles, tile_beg + p.tiles_per_split);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapP) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapQ) : "memory");
+    for (int i = 0; i < p.np_stage; ++i) { mbar_init(smem_u32(&p_full[i]), 1); mbar_init(smem_u32(&p_empty[i]), 1); }
+    for (int i = 0; i < p.nq_stage; ++i) { mbar_init(smem_u32(&q_full[i]), 1); mbar_init(smem_u32(&q_empty[i]), 1); }
+    mbar_init(smem_u32(tmem_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int ps = 0, qs = 0;
+      uint32_t pph = 0, qph = 0;
+      const uint32_t p_atom = (uint32_t)(p.KPIX * p.kbp * 4), q_atom = (uint32_t)(p.KPIX * p.kbq * 4);
+      for (int tile = tile_beg; tile < tile_end; ++tile) {
+        int tt = tile;
+        const int tx = tt % p.tiles_x; tt /= p.tiles_x;
+        const int ty = tt % p.tiles_y; tt /= p.tiles_y;
+        const int b0 = tt * p.TB, gy0 = ty * p.TH, gx0 = tx * p.TW;
+        mbar_wait(smem_u32(&p_empty[ps]), pph ^ 1);
+        const uint32_t pf = smem_u32(&p_full[ps]);
+        mbar_expect_tx(pf, p_atom * p.atoms_p);
+        for (int a = 0; a < p.atoms_p; ++a)
+          tma_load_4d(smem_u32(sP + (size_t)ps * p.p_stage_bytes) + a * p_atom, &mapP, pf, m0 + a * p.kbp, gx0, gy0, b0);
+        if (++ps == p.np_stage) { ps = 0; pph ^= 1; }
+        for (int tg = 0; tg < tg_n; ++tg) {
+          const int t = t0 + tg;
+          mbar_wait(smem_u32(&q_empty[qs]), qph ^ 1);
+          const uint32_t qf = smem_u32(&q_full[qs]);
+          mbar_expect_tx(qf, q_atom * p.atoms_q);
+          const uint32_t dq = smem_u32(sQ + (size_t)qs * p.q_stage_bytes);
+          for (int a = 0; a < p.atoms_q; ++a) {
+            if (p.s == 1)
+              tma_load_4d(dq + a * q_atom, &mapQ, qf, q0 + a * p.kbq, gx0 + p.ox[t], gy0 + p.oy[t], b0);
+            else
+              tma_load_5d(dq + a * q_atom, &mapQ, qf, p.px[t] * p.Cq + q0 + a * p.kbq, gx0 + p.ox[t], p.py[t], gy0 + p.oy[t], b0);
+          }
+          if (++qs == p.nq_stage) { qs = 0; qph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // D = f32, A = B = tf32, both MN-major (bits 15, 16), N = n_mma, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.n_mma >> 3) << 17) | ((128u >> 4) << 24);
+    int ps = 0, qs = 0;
+    uint32_t pph = 0, qph = 0;
+    const uint32_t lbo_p = (uint32_t)(p.KPIX * p.kbp * 4), lbo_q = (uint32_t)(p.KPIX * p.kbq * 4);
+    const uint32_t kstep_p = (uint32_t)(8 * p.kbp * 4), kstep_q = (uint32_t)(8 * p.kbq * 4);
+    const int ksteps = p.KPIX >> 3;
+    for (int tile = tile_beg; tile < tile_end; ++tile) {
+      mbar_wait(smem_u32(&p_full[ps]), pph);
+      const uint32_t pa = smem_u32(sP + (size_t)ps * p.p_stage_bytes);
+      for (int tg = 0; tg < tg_n; ++tg) {
+        mbar_wait(smem_u32(&q_full[qs]), qph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t qa = smem_u32(sQ + (size_t)qs * p.q_stage_bytes);
+          for (int k = 0; k < ksteps; ++k)
+            umma_tf32(tmem_base + (uint32_t)(tg * p.n_mma), make_mnmajor_desc(pa + k * kstep_p, p.kbp, lbo_p),
+                      make_mnmajor_desc(qa + k * kstep_q, p.kbq, lbo_q), idesc, (tile > tile_beg || k > 0) ? 1u : 0u);
+          umma_commit(smem_u32(&q_empty[qs]));
+          if (tg == tg_n - 1) {
+            umma_commit(smem_u32(&p_empty[ps]));
+            if (tile == tile_end - 1) umma_commit(smem_u32(tmem_full));
+          }
+        }
+        __syncwarp();
+        if (++qs == p.nq_stage) { qs = 0; qph ^= 1; }
+      }
+      if (++ps == p.np_stage) { ps = 0; pph ^= 1; }
+    }
+  } else if (tile_end > tile_beg) {
+    const int q = warp & 3;
+    const int cp = m0 + q * 32 + lane;
+    mbar_wait(smem_u32(tmem_full), 0);
+    tc_fence_after();
+    const int Ntot = p.ntaps * p.Cq;
+    float* drow = scratch + (long long)split * p.split_stride + (long long)cp * Ntot;
+    for (int tg = 0; tg < tg_n; ++tg) {
+      for (int c0 = 0; c0 < p.n_mma; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tg * p.n_mma + c0), v);
+        tmem_ld_wait();
+        if (cp < p.Cp) {
+          const int cq = q0 + c0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            if (cq + j + 3 < p.Cq) {
+              *reinterpret_cast<float4*>(drow + (t0 + tg) * p.Cq + cq + j) =
+                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (cq + j + e < p.Cq) drow[(t0 + tg) * p.Cq + cq + j + e] = __uint_as_float(v[j + e]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+struct WgTcCfg { WgParams p; int S, tap_groups, z; size_t smem; };
+
+static bool wg_tc_cfg(const WgradGeom& g, WgTcCfg& c) {
+  if (!g_encode) return false;
+  WgParams& p = c.p;
+  memset(&p, 0, sizeof(p));
+  // 32-channel atoms always; channel tails are TMA zero fill (only 16-byte row strides are required)
+  p.kbp = 32; p.kbq = 32;
+  if (g.Cp % 4 || g.Cq % 4 || g.Cp < 8 || g.Cq < 8 || g.ntaps < 1) return false;
+  if (g.s != 1 && g.s != 2) return false;
+  if (g.s == 2 && (g.Hq % 2 || g.Wq % 2)) return false;
+  p.Cp = g.Cp; p.Cq = g.Cq; p.ntaps = g.ntaps; p.s = g.s;
+  p.KPIX = 64;
+  p.TW = std::min(pow2_ge(g.Wp), p.KPIX);
+  p.TH = std::min(pow2_ge(g.Hp), p.KPIX / p.TW);
+  p.TB = p.KPIX / (p.TW * p.TH);
+  p.tiles_x = (g.Wp + p.TW - 1) / p.TW;
+  p.tiles_y = (g.Hp + p.TH - 1) / p.TH;
+  const int tiles_b = (g.N + p.TB - 1) / p.TB;
+  p.ntiles = tiles_b * p.tiles_y * p.tiles_x;
+  p.atoms_p = 128 / p.kbp;
+  const int cq32 = (g.Cq + 31) / 32 * 32;
+  p.n_mma = std::min(cq32, 256);
+  p.q_tiles = (g.Cq + p.n_mma - 1) / p.n_mma;
+  p.atoms_q = (p.n_mma + p.kbq - 1) / p.kbq;
+  p.TG = std::max(1, std::min(g.ntaps, 512 / p.n_mma));
+  c.tap_groups = (g.ntaps + p.TG - 1) / p.TG;
+  p.tmem_cols = std::max(32, pow2_ge(p.TG * p.n_mma));
+  p.p_stage_bytes = p.atoms_p * p.KPIX * p.kbp * 4;          // 128 channels x KPIX pixels x 4 B = 32 KB
+  p.q_stage_bytes = (p.atoms_q * p.KPIX * p.kbq * 4 + 1023) / 1024 * 1024;
+  p.np_stage = 2;
+  p.nq_stage = std::max(2, std::min(8, (120 * 1024) / p.q_stage_bytes));
+  const int mtiles = (g.Cp + 127) / 128;
+  c.z = mtiles * p.q_tiles;
+  const int other = c.tap_groups * c.z;
+  int S = std::max(1, (NSM * 2 + other - 1) / other);
+  S = std::min(S, p.ntiles);
+  p.tiles_per_split = (p.ntiles + S - 1) / S;
+  c.S = (p.ntiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.split_stride = (long long)g.Cp * g.ntaps * g.Cq;
+  for (int t = 0; t < g.ntaps; ++t) {
+    if (g.s == 1) { p.oy[t] = (short)g.dy[t]; p.ox[t] = (short)g.dx[t]; }
+    else {
+      int fy = floordiv2(g.dy[t]), fx = floordiv2(g.dx[t]);
+      p.oy[t] = (short)fy; p.ox[t] = (short)fx; p.py[t] = (short)(g.dy[t] - 2 * fy); p.px[t] = (short)(g.dx[t] - 2 * fx);
+    }
+  }
+  c.smem = 1024 + (size_t)p.np_stage * p.p_stage_bytes + (size_t)p.nq_stage * p.q_stage_bytes +
+           (2 * p.np_stage + 2 * p.nq_stage + 1) * sizeof(uint64_t) + 16;
+  return c.smem <= 200 * 1024;
+}
+
+bool tc_wgrad_supported(const WgradGeom& g) { WgTcCfg c; return wg_tc_cfg(g, c); }
+size_t wgrad_tc_scratch_bytes(const WgradGeom& g) {
+  WgTcCfg c;
+  if (!wg_tc_cfg(g, c)) return 0;
+  return (size_t)c.S * g.Cp * g.ntaps * g.Cq * sizeof(float);
+}
+
+bool k_wgrad_tc(St st, const WgradGeom& g, const float* P, const float* Q, float* grad_master, float* scratch, size_t scratch_bytes,
+                std::string* err) {
+  WgTcCfg c;
+  if (!wg_tc_cfg(g, c)) { if (err) *err = "wgrad geometry not supported by the tcgen05 path"; return false; }
+  if ((size_t)c.S * g.Cp * g.ntaps * g.Cq * sizeof(float) > scratch_bytes) { if (err) *err = "wgrad scratch too small"; return false; }
+  const WgParams& p = c.p;
+  CUtensorMap mapP, mapQ;
+  const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  CUresult r;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)g.Cp, (cuuint64_t)g.Wp, (cuuint64_t)g.Hp, (cuuint64_t)g.N};
+    cuuint64_t strides[3] = {(cuuint64_t)g.Cp * 4, (cuuint64_t)g.Wp * g.Cp * 4, (cuuint64_t)g.Hp * g.Wp * g.Cp * 4};
+    cuuint32_t box[4] = {(cuuint32_t)p.kbp, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TB};
+    r = g_encode(&mapP, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)P, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled(P) failed: " + std::to_string((int)r); return false; }
+  if (g.s == 1) {
+    cuuint64_t dims[4] = {(cuuint64_t)g.Cq, (cuuint64_t)g.Wq, (cuuint64_t)g.Hq, (cuuint64_t)g.N};
+    cuuint64_t strides[3] = {(cuuint64_t)g.Cq * 4, (cuuint64_t)g.Wq * g.Cq * 4, (cuuint64_t)g.Hq * g.Wq * g.Cq * 4};
+    cuuint32_t box[4] = {(cuuint32_t)p.kbq, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TB};
+    r = g_encode(&mapQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)Q, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[5] = {(cuuint64_t)2 * g.Cq, (cuuint64_t)g.Wq / 2, 2, (cuuint64_t)g.Hq / 2, (cuuint64_t)g.N};
+    cuuint64_t strides[4] = {(cuuint64_t)2 * g.Cq * 4, (cuuint64_t)g.Wq * g.Cq * 4, (cuuint64_t)2 * g.Wq * g.Cq * 4,
+                             (cuuint64_t)g.Hq * g.Wq * g.Cq * 4};
+    cuuint32_t box[5] = {(cuuint32_t)p.kbq, (cuuint32_t)p.TW, 1, (cuuint32_t)p.TH, (cuuint32_t)p.TB};
+    r = g_encode(&mapQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)Q, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled(Q) failed: " + std::to_string((int)r); return false; }
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+      if (err) *err = "cudaFuncSetAttribute(smem) failed";
+      return false;
+    }
+    configured = true;
+  }
+  dim3 grid((unsigned)c.S, (unsigned)c.tap_groups, (unsigned)c.z);
+  wgrad_tc_kernel<<<grid, TC_THREADS, c.smem, st.s>>>(mapP, mapQ, p, scratch);
+  DSR_LAUNCHED(st, "wgrad_tc", 2.0 * g.N * g.Hp * g.Wp * g.Cp * g.Cq * g.ntaps, WORK_FLOPS);
+  k_wgrad_reduce(st, scratch, c.S, g.Cp, g.Cq, g.ntaps, grad_master);
+  return true;
+}

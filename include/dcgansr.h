@@ -28,6 +28,7 @@
 extern "C" {
 #endif
 
+/* FFI-CDEF-BEGIN  (lua/dcgansr.lua feeds everything up to FFI-CDEF-END to LuaJIT ffi.cdef verbatim) */
 typedef struct dcgansr_ctx dcgansr_ctx;
 typedef struct dcgansr_net dcgansr_net;
 
@@ -211,6 +212,7 @@ int dcgansr_pixel_mse_per_sample(dcgansr_ctx* ctx, const float* real, const floa
 /* optim.adam on caller vectors (train.lua:280); t is the step count BEFORE the update */
 int dcgansr_adam_step(dcgansr_ctx* ctx, float* p, const float* g, float* m, float* v, int64_t count,
                       int64_t t, double lr, double beta1, double beta2, double eps);
+/* FFI-CDEF-END */
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,10 @@ def run(kind, what, n, cin, hh, w, cout, k, s, p):
         out = np.empty((n, cout, ho, wo), np.float32)
         L.check(getattr(lib, pre + "fwd")(h, ptr(x), ptr(wt), ptr(out), n, cin, hh, w, cout, k, s, p), h)
         ref = (ops.fullconv2d_fwd(X, W, s, p) if full else ops.conv2d_fwd(X, W, s, p)).numpy()
+    elif what == "wgrad":
+        out = np.empty_like(wt)
+        L.check(getattr(lib, pre + "wgrad")(h, ptr(x), ptr(dy), ptr(out), n, cin, hh, w, cout, k, s, p), h)
+        ref = (ops.fullconv2d_wgrad(X, DY, wt.shape, s, p) if full else ops.conv2d_wgrad(X, DY, wt.shape, s, p)).numpy()
     else:
         out = np.empty_like(x)
         L.check(getattr(lib, pre + "dgrad")(h, ptr(dy), ptr(wt), ptr(out), n, cin, hh, w, cout, k, s, p), h)
@@ -44,5 +48,5 @@ cases = [
     ("conv", 2, 128, 16, 16, 256, 4, 2, 1),   # 2 N tiles
 ]
 for c in cases:
-    for what in ("fwd", "dgrad"):
+    for what in (sys.argv[1:] or ("fwd", "dgrad", "wgrad")):
         run(c[0], what, *c[1:])

@@ -1,0 +1,137 @@
+"""FAST_TF32 mode (tcgen05 kind::tf32 implicit GEMM, fp32 accumulate in TMEM): per-layer and per-step parity
+within 2e-3 of the float64 oracle (north_star), norm-wise."""
+import numpy as np
+import pytest
+import torch
+
+import dcgan_super_resolution_b200 as dsr
+from dcgan_super_resolution_b200 import _lib as L
+from dcgan_super_resolution_b200 import models
+from oracle import ops
+from oracle import step as ostep
+from util import FAST_TOL, oracle_net, ostep_cfg, ptr, rel_err, rng, smooth_images, t64
+
+pytestmark = pytest.mark.gpu
+
+# (kind, n, cin, h, w, cout, k, s, p): contraction dims that are multiples of 8 ride the tensor cores
+TC_SHAPES = [
+    ("conv", 2, 32, 8, 8, 32, 3, 1, 1),        # stride 1, 128-byte swizzle
+    ("conv", 2, 64, 32, 32, 128, 4, 2, 1),     # D layer 2 of C3a: stride-2 gather through the 5-D view
+    ("conv", 4, 64, 6, 6, 128, 3, 1, 0),       # patch-D layer 2 of C1a
+    ("conv", 2, 16, 16, 16, 32, 4, 2, 1),      # 64-byte swizzle
+    ("conv", 2, 8, 16, 16, 16, 4, 2, 1),       # 32-byte swizzle
+    ("conv", 3, 512, 4, 4, 1, 4, 1, 0),        # D final layer: Co = 1 (N padded to 16 by TMA zero fill)
+    ("conv", 2, 24, 10, 14, 12, 4, 2, 1),      # ragged: tiles larger than the image, Co = 12
+    ("conv", 2, 128, 16, 16, 256, 4, 2, 1),    # two N tiles
+    ("conv", 130, 32, 2, 2, 48, 2, 1, 0),      # 1x1 output grid: a tile spans 128 images, batch tail
+    ("conv", 1, 32, 40, 40, 16, 3, 1, 1),      # several spatial tiles with partial edges
+    ("full", 2, 64, 16, 16, 32, 4, 2, 1),      # C2 G layer 3 (spatial reduced)
+    ("full", 2, 96, 8, 8, 48, 4, 2, 1),        # train.lua G layer 2
+    ("full", 3, 48, 6, 10, 24, 4, 2, 1),
+    ("full", 2, 32, 5, 5, 16, 3, 1, 1),
+]
+
+
+@pytest.mark.parametrize("shape", TC_SHAPES)
+def test_tc_conv_fwd_dgrad(ctx_fast, shape):
+    kind, n, cin, h, w, cout, k, s, p = shape
+    full = kind == "full"
+    r = rng(hash(shape[1:]) % 2**31)
+    x = r.standard_normal((n, cin, h, w)).astype(np.float32)
+    wt = (0.1 * r.standard_normal((cin, cout, k, k) if full else (cout, cin, k, k))).astype(np.float32)
+    ho, wo = ((h - 1) * s - 2 * p + k, (w - 1) * s - 2 * p + k) if full else ((h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1)
+    dy = r.standard_normal((n, cout, ho, wo)).astype(np.float32)
+    lib, hc = ctx_fast.lib, ctx_fast.h
+    pre = "dcgansr_fullconv2d_" if full else "dcgansr_conv2d_"
+    args = (n, cin, h, w, cout, k, s, p)
+    X, W, DY = t64(x), t64(wt), t64(dy)
+    y = np.empty((n, cout, ho, wo), np.float32)
+    L.check(getattr(lib, pre + "fwd")(hc, ptr(x), ptr(wt), ptr(y), *args), hc)
+    ref = (ops.fullconv2d_fwd(X, W, s, p) if full else ops.conv2d_fwd(X, W, s, p)).numpy()
+    assert rel_err(y, ref) <= FAST_TOL
+    dx = np.empty_like(x)
+    L.check(getattr(lib, pre + "dgrad")(hc, ptr(dy), ptr(wt), ptr(dx), *args), hc)
+    ref = (ops.fullconv2d_dgrad(DY, W, s, p) if full else ops.conv2d_dgrad(DY, W, x.shape, s, p)).numpy()
+    assert rel_err(dx, ref) <= FAST_TOL
+    dw = np.empty_like(wt)
+    L.check(getattr(lib, pre + "wgrad")(hc, ptr(x), ptr(dy), ptr(dw), *args), hc)
+    ref = (ops.fullconv2d_wgrad(X, DY, wt.shape, s, p) if full else ops.conv2d_wgrad(X, DY, wt.shape, s, p)).numpy()
+    assert rel_err(dw, ref) <= FAST_TOL
+
+
+def test_tc_epilogue_activation(ctx_fast):
+    """conv + LeakyReLU / Tanh fused in the tcgen05 epilogue == unfused oracle."""
+    for act in ("lrelu", "tanh", "sigmoid", "relu"):
+        specs = [dict(kind="conv", cin=16, cout=32, k=4, s=2, p=1), dict(kind=act, negval=0.2)]
+        onet = oracle_net(specs, 11)
+        net = dsr.Sequential.from_specs(specs).cuda(ctx_fast, (16, 16, 16), 3)
+        net.set_params(onet.get_flat_params().numpy().astype(np.float32))
+        x = rng(3).standard_normal((3, 16, 16, 16)).astype(np.float32)
+        assert rel_err(net.forward(x), onet.forward(t64(x)).numpy()) <= FAST_TOL, act
+        net.close()
+
+
+FAST_NETS = {
+    "train_lua_G": (models.train_lua_G(3, 8), (3, 8, 8)),
+    "train_gray_G": (models.train_gray_G(16), (1, 8, 8)),
+    "train_gray_3_G": (models.train_gray_3_G(8), (1, 4, 4)),
+    "dcgan64_D": (models.dcgan64_D(3, 16), (3, 64, 64)),
+    "patch_D": (models.patch_D(16), (1, 8, 8)),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FAST_NETS))
+def test_fast_net_forward_backward(ctx_fast, name):
+    specs, ishape = FAST_NETS[name]
+    B = 4
+    onet = oracle_net(specs, seed=4321)
+    net = dsr.Sequential.from_specs(specs).cuda(ctx_fast, ishape, B)
+    net.set_params(onet.get_flat_params().numpy().astype(np.float32))
+    r = rng(1234)
+    x = r.uniform(-1, 1, (B,) + ishape).astype(np.float32)
+    y = net.forward(x)
+    ry = onet.forward(t64(x))
+    assert rel_err(y.reshape(-1), ry.numpy().reshape(-1)) <= FAST_TOL
+    dy = r.standard_normal(y.shape).astype(np.float32)
+    net.zeroGradParameters()
+    onet.zero_grad_parameters()
+    dx = net.backward(x, dy)
+    rdx = onet.backward(t64(x), t64(dy).reshape(ry.shape))
+    # a deep chain of TF32 layers: errors compound, 2e-3 per layer -> allow 3x on the end-to-end gradient
+    assert rel_err(dx, rdx.numpy()) <= 3 * FAST_TOL
+    g, rg = net.get_grads(), onet.get_flat_grads().numpy()
+    off = 0
+    for _, p, _g in onet.param_list():
+        n = p.numel()
+        assert rel_err(g[off:off + n], rg[off:off + n]) <= 3 * FAST_TOL, (name, off)
+        off += n
+    net.close()
+
+
+def test_fast_step_losses_close_to_oracle(ctx_fast):
+    """One fused step in FAST_TF32: losses within 2e-3, updated parameters within 2e-3 of the oracle's update."""
+    case = dict(G=models.train_gray_G(16), D=models.dcgan64_D(1, 16), nc=1, hr=64, batch=4,
+                step=dict(family="mse", real_label=0.001, fake_label=0.0, gen_label=0.0, pixel_label=True, pixel_div=64.0 * 64.0))
+    oG, oD = oracle_net(case["G"], 4321), oracle_net(case["D"], 8765)
+    G = dsr.Sequential.from_specs(case["G"]).cuda(ctx_fast, (1, 32, 32), 4)
+    D = dsr.Sequential.from_specs(case["D"]).cuda(ctx_fast, (1, 64, 64), 4)
+    G.set_params(oG.get_flat_params().numpy().astype(np.float32))
+    D.set_params(oD.get_flat_params().numpy().astype(np.float32))
+    real = smooth_images(rng(5), (4, 1, 64, 64), -1.0, 1.0)
+    trace = {}
+    oerr = ostep.train_step(oG, oD, ostep.new_adam_state(oG), ostep.new_adam_state(oD), torch.from_numpy(real),
+                            ostep_cfg(case["step"]), trace)
+    err = dsr.train_step(ctx_fast, G, D, dsr.make_step_cfg(**case["step"]), real)
+    for a, b in zip(err, oerr):
+        assert abs(a - b) <= FAST_TOL * max(abs(b), 1e-3), (err, oerr)
+    assert rel_err(D.get_grads(), trace["gradD"].numpy()) <= 5 * FAST_TOL
+    assert rel_err(G.get_grads(), trace["gradG"].numpy()) <= 5 * FAST_TOL
+    G.close(); D.close()
+
+
+def test_fast_trajectory_200_steps(ctx_fast):
+    """Err_D / Err_G over 200 free-running FAST_TF32 steps stay within 1 % of the float32 oracle (train-gray.lua graph)."""
+    from test_gpu_step import STEP_CASES, _trajectory
+    ours, ref = _trajectory(ctx_fast, STEP_CASES["mse_gray"], 200)
+    rel = np.abs(ours - ref) / np.maximum(np.abs(ref), 1e-6)
+    assert rel.max() <= 0.01, (rel.max(), rel.argmax())
