@@ -190,6 +190,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample-batch", type=int, default=8)
     ap.add_argument("--profile-steps", type=int, default=2)
+    ap.add_argument("--profile-out", default="", help="write the full per-kernel profile table (JSON) here")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)
@@ -286,6 +287,9 @@ def main():
             dsr.train_step_staged(ctx, G, D, scfg, i % NPOOL, B)
         prof = ctx.profile_end()
     barrier()
+    if args.profile_out and rank == 0:
+        with open(args.profile_out, "w") as f:
+            json.dump({"profile_steps": args.profile_steps, "kernels": prof}, f, indent=1)
 
     if os.environ.get("DCGANSR_DEBUG_LEGS"):
         for label, sync_each in (("staged-async", False), ("staged-sync-each-step", True)):
