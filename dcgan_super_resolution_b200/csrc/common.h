@@ -125,6 +125,12 @@ void k_wgrad_simt(St st, const WgradGeom& g, const float* P, const float* Q, flo
 // grad_master[cp*(Cq*T) + cq*T + t] += sum_s scratch[s][cp][t*Cq + cq]   (fixed order)
 void k_wgrad_reduce(St st, const float* scratch, int S, int Cp, int Cq, int T, float* grad_master);
 
+// ---- kernels_thin.cu : streaming fp32 kernels for layers with a 1..4-channel side -------------------
+bool thin_wgrad_supported(const WgradGeom& g);
+size_t thin_wgrad_scratch_bytes(const WgradGeom& g);
+// false when the geometry is not covered (caller falls through to the GEMM kernels)
+bool k_wgrad_thin(St st, const WgradGeom& g, const float* P, const float* Q, float* grad_master, float* scratch, size_t scratch_bytes);
+
 // ---- kernels_tc.cu : tcgen05 / TMA / TMEM implicit-GEMM convolutions (FAST_TF32) --------------
 bool tc_init(std::string* err);                       // resolves cuTensorMapEncodeTiled
 bool tc_tapconv_supported(const TapGeom& g);

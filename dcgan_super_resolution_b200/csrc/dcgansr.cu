@@ -313,6 +313,7 @@ struct ConvPlan {
     WgradGeom g = wg;
     g.N = N;
     size_t b = wgrad_simt_scratch_bytes(g);
+    b = std::max(b, thin_wgrad_scratch_bytes(g));
     if (fast && tc_wgrad_supported(g)) b = std::max(b, wgrad_tc_scratch_bytes(g));
     return b;
   }
@@ -322,6 +323,7 @@ struct ConvPlan {
     g.N = N;
     const float* Pp = full ? x : dy;
     const float* Qp = full ? dy : x;
+    if (k_wgrad_thin(ctx->st(), g, Pp, Qp, grad_master, scratch, scratch_bytes)) return;   // 1..4-channel side: streaming kernel
     if (fast && tc_wgrad_supported(g)) {
       std::string e;
       if (k_wgrad_tc(ctx->st(), g, Pp, Qp, grad_master, scratch, scratch_bytes, &e)) return;
@@ -1200,6 +1202,42 @@ int dcgansr_fullconv2d_dgrad(dcgansr_ctx* ctx, const float* dy, const float* w, 
 }
 int dcgansr_fullconv2d_wgrad(dcgansr_ctx* ctx, const float* x, const float* dy, float* dw, int n, int cin, int h, int wd, int cout, int k, int s, int p) {
   return conv_op(ctx, true, 2, x, dy, dw, n, cin, h, wd, cout, k, s, p);
+}
+
+// Device-resident timing of one convolution op (what: 0 fwd, 1 dgrad, 2 wgrad) at batch n: `iters` launches between two
+// CUDA events on the library stream after 2 warm-ups, tensors filled on the device (no host traffic).  Used by
+// scripts/bench_layers.py to put every layer of a config against its roofline.
+int dcgansr_bench_conv(dcgansr_ctx* ctx, int full, int what, int n, int cin, int h, int wd, int cout, int k, int s, int p,
+                       int iters, float* ms_out) {
+  NEED_CTX(ctx);
+  if (!ms_out || n <= 0 || iters <= 0 || what < 0 || what > 2) return fail(ctx, DCGANSR_ERR_INVALID, "bad argument");
+  ConvPlan plan;
+  std::string err = plan.build(full != 0, cin, cout, k, s, p, 0, h, wd);
+  if (!err.empty()) return fail(ctx, DCGANSR_ERR_INVALID, err);
+  struct Guard { ConvPlan& p; ~Guard() { p.free_device(); } } guard{plan};
+  if (int rc = plan.alloc_device(ctx)) return rc;
+  Arena ar;
+  int64_t xin = (int64_t)n * cin * h * wd, yout = (int64_t)n * cout * plan.Hout * plan.Wout, wn = plan.weight_count();
+  float *dX = ar.f(xin), *dY = ar.f(yout), *dW = ar.f(wn);
+  size_t sb = plan.wscratch_bytes(n);
+  float* sc = (float*)ar.bytes(sb);
+  if (!dX || !dY || !dW || !sc) return fail(ctx, DCGANSR_ERR_NOMEM, "device allocation failed");
+  St st = ctx->st();
+  k_fill(st, dX, xin, 0.37f); k_fill(st, dY, yout, -0.21f); k_fill(st, dW, wn, 0.02f);
+  plan.pack(st, dW);
+  for (int it = -2; it < iters; ++it) {
+    if (it == 0) CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    if (what == 0) plan.forward(ctx, dX, dY, n, ACT_NONE, 0.f);
+    else if (what == 1) plan.dgrad_run(ctx, dY, dX, n);
+    else plan.wgrad_run(ctx, dX, dY, dW, n, sc, sb);
+  }
+  CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+  CK(ctx, cudaEventSynchronize(ctx->ev1));
+  CKLAST(ctx);
+  float ms = 0.f;
+  CK(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  *ms_out = ms / iters;
+  return 0;
 }
 
 int dcgansr_bn_fwd_train(dcgansr_ctx* ctx, const float* x, const float* gamma, const float* beta, float* running_mean,

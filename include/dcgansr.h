@@ -187,6 +187,11 @@ int dcgansr_fullconv2d_dgrad(dcgansr_ctx* ctx, const float* dy, const float* w, 
                              int n, int cin, int h, int wd, int cout, int k, int s, int p);
 int dcgansr_fullconv2d_wgrad(dcgansr_ctx* ctx, const float* x, const float* dy, float* dw,
                              int n, int cin, int h, int wd, int cout, int k, int s, int p);
+/* Measurement aid (no reference counterpart): average device time in ms of one conv / full-conv op
+ * (what: 0 forward, 1 updateGradInput, 2 accGradParameters) over `iters` launches on device-resident tensors. */
+int dcgansr_bench_conv(dcgansr_ctx* ctx, int full, int what, int n, int cin, int h, int wd, int cout,
+                       int k, int s, int p, int iters, float* ms_out);
+
 /* nn.SpatialBatchNormalization training forward/backward (train.lua:100) */
 int dcgansr_bn_fwd_train(dcgansr_ctx* ctx, const float* x, const float* gamma, const float* beta,
                          float* running_mean, float* running_var, float* y,

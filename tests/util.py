@@ -55,3 +55,67 @@ def ostep_cfg(step: dict, **kw):
     d = dict(step)
     d.update(kw)
     return ostep.StepCfg(**d)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# TF32 emulation of the ORACLE (test infrastructure).  FAST_TF32 feeds the tensor cores fp32 activations (the
+# hardware ignores the low 13 mantissa bits) and TF32-rounded weights (cvt.rna at pack time).  On whole nets
+# with BatchNorm and ReLU kinks a *correct* TF32 evaluation is 3-11 % (max-norm) away from the float64 oracle
+# in the backward pass (scripts/tf32_conditioning.py), so net-level FAST tests compare against the float64
+# oracle evaluated with the same operand rounding; what remains is summation order.
+# ---------------------------------------------------------------------------------------------------------
+import contextlib
+
+from oracle import ops as _ops
+
+
+def trunc_tf32(x):
+    a = x.to(torch.float32).contiguous().view(torch.int32)
+    return (a & ~0x1FFF).view(torch.float32).to(x.dtype)
+
+
+def rna_tf32(x):
+    a = x.to(torch.float32).contiguous().view(torch.int32)
+    return ((a + 0x1000) & ~0x1FFF).view(torch.float32).to(x.dtype)
+
+
+@contextlib.contextmanager
+def tf32_oracle(act_round=trunc_tf32, thin_exact=True):
+    """Inside the block every convolution of the oracle rounds its operands like FAST_TF32 does.  Layers whose
+    contraction channel count is not a multiple of 8 (C in {1, 3}) run on the fp32 SIMT kernels in the library,
+    so they stay exact when `thin_exact`."""
+    names = ("conv2d_fwd", "conv2d_dgrad", "conv2d_wgrad", "fullconv2d_fwd", "fullconv2d_dgrad", "fullconv2d_wgrad")
+    orig = {k: getattr(_ops, k) for k in names}
+
+    def tc(c):
+        return (not thin_exact) or c % 8 == 0
+
+    def r(x, on):
+        return act_round(x) if on else x
+
+    def w_(w, on):
+        return rna_tf32(w) if on else w
+
+    # forward contracts over cin, dgrad over cout, wgrad over pixels (tensor cores need both channel counts >= 8, % 4)
+    _ops.conv2d_fwd = lambda x, w, s, p: orig["conv2d_fwd"](r(x, tc(w.shape[1])), w_(w, tc(w.shape[1])), s, p)
+    _ops.conv2d_dgrad = lambda dy, w, xs, s, p: orig["conv2d_dgrad"](r(dy, tc(w.shape[0])), w_(w, tc(w.shape[0])), xs, s, p)
+    _ops.conv2d_wgrad = lambda x, dy, ws, s, p: orig["conv2d_wgrad"](r(x, _wg(ws)), r(dy, _wg(ws)), ws, s, p)
+    _ops.fullconv2d_fwd = lambda x, w, s, p, adj=0: orig["fullconv2d_fwd"](r(x, tc(w.shape[0])), w_(w, tc(w.shape[0])), s, p, adj)
+    _ops.fullconv2d_dgrad = lambda dy, w, s, p: orig["fullconv2d_dgrad"](r(dy, tc(w.shape[1])), w_(w, tc(w.shape[1])), s, p)
+    _ops.fullconv2d_wgrad = lambda x, dy, ws, s, p: orig["fullconv2d_wgrad"](r(x, _wg(ws)), r(dy, _wg(ws)), ws, s, p)
+
+    def _wg(ws):
+        return (not thin_exact) or (ws[0] % 4 == 0 and ws[1] % 4 == 0 and ws[0] >= 8 and ws[1] >= 8)
+
+    try:
+        yield
+    finally:
+        for k, v in orig.items():
+            setattr(_ops, k, v)
+
+
+def l2_err(a, b):
+    a = np.asarray(a, np.float64).ravel()
+    b = np.asarray(b, np.float64).ravel()
+    n = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / n if n > 0 else np.linalg.norm(a - b)
