@@ -141,6 +141,10 @@ void k_pack_taps_tc(St st, const float* master, float* bp, int ntaps, const int*
 // returns false (with err) if the launch could not be configured
 bool k_tapconv_tc(St st, const TapGeom& g, const float* in, const float* bp, float* out, int act, float negval,
                   std::string* err);
+// ---- kernels_halo.cu : weights-resident halo-tile kernel (all sub-pixel classes of a module in one launch) ----
+bool halo_tapconv_supported(const TapGeom* classes, int ncls);
+bool k_tapconv_halo(St st, const TapGeom* classes, int ncls, const float* const* bp, const float* in, float* out, int act,
+                    float negval, std::string* err);
 bool tc_wgrad_supported(const WgradGeom& g);
 size_t wgrad_tc_scratch_bytes(const WgradGeom& g);
 bool k_wgrad_tc(St st, const WgradGeom& g, const float* P, const float* Q, float* grad_master, float* scratch, size_t scratch_bytes,

@@ -18,6 +18,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -292,6 +293,20 @@ struct ConvPlan {
         }
   }
   static void run_classes(dcgansr_ctx* ctx, std::vector<TapClass>& v, const float* in, float* out, int N, int act, float neg) {
+    // spatially large thin layers: one weights-resident halo launch for all sub-pixel classes
+    if (!v.empty() && v.size() <= 4 && !getenv("DCGANSR_NO_HALO")) {
+      TapGeom gs[4];
+      const float* bps[4];
+      bool all_tc = true;
+      for (size_t i = 0; i < v.size(); ++i) { gs[i] = v[i].g; gs[i].N = N; bps[i] = v[i].bp; all_tc = all_tc && v[i].bp; }
+      if (all_tc && halo_tapconv_supported(gs, (int)v.size())) {
+        std::string e;
+        if (k_tapconv_halo(ctx->st(), gs, (int)v.size(), bps, in, out, act, neg, &e)) return;
+        ctx->err = "tcgen05 halo path: " + e;
+        ctx->tc_failed = true;
+        return;
+      }
+    }
     for (auto& c : v) {
       if (c.g.Hg <= 0 || c.g.Wg <= 0) continue;
       TapGeom g = c.g;

@@ -1,0 +1,439 @@
+// kernels_halo.cu -- weights-resident, halo-tile tcgen05 implicit-GEMM convolution for the spatially large, thin
+// layers of the generator (FAST_TF32): nn.SpatialFullConvolution / nn.SpatialConvolution forward and updateGradInput
+// (train.lua:99-111, train-gray.lua:105-116) where the activations (hundreds of MB) dominate and the whole
+// weight tensor fits in shared memory.
+//
+// What bounds these layers is HBM, and what bounded the per-tap kernel (kernels_tc.cu) was the L2 -> SM path: it
+// re-fetches the input pixels once per tap (4..16x) and the weights once per 128-pixel tile.  Here
+//
+//   * a persistent CTA loads its slice of the packed weights ONCE (TMA, K-major, swizzled) and keeps it in smem;
+//   * per 16 x 8 tile of the output grid it loads the input pixels ONCE: a halo tile (one TMA box per 32-channel
+//     plane, zero fill = padding), double buffered;
+//   * every tap is then just another START ADDRESS of the same smem tile: the UMMA descriptor's swizzle is a
+//     function of the absolute shared-memory address, so a window shifted by whole pixel rows (and stepping
+//     `pitch` bytes between 8-pixel groups, SBO = halo row pitch) is a valid K-major operand
+//     (verified on B200 by scripts/exp/exp_desc.cu);
+//   * all stride^2 sub-pixel classes of a full-conv forward / conv dgrad are computed by the same CTA from the
+//     same halo tile into separate TMEM column ranges, so the input is read once, not once per class;
+//   * accumulators are double buffered in TMEM: the epilogue of tile i (tcgen05.ld -> activation -> NHWC stores)
+//     overlaps the TMA + MMA of tile i + 1.
+//
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue.
+#include "tc_ptx.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#define NSM 148
+#define HALO_TH 16
+#define HALO_TW 8
+#define HALO_MAXCLS 4
+#define HALO_MAXTAPS 16
+#define HALO_MAXPLANES 8
+#define HALO_THREADS 192
+
+struct HaloMaps { CUtensorMap b[HALO_MAXCLS]; };
+
+struct HaloParams {
+  int N, Hg, Wg, tiles_x, tiles_y, ntiles;
+  int Ho, Wo, Co, so, ncls, si, Ci;
+  int row_bytes, a_layout;           // A pixel-row bytes (128 / 64) and UMMA layout code (2 = SW128, 4 = SW64)
+  int KBw, kchunks, ksteps;          // weight rows: KBw floats; chunks per tap; K = 8 steps per chunk
+  int nplanes, plane_bytes, plane_tx, PH, PW, pitch_bytes;
+  short pl_c[HALO_MAXPLANES], pl_x[HALO_MAXPLANES], pl_py[HALO_MAXPLANES], pl_y[HALO_MAXPLANES];
+  int Npad, wtile_bytes, w_bytes, w_tx;
+  int ntaps[HALO_MAXCLS];
+  short coy[HALO_MAXCLS], cox[HALO_MAXCLS];
+  unsigned short tap_plane[HALO_MAXCLS][HALO_MAXTAPS], tap_wtile[HALO_MAXCLS][HALO_MAXTAPS];
+  int tap_aoff[HALO_MAXCLS][HALO_MAXTAPS];
+  int nstage, stage_bytes, acc_cols, nacc, tmem_cols, nmma;
+  int act;
+  float neg;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major descriptor with explicit SBO and layout (start address may be any 16-byte aligned window of the tile)
+__device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr, uint32_t sbo, uint64_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFFu) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
+
+__global__ void __launch_bounds__(HALO_THREADS) tapconv_halo_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                    const __grid_constant__ HaloMaps mapsB,
+                                                                    const HaloParams p, float* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sW = smem;
+  uint8_t* sA = smem + p.w_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)p.nstage * p.stage_bytes);
+  uint64_t* w_full = bars;
+  uint64_t* a_full = bars + 1;
+  uint64_t* a_empty = bars + 3;
+  uint64_t* acc_full = bars + 5;
+  uint64_t* acc_empty = bars + 7;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  // MMA issue table: one 8-byte entry per tcgen05.mma of a tile {A offset >> 4 | W offset >> 4 << 16, TMEM column | accumulate << 16}.
+  // The MMAs of these thin layers are small (N = 16..64: 8..32 tensor cycles each), so the single issuing thread must
+  // not spend more than a few instructions per MMA: everything that does not depend on the tile is precomputed here.
+  uint2* mma_tab = reinterpret_cast<uint2*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n0 = blockIdx.y * p.Npad;
+  for (int i = threadIdx.x; i < p.nmma; i += HALO_THREADS) {
+    // decode i -> (class, tap, chunk, kstep) in issue order
+    int rem = i, c = 0;
+    const int per_tap = p.kchunks * p.ksteps;
+    while (rem >= p.ntaps[c] * per_tap) { rem -= p.ntaps[c] * per_tap; ++c; }
+    const int t = rem / per_tap, q = (rem % per_tap) / p.ksteps, k = rem % p.ksteps;
+    const uint32_t aoff = (uint32_t)(p.tap_plane[c][t] + q) * p.plane_bytes + (uint32_t)p.tap_aoff[c][t] + k * 32;
+    const uint32_t woff = (uint32_t)(p.tap_wtile[c][t] + q) * p.wtile_bytes + k * 32;
+    mma_tab[i] = make_uint2((aoff >> 4) | ((woff >> 4) << 16), (uint32_t)(c * p.Npad) | (rem ? 0x10000u : 0u));
+  }
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    mbar_init(smem_u32(w_full), 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(smem_u32(&a_full[s]), 1);
+      mbar_init(smem_u32(&a_empty[s]), 1);
+      mbar_init(smem_u32(&acc_full[s]), 1);
+      mbar_init(smem_u32(&acc_empty[s]), 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      // resident weights: every (class, tap, chunk) tile of this CTA's cout slice
+      const uint32_t wf = smem_u32(w_full);
+      mbar_expect_tx(wf, (uint32_t)p.w_tx);
+      for (int c = 0; c < p.ncls; ++c)
+        for (int t = 0; t < p.ntaps[c]; ++t)
+          for (int q = 0; q < p.kchunks; ++q)
+            tma_load_2d(smem_u32(sW) + (uint32_t)(p.tap_wtile[c][t] + q) * p.wtile_bytes, &mapsB.b[c], wf,
+                        t * p.Ci + q * p.KBw, n0);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+        const int s = it % p.nstage;
+        const uint32_t ph = (uint32_t)(it / p.nstage) & 1u;
+        int tt = tile;
+        const int tx = tt % p.tiles_x; tt /= p.tiles_x;
+        const int ty = tt % p.tiles_y; tt /= p.tiles_y;
+        const int n = tt, gy0 = ty * HALO_TH, gx0 = tx * HALO_TW;
+        mbar_wait(smem_u32(&a_empty[s]), ph ^ 1u);
+        const uint32_t fb = smem_u32(&a_full[s]);
+        mbar_expect_tx(fb, (uint32_t)(p.nplanes * p.plane_tx));
+        const uint32_t dst0 = smem_u32(sA + (size_t)s * p.stage_bytes);
+        for (int pl = 0; pl < p.nplanes; ++pl) {
+          const uint32_t dst = dst0 + (uint32_t)pl * p.plane_bytes;
+          if (p.si == 1)
+            tma_load_4d(dst, &mapA, fb, p.pl_c[pl], gx0 + p.pl_x[pl], gy0 + p.pl_y[pl], n);
+          else
+            tma_load_5d(dst, &mapA, fb, p.pl_c[pl], gx0 + p.pl_x[pl], p.pl_py[pl], gy0 + p.pl_y[pl], n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);
+    const uint64_t wl = p.KBw == 32 ? 2ull : (p.KBw == 16 ? 4ull : 6ull);
+    const uint32_t w_sbo = 8u * (uint32_t)p.KBw * 4u;
+    mbar_wait(smem_u32(w_full), 0);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int s = it % p.nstage;
+      const uint32_t ph = (uint32_t)(it / p.nstage) & 1u;
+      const int buf = it % p.nacc;
+      const uint32_t aph = (uint32_t)(it / p.nacc) & 1u;
+      mbar_wait(smem_u32(&acc_empty[buf]), aph ^ 1u);
+      mbar_wait(smem_u32(&a_full[s]), ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t adesc = make_desc_k(smem_u32(sA + (size_t)s * p.stage_bytes), (uint32_t)p.pitch_bytes, (uint64_t)p.a_layout);
+        const uint64_t bdesc = make_desc_k(smem_u32(sW), w_sbo, wl);
+        const uint32_t dbase = tmem_base + (uint32_t)(buf * p.acc_cols);
+#pragma unroll 4
+        for (int i = 0; i < p.nmma; ++i) {
+          const uint2 e = mma_tab[i];
+          umma_tf32(dbase + (e.y & 0xFFFFu), adesc + (uint64_t)(e.x & 0xFFFFu), bdesc + (uint64_t)(e.x >> 16), idesc, e.y >> 16);
+        }
+        umma_commit(smem_u32(&a_empty[s]));
+        umma_commit(smem_u32(&acc_full[buf]));
+      }
+      __syncwarp();
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> activation -> NHWC global =====================
+    const int q = warp & 3;                       // TMEM lane quarter this warp may access
+    const int r = q * 32 + lane;                  // tile row = pixel
+    const int w = r % HALO_TW, h = r / HALO_TW;
+    const bool vec = (p.Co & 3) == 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+      const int buf = it % p.nacc;
+      const uint32_t aph = (uint32_t)(it / p.nacc) & 1u;
+      int tt = tile;
+      const int tx = tt % p.tiles_x; tt /= p.tiles_x;
+      const int ty = tt % p.tiles_y; tt /= p.tiles_y;
+      const int n = tt, gy = ty * HALO_TH + h, gx = tx * HALO_TW + w;
+      const bool valid = gy < p.Hg && gx < p.Wg;
+      mbar_wait(smem_u32(&acc_full[buf]), aph);
+      tc_fence_after();
+      for (int c = 0; c < p.ncls; ++c) {
+        float* orow = out + ((int64_t)(n * p.Ho + gy * p.so + p.coy[c]) * p.Wo + gx * p.so + p.cox[c]) * p.Co;
+        for (int c0 = 0; c0 < p.Npad; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.acc_cols + c * p.Npad + c0), v);
+          tmem_ld_wait();
+          if (valid) {
+            const int co = n0 + c0;
+            if (vec) {
+#pragma unroll
+              for (int j = 0; j < 16; j += 4) {
+                if (co + j < p.Co) {
+                  float4 o;
+                  o.x = act_apply_t(__uint_as_float(v[j]), p.act, p.neg);
+                  o.y = act_apply_t(__uint_as_float(v[j + 1]), p.act, p.neg);
+                  o.z = act_apply_t(__uint_as_float(v[j + 2]), p.act, p.neg);
+                  o.w = act_apply_t(__uint_as_float(v[j + 3]), p.act, p.neg);
+                  *reinterpret_cast<float4*>(orow + co + j) = o;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (co + j < p.Co) orow[co + j] = act_apply_t(__uint_as_float(v[j]), p.act, p.neg);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static inline int pow2_ge_h(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+static inline int floordiv2_h(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
+
+struct HaloCfg { HaloParams p; int nsplit; size_t smem; int grid_x; };
+
+#define HALO_SMEM_MAX 232448      // 227 KB: the sm_100 per-block dynamic shared memory limit
+
+static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
+  if (!tc_encode_fn() || ncls < 1 || ncls > HALO_MAXCLS) return false;
+  HaloParams& p = c.p;
+  memset(&p, 0, sizeof(p));
+  const TapGeom& g0 = cls[0];
+  const int Ci = g0.Ci;
+  if (!(Ci % 32 == 0 || Ci == 16)) return false;
+  if (g0.si != 1 && g0.si != 2) return false;
+  if (g0.si == 2 && (ncls != 1 || g0.so != 1 || g0.Hi % 2 || g0.Wi % 2)) return false;
+  if (g0.Hg < 8 || g0.Wg < HALO_TW) return false;            // small images: the per-tap kernel tiles several images
+  for (int i = 0; i < ncls; ++i) {
+    const TapGeom& g = cls[i];
+    if (g.Hg != g0.Hg || g.Wg != g0.Wg || g.Ci != Ci || g.Co != g0.Co || g.si != g0.si || g.so != g0.so || g.Hi != g0.Hi ||
+        g.Wi != g0.Wi || g.Ho != g0.Ho || g.Wo != g0.Wo)
+      return false;
+    if (g.ntaps < 1 || g.ntaps > HALO_MAXTAPS) return false;
+  }
+  p.N = g0.N; p.Hg = g0.Hg; p.Wg = g0.Wg; p.Ho = g0.Ho; p.Wo = g0.Wo; p.Co = g0.Co; p.so = g0.so; p.ncls = ncls; p.si = g0.si; p.Ci = Ci;
+  p.tiles_x = (p.Wg + HALO_TW - 1) / HALO_TW;
+  p.tiles_y = (p.Hg + HALO_TH - 1) / HALO_TH;
+  p.ntiles = p.N * p.tiles_y * p.tiles_x;
+  p.KBw = Ci % 32 == 0 ? 32 : 16;
+  p.kchunks = Ci / p.KBw;
+  p.ksteps = p.KBw / 8;
+  // ---- A planes ----
+  if (p.si == 1) {
+    p.row_bytes = p.KBw * 4;
+    p.a_layout = p.KBw == 32 ? 2 : 4;
+    int ymin = 1 << 20, ymax = -(1 << 20), xmin = 1 << 20, xmax = -(1 << 20);
+    for (int i = 0; i < ncls; ++i)
+      for (int t = 0; t < cls[i].ntaps; ++t) {
+        ymin = std::min(ymin, cls[i].dy[t]); ymax = std::max(ymax, cls[i].dy[t]);
+        xmin = std::min(xmin, cls[i].dx[t]); xmax = std::max(xmax, cls[i].dx[t]);
+      }
+    p.PH = HALO_TH + ymax - ymin; p.PW = HALO_TW + xmax - xmin;
+    p.nplanes = p.kchunks;
+    if (p.nplanes > HALO_MAXPLANES) return false;
+    for (int q = 0; q < p.nplanes; ++q) { p.pl_c[q] = (short)(q * p.KBw); p.pl_x[q] = (short)xmin; p.pl_y[q] = (short)ymin; p.pl_py[q] = 0; }
+    p.pitch_bytes = p.PW * p.row_bytes;
+    for (int i = 0; i < ncls; ++i)
+      for (int t = 0; t < cls[i].ntaps; ++t) {
+        p.tap_plane[i][t] = 0;
+        p.tap_aoff[i][t] = ((cls[i].dy[t] - ymin) * p.PW + (cls[i].dx[t] - xmin)) * p.row_bytes;
+      }
+  } else {
+    // parity view [N][H/2][2][W/2][2*Ci]: rows of 2*Ci floats; planes = (row parity) x (32-float chunk of the wide pixel)
+    p.row_bytes = 128;
+    p.a_layout = 2;
+    const int J = std::max(1, 2 * Ci / 32);
+    // x range per column parity when the two parities live in different planes (Ci >= 32); shared otherwise
+    int ymin[2] = {1 << 20, 1 << 20}, ymax[2] = {-(1 << 20), -(1 << 20)}, xmin[2] = {1 << 20, 1 << 20}, xmax[2] = {-(1 << 20), -(1 << 20)};
+    const TapGeom& g = cls[0];
+    const bool split_px = Ci >= 32;
+    for (int t = 0; t < g.ntaps; ++t) {
+      const int fy = floordiv2_h(g.dy[t]), py = g.dy[t] - 2 * fy, fx = floordiv2_h(g.dx[t]), px = split_px ? g.dx[t] - 2 * fx : 0;
+      ymin[py] = std::min(ymin[py], fy); ymax[py] = std::max(ymax[py], fy);
+      xmin[px] = std::min(xmin[px], fx); xmax[px] = std::max(xmax[px], fx);
+    }
+    int ext = 0, extx = 0, pyidx[2] = {-1, -1}, np = 0;
+    for (int py = 0; py < 2; ++py)
+      if (ymin[py] <= ymax[py]) { ext = std::max(ext, ymax[py] - ymin[py]); pyidx[py] = np++; }
+    for (int px = 0; px < 2; ++px)
+      if (xmin[px] <= xmax[px]) extx = std::max(extx, xmax[px] - xmin[px]);
+    p.PH = HALO_TH + ext; p.PW = HALO_TW + extx;
+    p.nplanes = np * J;
+    if (p.nplanes > HALO_MAXPLANES) return false;
+    for (int py = 0; py < 2; ++py) {
+      if (pyidx[py] < 0) continue;
+      for (int j = 0; j < J; ++j) {
+        const int pl = pyidx[py] * J + j;
+        const int px = split_px ? j / (Ci / 32) : 0;
+        p.pl_c[pl] = (short)(j * 32); p.pl_py[pl] = (short)py; p.pl_y[pl] = (short)ymin[py];
+        p.pl_x[pl] = (short)(xmin[px] <= xmax[px] ? xmin[px] : 0);
+      }
+    }
+    p.pitch_bytes = p.PW * p.row_bytes;
+    for (int t = 0; t < g.ntaps; ++t) {
+      const int fy = floordiv2_h(g.dy[t]), py = g.dy[t] - 2 * fy, fx = floordiv2_h(g.dx[t]), px = g.dx[t] - 2 * fx;
+      const int koff = Ci == 16 ? px * 64 : 0;
+      p.tap_plane[0][t] = (unsigned short)(pyidx[py] * J + (split_px ? px * (Ci / 32) : 0));
+      p.tap_aoff[0][t] = ((fy - ymin[py]) * p.PW + (fx - xmin[split_px ? px : 0])) * p.row_bytes + koff;
+    }
+  }
+  p.plane_tx = p.PH * p.PW * p.row_bytes;
+  p.plane_bytes = (p.plane_tx + 1023) / 1024 * 1024;
+  p.stage_bytes = p.nplanes * p.plane_bytes;
+  // ---- cout slice so that the resident weights + >= 1 stage fit ----
+  int ttot = 0;
+  for (int i = 0; i < ncls; ++i) {
+    p.ntaps[i] = cls[i].ntaps; p.coy[i] = (short)cls[i].oy0; p.cox[i] = (short)cls[i].ox0;
+    for (int t = 0; t < cls[i].ntaps; ++t) p.tap_wtile[i][t] = (unsigned short)((ttot + t) * p.kchunks);
+    ttot += cls[i].ntaps;
+  }
+  const int co16 = (p.Co + 15) / 16 * 16;
+  const size_t fixed = 1024 + 16 * sizeof(uint64_t) + (size_t)ttot * p.kchunks * p.ksteps * 8;
+  auto set_npad = [&](int npad) {
+    p.Npad = npad;
+    p.wtile_bytes = (npad * p.KBw * 4 + 1023) / 1024 * 1024;
+    p.w_bytes = ttot * p.kchunks * p.wtile_bytes;
+    p.w_tx = ttot * p.kchunks * npad * p.KBw * 4;
+    p.acc_cols = ncls * npad;
+  };
+  // largest cout slice whose weights leave room for a double-buffered halo tile; failing that, a single stage
+  bool found = false;
+  for (int want = 2; want >= 1 && !found; --want)
+    for (int npad = std::min(co16, 256); npad >= 16; npad -= 16) {
+      if (co16 % npad && npad != std::min(co16, 256)) continue;       // equal slices only
+      set_npad(npad);
+      if (p.acc_cols <= 512 && p.w_bytes + (size_t)want * p.stage_bytes + fixed <= HALO_SMEM_MAX) { p.nstage = want; found = true; break; }
+    }
+  if (!found) return false;
+  p.nmma = ttot * p.kchunks * p.ksteps;
+  if (p.nmma > 1024 || p.w_bytes > (1 << 20) || p.stage_bytes > (1 << 20)) return false;      // 16-bit (>> 4) offsets in the table
+  c.nsplit = (p.Co + p.Npad - 1) / p.Npad;
+  p.nacc = p.acc_cols <= 256 ? 2 : 1;
+  p.tmem_cols = std::max(32, pow2_ge_h(p.nacc * p.acc_cols));
+  c.smem = 1024 + (size_t)p.w_bytes + (size_t)p.nstage * p.stage_bytes + 16 * sizeof(uint64_t) + (size_t)p.nmma * 8;
+  int cps = std::min((int)(HALO_SMEM_MAX / c.smem), 512 / p.tmem_cols);
+  cps = std::max(1, std::min(cps, 2));
+  c.grid_x = std::max(1, std::min(p.ntiles, (NSM * cps + c.nsplit - 1) / c.nsplit));
+  return true;
+}
+
+// Supported AND expected to beat the per-tap kernel: the activations are read once only if the cout slices are few, and
+// TMA / MMA overlap needs the double-buffered halo tile.  DCGANSR_HALO_ALL=1 (tests) takes every supported geometry.
+bool halo_tapconv_supported(const TapGeom* classes, int ncls) {
+  HaloCfg c;
+  if (!halo_cfg(classes, ncls, c)) return false;
+  if (getenv("DCGANSR_HALO_ALL")) return true;
+  return c.nsplit <= 2 && c.p.nstage == 2;
+}
+
+bool k_tapconv_halo(St st, const TapGeom* classes, int ncls, const float* const* bp, const float* in, float* out, int act,
+                    float negval, std::string* err) {
+  HaloCfg c;
+  if (!halo_cfg(classes, ncls, c)) { if (err) *err = "geometry not supported by the halo kernel"; return false; }
+  HaloParams& p = c.p;
+  p.act = act; p.neg = negval;
+  const TapGeom& g = classes[0];
+  EncodeTiledFn enc = tc_encode_fn();
+  CUtensorMap mapA;
+  HaloMaps maps;
+  memset(&maps, 0, sizeof(maps));
+  const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  CUresult r;
+  const CUtensorMapSwizzle aswz = p.row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  if (p.si == 1) {
+    cuuint64_t dims[4] = {(cuuint64_t)g.Ci, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.N};
+    cuuint64_t strides[3] = {(cuuint64_t)g.Ci * 4, (cuuint64_t)g.Wi * g.Ci * 4, (cuuint64_t)g.Hi * g.Wi * g.Ci * 4};
+    cuuint32_t box[4] = {(cuuint32_t)p.KBw, (cuuint32_t)p.PW, (cuuint32_t)p.PH, 1};
+    r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, aswz,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[5] = {(cuuint64_t)2 * g.Ci, (cuuint64_t)g.Wi / 2, 2, (cuuint64_t)g.Hi / 2, (cuuint64_t)g.N};
+    cuuint64_t strides[4] = {(cuuint64_t)2 * g.Ci * 4, (cuuint64_t)g.Wi * g.Ci * 4, (cuuint64_t)2 * g.Wi * g.Ci * 4,
+                             (cuuint64_t)g.Hi * g.Wi * g.Ci * 4};
+    cuuint32_t box[5] = {32, (cuuint32_t)p.PW, 1, (cuuint32_t)p.PH, 1};
+    r = enc(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)in, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, aswz,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled(A, halo) failed: " + std::to_string((int)r); return false; }
+  const CUtensorMapSwizzle wswz = p.KBw == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+  for (int i = 0; i < ncls; ++i) {
+    const cuuint64_t ktot = (cuuint64_t)classes[i].ntaps * g.Ci;
+    cuuint64_t dims[2] = {ktot, (cuuint64_t)g.Co};
+    cuuint64_t strides[1] = {ktot * 4};
+    cuuint32_t box[2] = {(cuuint32_t)p.KBw, (cuuint32_t)p.Npad};
+    r = enc(&maps.b[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)bp[i], dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, wswz,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled(B, halo) failed: " + std::to_string((int)r); return false; }
+  }
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tapconv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      if (err) *err = "cudaFuncSetAttribute(smem, halo) failed";
+      return false;
+    }
+    configured = true;
+  }
+  dim3 grid((unsigned)c.grid_x, (unsigned)c.nsplit);
+  tapconv_halo_kernel<<<grid, HALO_THREADS, c.smem, st.s>>>(mapA, maps, p, out);
+  double flops = 0;
+  for (int i = 0; i < ncls; ++i) flops += 2.0 * g.N * g.Hg * g.Wg * classes[i].ntaps * g.Ci * g.Co;
+  DSR_LAUNCHED(st, "tapconv_halo", flops, WORK_FLOPS);
+  return true;
+}

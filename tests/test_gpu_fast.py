@@ -29,11 +29,24 @@ TC_SHAPES = [
     ("full", 2, 96, 8, 8, 48, 4, 2, 1),        # train.lua G layer 2
     ("full", 3, 48, 6, 10, 24, 4, 2, 1),
     ("full", 2, 32, 5, 5, 16, 3, 1, 1),
+    # spatially large thin layers (the halo-tile kernel's home turf)
+    ("full", 2, 64, 32, 24, 32, 4, 2, 1),      # C2 G layer 3 shape class: 4 sub-pixel classes from one halo tile
+    ("conv", 2, 32, 64, 48, 16, 4, 2, 1),      # C2 G layer 4: stride-2 parity planes; its dgrad contracts 16 channels (64-byte rows)
+    ("conv", 1, 16, 40, 36, 8, 4, 2, 1),       # Ci = 16 through the parity view (two taps share a 128-byte row), ragged tiles
+    ("full", 1, 96, 20, 12, 48, 4, 2, 1),      # train.lua G layer 2: 3 planes
+    ("conv", 3, 32, 17, 19, 24, 3, 1, 1),      # stride 1, odd sizes: partial tiles in both directions
 ]
 
 
+@pytest.mark.parametrize("halo_all", [False, True])
 @pytest.mark.parametrize("shape", TC_SHAPES)
-def test_tc_conv_fwd_dgrad(ctx_fast, shape):
+def test_tc_conv_fwd_dgrad(ctx_fast, shape, halo_all, monkeypatch):
+    # halo_all: force the weights-resident halo-tile kernel on every geometry it supports (by default it only takes
+    # the layers where it is expected to win), so its cout-sliced / single-stage configurations are covered too
+    if halo_all:
+        monkeypatch.setenv("DCGANSR_HALO_ALL", "1")
+    else:
+        monkeypatch.delenv("DCGANSR_HALO_ALL", raising=False)
     kind, n, cin, h, w, cout, k, s, p = shape
     full = kind == "full"
     r = rng(hash(shape[1:]) % 2**31)
