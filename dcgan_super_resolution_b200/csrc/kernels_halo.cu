@@ -26,6 +26,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <vector>
 
 #define NSM 148
 #define HALO_TH 16
@@ -33,9 +34,15 @@
 #define HALO_MAXCLS 4
 #define HALO_MAXTAPS 16
 #define HALO_MAXPLANES 8
-#define HALO_THREADS 192
+#define HALO_MAXGRP 4
+#define HALO_MAXSLOT 8
 
 struct HaloMaps { CUtensorMap b[HALO_MAXCLS]; };
+#define HALO_MAXMMA 256
+// MMA issue table (kernel parameter = constant bank, so the issuing warp reads it through the uniform datapath):
+// one entry per tcgen05.mma of a tile {A offset >> 4, W offset >> 4, TMEM column | accumulate << 31, instruction descriptor}:
+// everything the issuing thread would otherwise have to compute per MMA.
+struct HaloTab { uint4 e[HALO_MAXMMA]; };
 
 struct HaloParams {
   int N, Hg, Wg, tiles_x, tiles_y, ntiles;
@@ -47,11 +54,16 @@ struct HaloParams {
   int Npad, wtile_bytes, w_bytes, w_tx;
   int ntaps[HALO_MAXCLS];
   short coy[HALO_MAXCLS], cox[HALO_MAXCLS];
-  unsigned short tap_plane[HALO_MAXCLS][HALO_MAXTAPS], tap_wtile[HALO_MAXCLS][HALO_MAXTAPS];
+  unsigned short tap_plane[HALO_MAXCLS][HALO_MAXTAPS], tap_wtile[HALO_MAXCLS][HALO_MAXTAPS], tap_wstride[HALO_MAXCLS][HALO_MAXTAPS];
   int tap_aoff[HALO_MAXCLS][HALO_MAXTAPS];
   int nstage, stage_bytes, acc_cols, nacc, tmem_cols, nmma;
+  int ngrp, gbeg[HALO_MAXGRP + 1];      // MMA issuer warps and their table ranges
+  int nslots;                            // accumulator slots (Npad TMEM columns each)
+  int cls_nsl[HALO_MAXCLS];              // class c = sum of slots cls_sl[c][0 .. cls_nsl[c])
+  unsigned char cls_sl[HALO_MAXCLS][4];
   int act;
   float neg;
+  int dbg;                               // DCGANSR_HALO_DBG (timing experiments only): 1 skip MMAs, 2 skip stores, 4 skip the halo TMA loads
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
@@ -69,8 +81,68 @@ __device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr, uint32_t sbo, ui
   return d;
 }
 
-__global__ void __launch_bounds__(HALO_THREADS) tapconv_halo_kernel(const __grid_constant__ CUtensorMap mapA,
+// 8 epilogue warps: two per TMEM lane quarter (`half` 0 / 1), which split the tile's (class, 16-column chunk) items between
+// them.  Per item all TMEM loads (one per accumulator slot of the class) are issued before a single wait.
+template <int ACT>
+__device__ __forceinline__ void halo_epilogue(const HaloParams& p, float* __restrict__ out, uint32_t tmem_base, uint64_t* acc_full,
+                                              uint64_t* acc_empty, int warp, int half, int lane, int n0) {
+  const int q = warp & 3;                       // TMEM lane quarter this warp may access
+  const int r = q * 32 + lane;                  // tile row = pixel
+  const int w = r % HALO_TW, h = r / HALO_TW;
+  const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+  const int chunks = p.Npad >> 4;
+  const int nitems = p.ncls * chunks;
+  int it = 0;
+  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    const int buf = it % p.nacc;
+    const uint32_t aph = (uint32_t)(it / p.nacc) & 1u;
+    int tt = tile;
+    const int tx = tt % p.tiles_x; tt /= p.tiles_x;
+    const int ty = tt % p.tiles_y; tt /= p.tiles_y;
+    const int n = tt, gy = ty * HALO_TH + h, gx = tx * HALO_TW + w;
+    const bool valid = gy < p.Hg && gx < p.Wg && !(p.dbg & 2);
+    float* pix = out + ((int64_t)(n * p.Ho + gy * p.so) * p.Wo + gx * p.so) * p.Co + n0;
+    const uint32_t cbase = lane_base + (uint32_t)(buf * p.acc_cols);
+    mbar_wait(smem_u32(&acc_full[buf]), aph);
+    tc_fence_after();
+    for (int item = half; item < nitems; item += 2) {
+      const int c = item / chunks, c0 = (item % chunks) << 4;
+      float* orow = pix + ((int64_t)p.coy[c] * p.Wo + p.cox[c]) * p.Co + c0;
+      const int nsl = p.cls_nsl[c];
+      uint32_t v[16];
+      tmem_ld16(cbase + (uint32_t)(p.cls_sl[c][0] * p.Npad + c0), v);
+      if (nsl == 1) {
+        tmem_ld_wait();
+      } else if (nsl == 2) {
+        uint32_t u[16];
+        tmem_ld16(cbase + (uint32_t)(p.cls_sl[c][1] * p.Npad + c0), u);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+      } else {
+        uint32_t u[16], x[16], y[16];
+        tmem_ld16(cbase + (uint32_t)(p.cls_sl[c][1] * p.Npad + c0), u);
+        tmem_ld16(cbase + (uint32_t)(p.cls_sl[c][2] * p.Npad + c0), x);
+        if (nsl > 3) tmem_ld16(cbase + (uint32_t)(p.cls_sl[c][3] * p.Npad + c0), y);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float sum = (__uint_as_float(v[j]) + __uint_as_float(u[j])) + __uint_as_float(x[j]);
+          if (nsl > 3) sum += __uint_as_float(y[j]);
+          v[j] = __float_as_uint(sum);
+        }
+      }
+      if (valid) store_row<ACT, 16>(orow, v, n0 + c0, p.Co, p.neg);
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+  }
+}
+
+__global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                     const __grid_constant__ HaloMaps mapsB,
+                                                                    const __grid_constant__ HaloTab tab,
                                                                     const HaloParams p, float* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -81,38 +153,25 @@ __global__ void __launch_bounds__(HALO_THREADS) tapconv_halo_kernel(const __grid
   uint64_t* a_full = bars + 1;
   uint64_t* a_empty = bars + 3;
   uint64_t* acc_full = bars + 5;
-  uint64_t* acc_empty = bars + 7;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-  // MMA issue table: one 8-byte entry per tcgen05.mma of a tile {A offset >> 4 | W offset >> 4 << 16, TMEM column | accumulate << 16}.
-  // The MMAs of these thin layers are small (N = 16..64: 8..32 tensor cycles each), so the single issuing thread must
-  // not spend more than a few instructions per MMA: everything that does not depend on the tile is precomputed here.
-  uint2* mma_tab = reinterpret_cast<uint2*>(bars + 16);
-
+  uint64_t* acc_empty = bars + 9;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * p.Npad;
-  for (int i = threadIdx.x; i < p.nmma; i += HALO_THREADS) {
-    // decode i -> (class, tap, chunk, kstep) in issue order
-    int rem = i, c = 0;
-    const int per_tap = p.kchunks * p.ksteps;
-    while (rem >= p.ntaps[c] * per_tap) { rem -= p.ntaps[c] * per_tap; ++c; }
-    const int t = rem / per_tap, q = (rem % per_tap) / p.ksteps, k = rem % p.ksteps;
-    const uint32_t aoff = (uint32_t)(p.tap_plane[c][t] + q) * p.plane_bytes + (uint32_t)p.tap_aoff[c][t] + k * 32;
-    const uint32_t woff = (uint32_t)(p.tap_wtile[c][t] + q) * p.wtile_bytes + k * 32;
-    mma_tab[i] = make_uint2((aoff >> 4) | ((woff >> 4) << 16), (uint32_t)(c * p.Npad) | (rem ? 0x10000u : 0u));
-  }
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     mbar_init(smem_u32(w_full), 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(smem_u32(&a_full[s]), 1);
-      mbar_init(smem_u32(&a_empty[s]), 1);
-      mbar_init(smem_u32(&acc_full[s]), 1);
-      mbar_init(smem_u32(&acc_empty[s]), 4);
+      mbar_init(smem_u32(&a_empty[s]), (uint32_t)p.ngrp);
+    }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(smem_u32(&acc_full[s]), (uint32_t)p.ngrp);
+      mbar_init(smem_u32(&acc_empty[s]), 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == 1) {      // TMEM owner
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -131,9 +190,10 @@ __global__ void __launch_bounds__(HALO_THREADS) tapconv_halo_kernel(const __grid
       for (int c = 0; c < p.ncls; ++c)
         for (int t = 0; t < p.ntaps[c]; ++t)
           for (int q = 0; q < p.kchunks; ++q)
-            tma_load_2d(smem_u32(sW) + (uint32_t)(p.tap_wtile[c][t] + q) * p.wtile_bytes, &mapsB.b[c], wf,
+            tma_load_2d(smem_u32(sW) + (uint32_t)(p.tap_wtile[c][t] + q * p.tap_wstride[c][t]) * p.wtile_bytes, &mapsB.b[c], wf,
                         t * p.Ci + q * p.KBw, n0);
       int it = 0;
+      const int pf_dist = p.nstage + 1;
       for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
         const int s = it % p.nstage;
         const uint32_t ph = (uint32_t)(it / p.nstage) & 1u;
@@ -141,8 +201,25 @@ __global__ void __launch_bounds__(HALO_THREADS) tapconv_halo_kernel(const __grid
         const int tx = tt % p.tiles_x; tt /= p.tiles_x;
         const int ty = tt % p.tiles_y; tt /= p.tiles_y;
         const int n = tt, gy0 = ty * HALO_TH, gx0 = tx * HALO_TW;
+        // L2 prefetch of the halo tile `pf_dist` tiles ahead: the smem ring is only 1-2 tiles deep (the weights take
+        // most of the shared memory), which alone does not keep enough DRAM reads in flight
+        {
+          const int ptile = tile + pf_dist * (int)gridDim.x;
+          if (ptile < p.ntiles) {
+            int pt = ptile;
+            const int ptx = pt % p.tiles_x; pt /= p.tiles_x;
+            const int pty = pt % p.tiles_y; pt /= p.tiles_y;
+            for (int pl = 0; pl < p.nplanes; ++pl) {
+              if (p.si == 1)
+                tma_prefetch_4d(&mapA, p.pl_c[pl], ptx * HALO_TW + p.pl_x[pl], pty * HALO_TH + p.pl_y[pl], pt);
+              else
+                tma_prefetch_5d(&mapA, p.pl_c[pl], ptx * HALO_TW + p.pl_x[pl], p.pl_py[pl], pty * HALO_TH + p.pl_y[pl], pt);
+            }
+          }
+        }
         mbar_wait(smem_u32(&a_empty[s]), ph ^ 1u);
         const uint32_t fb = smem_u32(&a_full[s]);
+        if (p.dbg & 4) { mbar_arrive(fb); continue; }
         mbar_expect_tx(fb, (uint32_t)(p.nplanes * p.plane_tx));
         const uint32_t dst0 = smem_u32(sA + (size_t)s * p.stage_bytes);
         for (int pl = 0; pl < p.nplanes; ++pl) {
@@ -154,11 +231,16 @@ __global__ void __launch_bounds__(HALO_THREADS) tapconv_halo_kernel(const __grid
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.Npad >> 3) << 17) | ((128u >> 4) << 24);
+  } else if (warp <= p.ngrp) {
+    // ===================== MMA issuers =====================
+    // The MMAs of these thin layers are small (N = 16..64: 8..32 tensor cycles each) while issuing one costs a single
+    // thread ~40 cycles (descriptor arithmetic + 5 R2UR), so the tile's MMA list is split over up to 4 issuer warps,
+    // each accumulating into its own TMEM slot(s): a class per issuer when there are sub-pixel classes, a range of
+    // taps otherwise (the epilogue then adds the partial accumulators).
+    const int grp = warp - 1;
     const uint64_t wl = p.KBw == 32 ? 2ull : (p.KBw == 16 ? 4ull : 6ull);
     const uint32_t w_sbo = 8u * (uint32_t)p.KBw * 4u;
+    const int ibeg = p.gbeg[grp], iend = p.gbeg[grp + 1];
     mbar_wait(smem_u32(w_full), 0);
     int it = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
@@ -174,63 +256,24 @@ __global__ void __launch_bounds__(HALO_THREADS) tapconv_halo_kernel(const __grid
         const uint64_t bdesc = make_desc_k(smem_u32(sW), w_sbo, wl);
         const uint32_t dbase = tmem_base + (uint32_t)(buf * p.acc_cols);
 #pragma unroll 4
-        for (int i = 0; i < p.nmma; ++i) {
-          const uint2 e = mma_tab[i];
-          umma_tf32(dbase + (e.y & 0xFFFFu), adesc + (uint64_t)(e.x & 0xFFFFu), bdesc + (uint64_t)(e.x >> 16), idesc, e.y >> 16);
+        for (int i = ibeg; i < ((p.dbg & 1) ? ibeg + 1 : iend); ++i) {
+          const uint4 e = tab.e[i];
+          umma_tf32(dbase + (e.z & 0xFFFFu), adesc + (uint64_t)e.x, bdesc + (uint64_t)e.y, e.w, (uint32_t)((int)e.z < 0 ? 0 : 1));
         }
         umma_commit(smem_u32(&a_empty[s]));
         umma_commit(smem_u32(&acc_full[buf]));
       }
       __syncwarp();
     }
-  } else {
+  } else if (warp <= p.ngrp + 8) {
+    const int half = (warp - p.ngrp - 1) >> 2;
     // ===================== epilogue: TMEM -> registers -> activation -> NHWC global =====================
-    const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;                  // tile row = pixel
-    const int w = r % HALO_TW, h = r / HALO_TW;
-    const bool vec = (p.Co & 3) == 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int buf = it % p.nacc;
-      const uint32_t aph = (uint32_t)(it / p.nacc) & 1u;
-      int tt = tile;
-      const int tx = tt % p.tiles_x; tt /= p.tiles_x;
-      const int ty = tt % p.tiles_y; tt /= p.tiles_y;
-      const int n = tt, gy = ty * HALO_TH + h, gx = tx * HALO_TW + w;
-      const bool valid = gy < p.Hg && gx < p.Wg;
-      mbar_wait(smem_u32(&acc_full[buf]), aph);
-      tc_fence_after();
-      for (int c = 0; c < p.ncls; ++c) {
-        float* orow = out + ((int64_t)(n * p.Ho + gy * p.so + p.coy[c]) * p.Wo + gx * p.so + p.cox[c]) * p.Co;
-        for (int c0 = 0; c0 < p.Npad; c0 += 16) {
-          uint32_t v[16];
-          tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * p.acc_cols + c * p.Npad + c0), v);
-          tmem_ld_wait();
-          if (valid) {
-            const int co = n0 + c0;
-            if (vec) {
-#pragma unroll
-              for (int j = 0; j < 16; j += 4) {
-                if (co + j < p.Co) {
-                  float4 o;
-                  o.x = act_apply_t(__uint_as_float(v[j]), p.act, p.neg);
-                  o.y = act_apply_t(__uint_as_float(v[j + 1]), p.act, p.neg);
-                  o.z = act_apply_t(__uint_as_float(v[j + 2]), p.act, p.neg);
-                  o.w = act_apply_t(__uint_as_float(v[j + 3]), p.act, p.neg);
-                  *reinterpret_cast<float4*>(orow + co + j) = o;
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (co + j < p.Co) orow[co + j] = act_apply_t(__uint_as_float(v[j]), p.act, p.neg);
-            }
-          }
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+    switch (p.act) {
+      case ACT_RELU: halo_epilogue<ACT_RELU>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0); break;
+      case ACT_LRELU: halo_epilogue<ACT_LRELU>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0); break;
+      case ACT_TANH: halo_epilogue<ACT_TANH>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0); break;
+      case ACT_SIGMOID: halo_epilogue<ACT_SIGMOID>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0); break;
+      default: halo_epilogue<ACT_NONE>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0); break;
     }
   }
   tc_fence_before();
@@ -247,7 +290,7 @@ __global__ void __launch_bounds__(HALO_THREADS) tapconv_halo_kernel(const __grid
 static inline int pow2_ge_h(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 static inline int floordiv2_h(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
 
-struct HaloCfg { HaloParams p; int nsplit; size_t smem; int grid_x; };
+struct HaloCfg { HaloParams p; HaloTab tab; int nsplit; size_t smem; int grid_x; };
 
 #define HALO_SMEM_MAX 232448      // 227 KB: the sm_100 per-block dynamic shared memory limit
 
@@ -255,6 +298,7 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
   if (!tc_encode_fn() || ncls < 1 || ncls > HALO_MAXCLS) return false;
   HaloParams& p = c.p;
   memset(&p, 0, sizeof(p));
+  memset(&c.tab, 0, sizeof(c.tab));
   const TapGeom& g0 = cls[0];
   const int Ci = g0.Ci;
   if (!(Ci % 32 == 0 || Ci == 16)) return false;
@@ -341,36 +385,168 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
   int ttot = 0;
   for (int i = 0; i < ncls; ++i) {
     p.ntaps[i] = cls[i].ntaps; p.coy[i] = (short)cls[i].oy0; p.cox[i] = (short)cls[i].ox0;
-    for (int t = 0; t < cls[i].ntaps; ++t) p.tap_wtile[i][t] = (unsigned short)((ttot + t) * p.kchunks);
     ttot += cls[i].ntaps;
   }
+  // 2 x 2 sub-pixel classes: taps of different classes that read the SAME shifted window are merged into one MMA
+  // (N = 2 or 4 classes) -- the A operand is read from shared memory once per shift instead of once per (class, tap),
+  // which is what bounds these N = 16..64 MMAs.  See plan_merged().
+  int ring[5] = {-1, -1, -1, -1, -1};
+  bool try_merge = ncls == 4 && p.so == 2 && !getenv("DCGANSR_HALO_NOMERGE");
+  if (try_merge) {
+    int ci[2][2] = {{-1, -1}, {-1, -1}};
+    for (int i = 0; i < 4; ++i)
+      if (cls[i].oy0 >= 0 && cls[i].oy0 < 2 && cls[i].ox0 >= 0 && cls[i].ox0 < 2) ci[cls[i].oy0][cls[i].ox0] = i;
+    if (ci[0][0] < 0 || ci[0][1] < 0 || ci[1][0] < 0 || ci[1][1] < 0) try_merge = false;
+    else { ring[0] = ci[0][0]; ring[1] = ci[0][1]; ring[2] = ci[1][1]; ring[3] = ci[1][0]; ring[4] = ci[0][0]; }
+  }
   const int co16 = (p.Co + 15) / 16 * 16;
-  const size_t fixed = 1024 + 16 * sizeof(uint64_t) + (size_t)ttot * p.kchunks * p.ksteps * 8;
+  const size_t fixed = 1024 + 16 * sizeof(uint64_t);
   auto set_npad = [&](int npad) {
     p.Npad = npad;
-    p.wtile_bytes = (npad * p.KBw * 4 + 1023) / 1024 * 1024;
+    p.wtile_bytes = npad * p.KBw * 4;            // a multiple of 1024 (npad % 16 == 0, KBw >= 16)
     p.w_bytes = ttot * p.kchunks * p.wtile_bytes;
-    p.w_tx = ttot * p.kchunks * npad * p.KBw * 4;
-    p.acc_cols = ncls * npad;
+    p.w_tx = p.w_bytes;
+    p.acc_cols = (try_merge ? 5 : (ncls > 1 ? ncls : std::min(HALO_MAXGRP, cls[0].ntaps))) * npad;
   };
   // largest cout slice whose weights leave room for a double-buffered halo tile; failing that, a single stage
   bool found = false;
   for (int want = 2; want >= 1 && !found; --want)
     for (int npad = std::min(co16, 256); npad >= 16; npad -= 16) {
       if (co16 % npad && npad != std::min(co16, 256)) continue;       // equal slices only
+      if (try_merge && 4 * npad > 256) continue;                      // a merged MMA spans up to 4 slots (N <= 256)
       set_npad(npad);
       if (p.acc_cols <= 512 && p.w_bytes + (size_t)want * p.stage_bytes + fixed <= HALO_SMEM_MAX) { p.nstage = want; found = true; break; }
     }
   if (!found) return false;
-  p.nmma = ttot * p.kchunks * p.ksteps;
-  if (p.nmma > 1024 || p.w_bytes > (1 << 20) || p.stage_bytes > (1 << 20)) return false;      // 16-bit (>> 4) offsets in the table
+  if (p.w_bytes > (1 << 20) || p.stage_bytes > (1 << 20)) return false;      // 16-bit (>> 4) offsets in the table
+
+  struct Op { int a_plane, a_off, m, slot0, cl[4], tp[4]; bool init; };
+  std::vector<Op> ops;
+  bool merged = false;
+  if (try_merge) {
+    // group (class, tap) by shift
+    struct Sh { int dy, dx, n, cl[4], tp[4]; };
+    std::vector<Sh> shifts;
+    for (int i = 0; i < 4; ++i)
+      for (int t = 0; t < cls[i].ntaps; ++t) {
+        Sh* f = nullptr;
+        for (auto& sh : shifts) if (sh.dy == cls[i].dy[t] && sh.dx == cls[i].dx[t]) f = &sh;
+        if (!f) { shifts.push_back(Sh{cls[i].dy[t], cls[i].dx[t], 0, {0, 0, 0, 0}, {0, 0, 0, 0}}); f = &shifts.back(); }
+        if (f->n < 4) { f->cl[f->n] = i; f->tp[f->n] = t; ++f->n; } else try_merge = false;   // a class twice on one shift
+      }
+    auto tap_of = [&](const Sh& sh, int c) { for (int j = 0; j < sh.n; ++j) if (sh.cl[j] == c) return sh.tp[j]; return -1; };
+    auto single = [&](const Sh& sh, int j, int slot) {
+      Op o; memset(&o, 0, sizeof(o));
+      o.a_plane = p.tap_plane[sh.cl[j]][sh.tp[j]]; o.a_off = p.tap_aoff[sh.cl[j]][sh.tp[j]]; o.m = 1; o.slot0 = slot; o.cl[0] = sh.cl[j]; o.tp[0] = sh.tp[j];
+      return o;
+    };
+    int full_idx = -1;
+    for (auto& sh : shifts) {
+      if (!try_merge) break;
+      int run0 = -1, runm = 0;
+      if (sh.n == 4) { run0 = 0; runm = 4; }
+      else if (sh.n == 2)
+        for (int r = 0; r < 4; ++r)
+          if ((ring[r] == sh.cl[0] && ring[r + 1] == sh.cl[1]) || (ring[r] == sh.cl[1] && ring[r + 1] == sh.cl[0])) { run0 = r; runm = 2; }
+      if (run0 >= 0) {
+        Op o; memset(&o, 0, sizeof(o));
+        o.a_plane = p.tap_plane[sh.cl[0]][sh.tp[0]]; o.a_off = p.tap_aoff[sh.cl[0]][sh.tp[0]]; o.m = runm; o.slot0 = run0;
+        for (int j = 0; j < runm; ++j) { o.cl[j] = ring[run0 + j]; o.tp[j] = tap_of(sh, ring[run0 + j]); }
+        if (runm == 4) full_idx = (int)ops.size();
+        ops.push_back(o);
+      } else {
+        for (int j = 0; j < sh.n; ++j) {
+          int slot = 0;
+          for (int r = 0; r < 4; ++r) if (ring[r] == sh.cl[j]) slot = r;
+          ops.push_back(single(sh, j, slot));
+        }
+      }
+    }
+    if (try_merge && full_idx >= 0) {
+      // slot 4 duplicates class ring[0] so that the pair {ring[3], ring[0]} is a contiguous run; it needs an op of its own
+      // to initialise it: a single-class op of ring[0] is moved there.  Without one, that pair is split into singles.
+      bool uses4 = false;
+      for (auto& o : ops) if (o.slot0 + o.m > 4) uses4 = true;
+      int init4 = -1;
+      if (uses4)
+        for (size_t i = 0; i < ops.size(); ++i) if (ops[i].m == 1 && ops[i].cl[0] == ring[0]) { init4 = (int)i; break; }
+      if (uses4 && init4 < 0) {
+        std::vector<Op> o2;
+        for (auto& o : ops) {
+          if (o.slot0 + o.m > 4) {
+            Op a = o, b = o;
+            a.m = 1; a.slot0 = 3; a.cl[0] = o.cl[0]; a.tp[0] = o.tp[0];
+            b.m = 1; b.slot0 = 0; b.cl[0] = o.cl[1]; b.tp[0] = o.tp[1];
+            b.a_plane = p.tap_plane[b.cl[0]][b.tp[0]]; b.a_off = p.tap_aoff[b.cl[0]][b.tp[0]];
+            o2.push_back(a); o2.push_back(b);
+          } else o2.push_back(o);
+        }
+        ops.swap(o2);
+        uses4 = false;
+        for (size_t i = 0; i < ops.size(); ++i) if (ops[i].m == 4) full_idx = (int)i;
+      }
+      if (init4 >= 0) ops[init4].slot0 = 4;
+      // order: the all-class op first (initialises slots 0..3), then slot 4's initialiser, then the rest
+      std::vector<Op> ord;
+      ops[full_idx].init = true;
+      ord.push_back(ops[full_idx]);
+      if (init4 >= 0) { ops[init4].init = true; ord.push_back(ops[init4]); }
+      for (size_t i = 0; i < ops.size(); ++i) if ((int)i != full_idx && (int)i != init4) ord.push_back(ops[i]);
+      ops.swap(ord);
+      merged = true;
+      p.ngrp = 1; p.nslots = uses4 ? 5 : 4;
+      for (int r = 0; r < 4; ++r) { p.cls_nsl[ring[r]] = 1; p.cls_sl[ring[r]][0] = (unsigned char)r; }
+      if (uses4) { p.cls_nsl[ring[0]] = 2; p.cls_sl[ring[0]][1] = 4; }
+      p.gbeg[0] = 0;
+    }
+  }
+  if (!merged) {
+    // issuer groups and accumulator slots: one class per issuer, or (single class) contiguous tap ranges with partial sums
+    ops.clear();
+    p.ngrp = ncls > 1 ? ncls : std::min(HALO_MAXGRP, p.ntaps[0]);
+    p.nslots = p.ngrp;
+    for (int cl = 0; cl < ncls; ++cl) p.cls_nsl[cl] = 0;
+    for (int g = 0; g < p.ngrp; ++g) {
+      p.gbeg[g] = (int)ops.size() * p.kchunks * p.ksteps;
+      const int cl = ncls > 1 ? g : 0;
+      const int tb = ncls > 1 ? 0 : g * p.ntaps[0] / p.ngrp, te = ncls > 1 ? p.ntaps[cl] : (g + 1) * p.ntaps[0] / p.ngrp;
+      p.cls_sl[cl][p.cls_nsl[cl]++] = (unsigned char)g;
+      for (int t = tb; t < te; ++t) {
+        Op o; memset(&o, 0, sizeof(o));
+        o.a_plane = p.tap_plane[cl][t]; o.a_off = p.tap_aoff[cl][t]; o.m = 1; o.slot0 = g; o.cl[0] = cl; o.tp[0] = t; o.init = t == tb;
+        ops.push_back(o);
+      }
+    }
+  }
+  p.nmma = (int)ops.size() * p.kchunks * p.ksteps;
+  if (p.nmma > HALO_MAXMMA) return false;
+  p.gbeg[p.ngrp] = p.nmma;
+  {
+    int i = 0, wt = 0;       // wt: running weight-tile index
+    for (auto& o : ops) {
+      for (int j = 0; j < o.m; ++j) { p.tap_wtile[o.cl[j]][o.tp[j]] = (unsigned short)(wt + j); p.tap_wstride[o.cl[j]][o.tp[j]] = (unsigned short)o.m; }
+      for (int q = 0; q < p.kchunks; ++q)
+        for (int k = 0; k < p.ksteps; ++k, ++i) {
+          const uint32_t aoff = (uint32_t)(o.a_plane + q) * p.plane_bytes + (uint32_t)o.a_off + k * 32;
+          const uint32_t woff = (uint32_t)(wt + q * o.m) * p.wtile_bytes + k * 32;
+          const uint32_t accum = (o.init && q == 0 && k == 0) ? 0u : 1u;
+          // D = f32, A = B = tf32, K-major, M = 128, N = m * Npad
+          const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((o.m * p.Npad) >> 3) << 17) | ((128u >> 4) << 24);
+          c.tab.e[i] = make_uint4(aoff >> 4, woff >> 4, (uint32_t)(o.slot0 * p.Npad) | (accum ? 0u : 0x80000000u), idesc);
+        }
+      wt += o.m * p.kchunks;
+    }
+  }
+  p.acc_cols = p.nslots * p.Npad;
+  if (p.acc_cols > 512) return false;
   c.nsplit = (p.Co + p.Npad - 1) / p.Npad;
-  p.nacc = p.acc_cols <= 256 ? 2 : 1;
+  p.nacc = std::max(1, std::min(4, 512 / p.acc_cols));      // accumulator ring in TMEM
+  if (const char* e = getenv("DCGANSR_HALO_NACC")) p.nacc = std::max(1, std::min(p.nacc, atoi(e)));
   p.tmem_cols = std::max(32, pow2_ge_h(p.nacc * p.acc_cols));
-  c.smem = 1024 + (size_t)p.w_bytes + (size_t)p.nstage * p.stage_bytes + 16 * sizeof(uint64_t) + (size_t)p.nmma * 8;
-  int cps = std::min((int)(HALO_SMEM_MAX / c.smem), 512 / p.tmem_cols);
-  cps = std::max(1, std::min(cps, 2));
-  c.grid_x = std::max(1, std::min(p.ntiles, (NSM * cps + c.nsplit - 1) / c.nsplit));
+  if (p.tmem_cols > 512) return false;
+  c.smem = 1024 + (size_t)p.w_bytes + (size_t)p.nstage * p.stage_bytes + 16 * sizeof(uint64_t);
+  // one persistent CTA per SM (13 warps x ~100 registers; the 8 epilogue warps provide the memory-level parallelism)
+  c.grid_x = std::max(1, std::min(p.ntiles, (NSM + c.nsplit - 1) / c.nsplit));
   return true;
 }
 
@@ -389,6 +565,7 @@ bool k_tapconv_halo(St st, const TapGeom* classes, int ncls, const float* const*
   if (!halo_cfg(classes, ncls, c)) { if (err) *err = "geometry not supported by the halo kernel"; return false; }
   HaloParams& p = c.p;
   p.act = act; p.neg = negval;
+  if (const char* d = getenv("DCGANSR_HALO_DBG")) p.dbg = atoi(d);
   const TapGeom& g = classes[0];
   EncodeTiledFn enc = tc_encode_fn();
   CUtensorMap mapA;
@@ -431,7 +608,7 @@ bool k_tapconv_halo(St st, const TapGeom* classes, int ncls, const float* const*
     configured = true;
   }
   dim3 grid((unsigned)c.grid_x, (unsigned)c.nsplit);
-  tapconv_halo_kernel<<<grid, HALO_THREADS, c.smem, st.s>>>(mapA, maps, p, out);
+  tapconv_halo_kernel<<<grid, 32 * (9 + p.ngrp), c.smem, st.s>>>(mapA, maps, c.tab, p, out);
   double flops = 0;
   for (int i = 0; i < ncls; ++i) flops += 2.0 * g.N * g.Hg * g.Wg * classes[i].ntaps * g.Ci * g.Co;
   DSR_LAUNCHED(st, "tapconv_halo", flops, WORK_FLOPS);

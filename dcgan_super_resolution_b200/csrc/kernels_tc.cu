@@ -203,14 +203,23 @@ __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_con
     if (valid) orow = out + ((int64_t)(n * p.Ho + gy * p.so + p.oy0) * p.Wo + gx * p.so + p.ox0) * p.Co;
     mbar_wait(smem_u32(tmem_full), 0);
     tc_fence_after();
-    const bool vec = (p.Co & 3) == 0;
+    const bool vec = (p.Co & 3) == 0, vec8 = (p.Co & 7) == 0;
     for (int c0 = 0; c0 < p.BN; c0 += 16) {
       uint32_t v[16];
       tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
       tmem_ld_wait();
       if (valid) {
         const int co = n0 + c0;
-        if (vec) {
+        if (vec8) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 8) {
+            if (co + j < p.Co)
+              st_global_v8(orow + co + j, act_apply_t(__uint_as_float(v[j]), p.act, p.neg), act_apply_t(__uint_as_float(v[j + 1]), p.act, p.neg),
+                           act_apply_t(__uint_as_float(v[j + 2]), p.act, p.neg), act_apply_t(__uint_as_float(v[j + 3]), p.act, p.neg),
+                           act_apply_t(__uint_as_float(v[j + 4]), p.act, p.neg), act_apply_t(__uint_as_float(v[j + 5]), p.act, p.neg),
+                           act_apply_t(__uint_as_float(v[j + 6]), p.act, p.neg), act_apply_t(__uint_as_float(v[j + 7]), p.act, p.neg));
+          }
+        } else if (vec) {
 #pragma unroll
           for (int j = 0; j < 16; j += 4) {
             if (co + j < p.Co) {

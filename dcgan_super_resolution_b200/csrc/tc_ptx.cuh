@@ -58,6 +58,14 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
                "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
                : "memory");
 }
+// L2 prefetch of a TMA box (no shared memory, no barrier): puts the DRAM reads of a later tile in flight early
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* map, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap* map, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -77,6 +85,16 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
         "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+      "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
+        "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major shared-memory matrix descriptor (sm_100 "version 1"): rows of KB floats (= the swizzle span),
@@ -91,6 +109,45 @@ __device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr, int kb) {
   d |= (uint64_t)1 << 46;                                                     // descriptor version (Blackwell)
   d |= layout << 61;
   return d;
+}
+
+// 256-bit global store (sm_100: STG.256): one full 32-byte sector per lane
+__device__ __forceinline__ void st_global_v8(float* p, float a, float b, float c, float d, float e, float f, float g, float h) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d), "f"(e), "f"(f), "f"(g), "f"(h)
+               : "memory");
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_c(float v, float neg) {
+  if (ACT == ACT_RELU) return v > 0.f ? v : 0.f;
+  if (ACT == ACT_LRELU) return v > 0.f ? v : v * neg;
+  if (ACT == ACT_TANH) return tanhf(v);
+  if (ACT == ACT_SIGMOID) return 1.f / (1.f + expf(-v));
+  return v;
+}
+// NV accumulator values of one pixel -> activation -> NHWC row (dst = channel `co` of the pixel).  8-channel groups as
+// 256-bit stores when the row is 32-byte aligned (Co % 8 == 0), else 16-byte or scalar stores; channels >= Co are dropped.
+template <int ACT, int NV>
+__device__ __forceinline__ void store_row(float* dst, const uint32_t (&v)[NV], int co, int Co, float neg, int chunk_stride = 8) {
+  if ((Co & 7) == 0) {
+#pragma unroll
+    for (int j = 0; j < NV; j += 8)
+      if (co + j < Co)
+        st_global_v8(dst + (j >> 3) * chunk_stride, act_c<ACT>(__uint_as_float(v[j]), neg), act_c<ACT>(__uint_as_float(v[j + 1]), neg),
+                     act_c<ACT>(__uint_as_float(v[j + 2]), neg), act_c<ACT>(__uint_as_float(v[j + 3]), neg),
+                     act_c<ACT>(__uint_as_float(v[j + 4]), neg), act_c<ACT>(__uint_as_float(v[j + 5]), neg),
+                     act_c<ACT>(__uint_as_float(v[j + 6]), neg), act_c<ACT>(__uint_as_float(v[j + 7]), neg));
+  } else if ((Co & 3) == 0) {
+#pragma unroll
+    for (int j = 0; j < NV; j += 4)
+      if (co + j < Co)
+        *reinterpret_cast<float4*>(dst + j) = make_float4(act_c<ACT>(__uint_as_float(v[j]), neg), act_c<ACT>(__uint_as_float(v[j + 1]), neg),
+                                                          act_c<ACT>(__uint_as_float(v[j + 2]), neg), act_c<ACT>(__uint_as_float(v[j + 3]), neg));
+  } else {
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+      if (co + j < Co) dst[j] = act_c<ACT>(__uint_as_float(v[j]), neg);
+  }
 }
 
 __device__ __forceinline__ float act_apply_t(float v, int act, float neg) {
