@@ -145,6 +145,11 @@ bool k_tapconv_tc(St st, const TapGeom& g, const float* in, const float* bp, flo
 bool halo_tapconv_supported(const TapGeom* classes, int ncls);
 bool k_tapconv_halo(St st, const TapGeom* classes, int ncls, const float* const* bp, const float* in, float* out, int act,
                     float negval, std::string* err);
+// ---- kernels_wgrad_halo.cu : stacked-shift halo-tile wgrad ----
+bool wgrad_halo_supported(const WgradGeom& g);
+size_t wgrad_halo_scratch_bytes(const WgradGeom& g);
+bool k_wgrad_halo(St st, const WgradGeom& g, const float* P, const float* Q, float* grad_master, float* scratch, size_t scratch_bytes,
+                  std::string* err);
 bool tc_wgrad_supported(const WgradGeom& g);
 size_t wgrad_tc_scratch_bytes(const WgradGeom& g);
 bool k_wgrad_tc(St st, const WgradGeom& g, const float* P, const float* Q, float* grad_master, float* scratch, size_t scratch_bytes,

@@ -330,6 +330,7 @@ struct ConvPlan {
     size_t b = wgrad_simt_scratch_bytes(g);
     b = std::max(b, thin_wgrad_scratch_bytes(g));
     if (fast && tc_wgrad_supported(g)) b = std::max(b, wgrad_tc_scratch_bytes(g));
+    if (fast) b = std::max(b, wgrad_halo_scratch_bytes(g));
     return b;
   }
   // x: module input, dy: gradient w.r.t. module output
@@ -339,6 +340,13 @@ struct ConvPlan {
     const float* Pp = full ? x : dy;
     const float* Qp = full ? dy : x;
     if (k_wgrad_thin(ctx->st(), g, Pp, Qp, grad_master, scratch, scratch_bytes)) return;   // 1..4-channel side: streaming kernel
+    if (fast && wgrad_halo_supported(g)) {
+      std::string e;
+      if (k_wgrad_halo(ctx->st(), g, Pp, Qp, grad_master, scratch, scratch_bytes, &e)) return;
+      ctx->err = "tcgen05 halo wgrad: " + e;
+      ctx->tc_failed = true;
+      return;
+    }
     if (fast && tc_wgrad_supported(g)) {
       std::string e;
       if (k_wgrad_tc(ctx->st(), g, Pp, Qp, grad_master, scratch, scratch_bytes, &e)) return;
