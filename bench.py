@@ -247,11 +247,11 @@ def main():
     # ---------------- device-resident leg ----------------
     for i in range(args.warmup):
         dsr.train_step_staged(ctx, G, D, scfg, i % NPOOL, B)
-    barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0 and not os.environ.get("DCGANSR_NO_SAMPLER"):
         sampler.start()
         time.sleep(0.25)
+    barrier()                      # AFTER the sampler start-up: every rank enters the timed region together
     l0 = ctx.launch_count()
     lo_mark = sampler.mark()
     ctx.timer_begin()
