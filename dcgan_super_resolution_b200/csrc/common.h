@@ -117,6 +117,9 @@ void k_flush(St st, float* buf, int64_t count);
 // Packed weights for the tap-list kernels: Wp[t][a][b] = master[a*sa + b*sb + tapidx[t]]
 void k_pack_taps(St st, const float* master, float* wp, int ntaps, const int* tapidx_dev, int A, int B,
                  int64_t sa, int64_t sb);
+// one fused pack launch per net: job j repacks master weights into dst (tc: K-major TF32 pack, else [t][a][b])
+struct PackJob { const float* src; float* dst; const int* tapidx; int ntaps, A, B, tc; int64_t sa, sb, begin; };
+void k_pack_all(St st, const PackJob* jobs_dev, int njobs, int64_t total);
 void k_tapconv_simt(St st, const TapGeom& g, const float* in, const float* wp, float* out, int act, float negval);
 // wgrad: accumulates into grad_master (+=) through a deterministic split-K reduction in `scratch`
 size_t wgrad_simt_scratch_bytes(const WgradGeom& g);
@@ -130,6 +133,12 @@ bool thin_wgrad_supported(const WgradGeom& g);
 size_t thin_wgrad_scratch_bytes(const WgradGeom& g);
 // false when the geometry is not covered (caller falls through to the GEMM kernels)
 bool k_wgrad_thin(St st, const WgradGeom& g, const float* P, const float* Q, float* grad_master, float* scratch, size_t scratch_bytes);
+
+// thin-input (Ci <= 4, all classes in one launch; wp[i] = SIMT pack [t][ci][co]) and thin-output (Co <= 4) convolutions
+bool thin_in_supported(const TapGeom* classes, int ncls);
+bool k_tapconv_thin_in(St st, const TapGeom* classes, int ncls, const float* const* wp, const float* in, float* out, int act, float neg);
+bool thin_out_supported(const TapGeom& g);
+bool k_tapconv_thin_out(St st, const TapGeom& g, const float* in, const float* wp, float* out, int act, float neg);
 
 // ---- kernels_tc.cu : tcgen05 / TMA / TMEM implicit-GEMM convolutions (FAST_TF32) --------------
 bool tc_init(std::string* err);                       // resolves cuTensorMapEncodeTiled
@@ -150,6 +159,10 @@ bool wgrad_halo_supported(const WgradGeom& g);
 size_t wgrad_halo_scratch_bytes(const WgradGeom& g);
 bool k_wgrad_halo(St st, const WgradGeom& g, const float* P, const float* Q, float* grad_master, float* scratch, size_t scratch_bytes,
                   std::string* err);
+// all sub-pixel classes of a module in one launch (blockIdx.z); classes must share the iterated grid
+bool tc_tapconv_multi_ok(const TapGeom* classes, int ncls);
+bool k_tapconv_tc_multi(St st, const TapGeom* classes, int ncls, const float* const* bp, const float* in, float* out, int act,
+                        float negval, std::string* err);
 bool tc_wgrad_supported(const WgradGeom& g);
 size_t wgrad_tc_scratch_bytes(const WgradGeom& g);
 bool k_wgrad_tc(St st, const WgradGeom& g, const float* P, const float* Q, float* grad_master, float* scratch, size_t scratch_bytes,

@@ -288,21 +288,55 @@ struct ConvPlan {
     for (auto* v : {&fwd, &dgrad})
       for (auto& c : *v)
         if (c.g.ntaps > 0) {
-          if (c.bp) k_pack_taps_tc(st, master, c.bp, c.g.ntaps, c.tapidx_dev, c.A, c.B, c.sa, c.sb);
+          const bool thin = c.A <= 4 || c.B <= 4;          // streaming kernels read the [t][a][b] pack
+          if (c.bp && !thin) k_pack_taps_tc(st, master, c.bp, c.g.ntaps, c.tapidx_dev, c.A, c.B, c.sa, c.sb);
           else k_pack_taps(st, master, c.wp, c.g.ntaps, c.tapidx_dev, c.A, c.B, c.sa, c.sb);
         }
   }
+  void collect_jobs(std::vector<PackJob>& jobs, const float* master, int64_t& total) {
+    for (auto* v : {&fwd, &dgrad})
+      for (auto& c : *v)
+        if (c.g.ntaps > 0) {
+          const bool thin = c.A <= 4 || c.B <= 4;
+          PackJob j;
+          j.src = master; j.tapidx = c.tapidx_dev; j.ntaps = c.g.ntaps; j.A = c.A; j.B = c.B; j.sa = c.sa; j.sb = c.sb;
+          j.tc = (c.bp && !thin) ? 1 : 0;
+          j.dst = j.tc ? c.bp : c.wp;
+          j.begin = total;
+          total += (int64_t)c.g.ntaps * c.A * c.B;
+          jobs.push_back(j);
+        }
+  }
   static void run_classes(dcgansr_ctx* ctx, std::vector<TapClass>& v, const float* in, float* out, int N, int act, float neg) {
+    // 1..4-channel side: streaming fp32 kernels (both precisions)
+    if (!v.empty() && v.size() <= 4 && !getenv("DCGANSR_NO_THIN")) {
+      TapGeom gs[4];
+      const float* wps[4];
+      for (size_t i = 0; i < v.size(); ++i) { gs[i] = v[i].g; gs[i].N = N; wps[i] = v[i].wp; }
+      if (thin_in_supported(gs, (int)v.size()) && k_tapconv_thin_in(ctx->st(), gs, (int)v.size(), wps, in, out, act, neg)) return;
+      if (thin_out_supported(gs[0])) {
+        for (size_t i = 0; i < v.size(); ++i)
+          if (gs[i].Hg > 0 && gs[i].Wg > 0) k_tapconv_thin_out(ctx->st(), gs[i], in, wps[i], out, act, neg);
+        return;
+      }
+    }
     // spatially large thin layers: one weights-resident halo launch for all sub-pixel classes
     if (!v.empty() && v.size() <= 4 && !getenv("DCGANSR_NO_HALO")) {
       TapGeom gs[4];
       const float* bps[4];
       bool all_tc = true;
-      for (size_t i = 0; i < v.size(); ++i) { gs[i] = v[i].g; gs[i].N = N; bps[i] = v[i].bp; all_tc = all_tc && v[i].bp; }
+      for (size_t i = 0; i < v.size(); ++i) { gs[i] = v[i].g; gs[i].N = N; bps[i] = v[i].bp; all_tc = all_tc && v[i].bp && v[i].A > 4 && v[i].B > 4; }
       if (all_tc && halo_tapconv_supported(gs, (int)v.size())) {
         std::string e;
         if (k_tapconv_halo(ctx->st(), gs, (int)v.size(), bps, in, out, act, neg, &e)) return;
         ctx->err = "tcgen05 halo path: " + e;
+        ctx->tc_failed = true;
+        return;
+      }
+      if (all_tc && v.size() > 1 && tc_tapconv_multi_ok(gs, (int)v.size())) {
+        std::string e;
+        if (k_tapconv_tc_multi(ctx->st(), gs, (int)v.size(), bps, in, out, act, neg, &e)) return;
+        ctx->err = "tcgen05 path: " + e;
         ctx->tc_failed = true;
         return;
       }
@@ -311,7 +345,7 @@ struct ConvPlan {
       if (c.g.Hg <= 0 || c.g.Wg <= 0) continue;
       TapGeom g = c.g;
       g.N = N;
-      if (c.bp) {
+      if (c.bp && c.A > 4 && c.B > 4) {
         std::string e;
         if (k_tapconv_tc(ctx->st(), g, in, c.bp, out, act, neg, &e)) continue;
         ctx->err = "tcgen05 path: " + e;       // surfaced by the caller's CKLAST / status
@@ -397,6 +431,9 @@ struct dcgansr_net {
   const float* last_out = nullptr;
   int out_c = 0, out_h = 0, out_w = 0;
   std::vector<std::pair<int64_t, int64_t>> buckets;   // gradient buckets (offset, count), forward order
+  PackJob* pack_jobs = nullptr;                       // fused weight repack (one launch per net)
+  int n_pack_jobs = 0;
+  int64_t pack_total = 0;
 
   float* own(const float* cur) { return (cur == gbuf[0] || cur == gbuf[1]) ? const_cast<float*>(cur) : gbuf[0]; }
   float* other(const float* cur) { return cur == gbuf[0] ? gbuf[1] : gbuf[0]; }
@@ -420,6 +457,7 @@ static int nccl_allreduce(dcgansr_ctx* ctx, void* buf, size_t count, ncclDataTyp
 }
 
 static void net_pack_all(dcgansr_net* net) {
+  if (net->pack_jobs) { k_pack_all(net->ctx->st(), net->pack_jobs, net->n_pack_jobs, net->pack_total); return; }
   for (auto& m : net->mods)
     if (m.conv) m.conv->pack(net->ctx->st(), net->params + m.p_off);
 }
@@ -749,7 +787,7 @@ void dcgansr_net_destroy(dcgansr_net* net) {
   }
   void* ptrs[] = {net->params, net->grads, net->adam_m, net->adam_v, net->adam_t, net->adam_step, net->bn_rmean,
                   net->bn_rvar, net->bn_save, net->in_buf, net->gbuf[0], net->gbuf[1], net->bn_partials, net->bn_sums,
-                  net->bn_sums_total, net->wscratch};
+                  net->bn_sums_total, net->wscratch, net->pack_jobs};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete net;
 }
@@ -890,6 +928,22 @@ int dcgansr_net_create(dcgansr_ctx* ctx, const dcgansr_layer* layers, int n_laye
     std::string msg = std::string("device allocation failed: ") + cudaGetErrorString(e);
     dcgansr_net_destroy(net);
     return fail(ctx, DCGANSR_ERR_NOMEM, msg);
+  }
+  {
+    std::vector<PackJob> jobs;
+    int64_t total = 0;
+    for (auto& m : net->mods)
+      if (m.conv) m.conv->collect_jobs(jobs, net->params + m.p_off, total);
+    if (!jobs.empty()) {
+      PackJob sentinel = jobs.back();
+      sentinel.begin = total;
+      jobs.push_back(sentinel);
+      if (cudaMalloc((void**)&net->pack_jobs, jobs.size() * sizeof(PackJob)) == cudaSuccess &&
+          cudaMemcpy(net->pack_jobs, jobs.data(), jobs.size() * sizeof(PackJob), cudaMemcpyHostToDevice) == cudaSuccess) {
+        net->n_pack_jobs = (int)jobs.size() - 1;
+        net->pack_total = total;
+      } else if (net->pack_jobs) { cudaFree(net->pack_jobs); net->pack_jobs = nullptr; }
+    }
   }
   // BN running_var starts at 1 (Torch7 init)
   if (net->nbn > 0) k_fill(ctx->st(), net->bn_rvar, net->nbn, 1.f);

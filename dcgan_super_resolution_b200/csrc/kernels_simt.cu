@@ -37,6 +37,45 @@ void k_pack_taps(St st, const float* master, float* wp, int ntaps, const int* ta
   DSR_LAUNCHED(st, "pack_taps", 8.0 * total, WORK_BYTES);
 }
 
+// ------------------------------------------------------------------------------------------
+// all weight packs of a net in ONE launch (after every Adam step): jobs[j] covers flat elements [begin_j, begin_{j+1})
+// ------------------------------------------------------------------------------------------
+__global__ void pack_all_kernel(const PackJob* __restrict__ jobs, int njobs, int64_t total) {
+  int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    int lo = 0, hi = njobs - 1;
+    while (lo < hi) {                       // last job with begin <= i
+      int mid = (lo + hi + 1) >> 1;
+      if (jobs[mid].begin <= i) lo = mid; else hi = mid - 1;
+    }
+    const PackJob& j = jobs[lo];
+    const int64_t l = i - j.begin;
+    if (j.tc) {                             // K-major tensor-core pack bp[b][t*A + a], TF32-rounded
+      int a = (int)(l % j.A);
+      int64_t r = l / j.A;
+      int t = (int)(r % j.ntaps);
+      int b = (int)(r / j.ntaps);
+      float v = j.src[a * j.sa + b * j.sb + j.tapidx[t]];
+      uint32_t u;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+      j.dst[l] = __uint_as_float(u);
+    } else {                                // SIMT / streaming pack wp[t][a][b]
+      int b = (int)(l % j.B);
+      int64_t r = l / j.B;
+      int a = (int)(r % j.A);
+      int t = (int)(r / j.A);
+      j.dst[l] = j.src[a * j.sa + b * j.sb + j.tapidx[t]];
+    }
+  }
+}
+void k_pack_all(St st, const PackJob* jobs_dev, int njobs, int64_t total) {
+  if (njobs <= 0 || total <= 0) return;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > NSM * 8) blocks = NSM * 8;
+  pack_all_kernel<<<(int)blocks, 256, 0, st.s>>>(jobs_dev, njobs, total);
+  DSR_LAUNCHED(st, "pack_all", 8.0 * total, WORK_BYTES);
+}
+
 __device__ __forceinline__ float act_apply_s(float v, int act, float neg) {
   switch (act) {
     case ACT_RELU: return v > 0.f ? v : 0.f;

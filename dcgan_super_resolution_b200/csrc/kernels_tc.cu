@@ -92,22 +92,25 @@ void k_pack_taps_tc(St st, const float* master, float* bp, int ntaps, const int*
 // ------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------
+#define TC_MAXCLS 4
 struct TcParams {
   int N, Hg, Wg, Ho, Wo, Co;
-  int so, oy0, ox0, si, Ci;
+  int so, si, Ci;
   int TW, TH, TB, tiles_x, tiles_y;
-  int ntaps, KB, kchunks, BN, nstage;
+  int KB, kchunks, BN, nstage;
+  int ncls, oy0[TC_MAXCLS], ox0[TC_MAXCLS], ntaps[TC_MAXCLS];      // sub-pixel classes: blockIdx.z
   int a_stage_bytes, b_stage_bytes, tmem_cols;
   int act;
   float neg;
   // per tap: box origin offsets (si = 1: dy,dx; si = 2: floor(dy/2), floor(dx/2) and the parities)
-  short oy[DSR_MAX_TAPS], ox[DSR_MAX_TAPS], py[DSR_MAX_TAPS], px[DSR_MAX_TAPS];
+  short oy[TC_MAXCLS][DSR_MAX_TAPS], ox[TC_MAXCLS][DSR_MAX_TAPS], py[TC_MAXCLS][DSR_MAX_TAPS], px[TC_MAXCLS][DSR_MAX_TAPS];
 };
+struct TcMaps { CUtensorMap b[TC_MAXCLS]; };
 
 #define TC_THREADS 192
 
 __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_constant__ CUtensorMap mapA,
-                                                                const __grid_constant__ CUtensorMap mapB, const TcParams p,
+                                                                const __grid_constant__ TcMaps mapsB, const TcParams p,
                                                                 float* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [A stages][B stages][barriers]
@@ -121,7 +124,9 @@ __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_con
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.nstage + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nk = p.ntaps * p.kchunks;
+  const int cls = blockIdx.z;
+  const int ntaps = p.ntaps[cls];
+  const int nk = ntaps * p.kchunks;
 
   // tile coordinates
   int tile = blockIdx.x;
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_con
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapsB.b[cls]) : "memory");
     for (int s = 0; s < p.nstage; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
     mbar_init(smem_u32(tmem_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -154,17 +159,17 @@ __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_con
       uint32_t ph = 0;
       const uint32_t bytes = (uint32_t)(128 * p.KB * 4 + p.BN * p.KB * 4);
       int kb = 0;
-      for (int t = 0; t < p.ntaps; ++t) {
+      for (int t = 0; t < ntaps; ++t) {
         for (int c = 0; c < p.kchunks; ++c, ++kb) {
           mbar_wait(smem_u32(&empty[s]), ph ^ 1);
           const uint32_t fb = smem_u32(&full[s]);
           mbar_expect_tx(fb, bytes);
           const uint32_t da = smem_u32(sA + (size_t)s * p.a_stage_bytes);
           if (p.si == 1)
-            tma_load_4d(da, &mapA, fb, c * p.KB, gx0 + p.ox[t], gy0 + p.oy[t], b0);
+            tma_load_4d(da, &mapA, fb, c * p.KB, gx0 + p.ox[cls][t], gy0 + p.oy[cls][t], b0);
           else
-            tma_load_5d(da, &mapA, fb, p.px[t] * p.Ci + c * p.KB, gx0 + p.ox[t], p.py[t], gy0 + p.oy[t], b0);
-          tma_load_2d(smem_u32(sB + (size_t)s * p.b_stage_bytes), &mapB, fb, (t * p.kchunks + c) * p.KB, n0);
+            tma_load_5d(da, &mapA, fb, p.px[cls][t] * p.Ci + c * p.KB, gx0 + p.ox[cls][t], p.py[cls][t], gy0 + p.oy[cls][t], b0);
+          tma_load_2d(smem_u32(sB + (size_t)s * p.b_stage_bytes), &mapsB.b[cls], fb, (t * p.kchunks + c) * p.KB, n0);
           if (++s == p.nstage) { s = 0; ph ^= 1; }
         }
       }
@@ -200,7 +205,7 @@ __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_con
     const int n = b0 + b, gy = gy0 + h, gx = gx0 + w;
     const bool valid = n < p.N && gy < p.Hg && gx < p.Wg;
     float* orow = nullptr;
-    if (valid) orow = out + ((int64_t)(n * p.Ho + gy * p.so + p.oy0) * p.Wo + gx * p.so + p.ox0) * p.Co;
+    if (valid) orow = out + ((int64_t)(n * p.Ho + gy * p.so + p.oy0[cls]) * p.Wo + gx * p.so + p.ox0[cls]) * p.Co;
     mbar_wait(smem_u32(tmem_full), 0);
     tc_fence_after();
     const bool vec = (p.Co & 3) == 0, vec8 = (p.Co & 7) == 0;
@@ -253,15 +258,28 @@ __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_con
 static inline int pow2_ge(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 static inline int floordiv2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
 
-bool k_tapconv_tc(St st, const TapGeom& g, const float* in, const float* bp, float* out, int act, float negval, std::string* err) {
-  if (!tc_tapconv_supported(g)) { if (err) *err = "geometry not supported by the tcgen05 path"; return false; }
+// All classes share the input / output tensors and the iterated grid (Hg, Wg); they differ in taps and output offset.
+bool tc_tapconv_multi_ok(const TapGeom* cls, int ncls) {
+  if (ncls < 1 || ncls > TC_MAXCLS) return false;
+  for (int i = 0; i < ncls; ++i) {
+    if (!tc_tapconv_supported(cls[i])) return false;
+    if (cls[i].Hg != cls[0].Hg || cls[i].Wg != cls[0].Wg || cls[i].Ci != cls[0].Ci || cls[i].Co != cls[0].Co || cls[i].si != cls[0].si ||
+        cls[i].so != cls[0].so)
+      return false;
+  }
+  return true;
+}
+
+bool k_tapconv_tc_multi(St st, const TapGeom* cls, int ncls, const float* const* bp, const float* in, float* out, int act, float negval,
+                        std::string* err) {
+  if (!tc_tapconv_multi_ok(cls, ncls)) { if (err) *err = "geometry not supported by the tcgen05 path"; return false; }
+  const TapGeom& g = cls[0];
   TcParams p;
   memset(&p, 0, sizeof(p));
   p.N = g.N; p.Hg = g.Hg; p.Wg = g.Wg; p.Ho = g.Ho; p.Wo = g.Wo; p.Co = g.Co;
-  p.so = g.so; p.oy0 = g.oy0; p.ox0 = g.ox0; p.si = g.si; p.Ci = g.Ci;
+  p.so = g.so; p.si = g.si; p.Ci = g.Ci; p.ncls = ncls;
   p.KB = kb_of(g.Ci);
   p.kchunks = g.Ci / p.KB;
-  p.ntaps = g.ntaps;
   p.TW = std::min(pow2_ge(g.Wg), 128);
   p.TH = std::min(pow2_ge(g.Hg), 128 / p.TW);
   p.TB = 128 / (p.TW * p.TH);
@@ -274,18 +292,26 @@ bool k_tapconv_tc(St st, const TapGeom& g, const float* in, const float* bp, flo
   p.a_stage_bytes = 128 * p.KB * 4;
   p.b_stage_bytes = (p.BN * p.KB * 4 + 1023) / 1024 * 1024;
   const int stage = p.a_stage_bytes + p.b_stage_bytes;
-  p.nstage = std::max(2, std::min(8, (96 * 1024) / stage));
+  // small grids (<= one CTA per SM) take the whole shared memory for a deeper TMA ring; larger ones keep two CTAs per SM
+  const long long nctas = (long long)tiles_b * p.tiles_y * p.tiles_x * ntiles_n * ncls;
+  const int budget = nctas <= NSM ? 200 * 1024 : 96 * 1024;
+  p.nstage = std::max(2, std::min(8, budget / stage));
   p.tmem_cols = std::max(32, pow2_ge(p.BN));
   p.act = act; p.neg = negval;
-  for (int t = 0; t < g.ntaps; ++t) {
-    if (g.si == 1) { p.oy[t] = (short)g.dy[t]; p.ox[t] = (short)g.dx[t]; p.py[t] = 0; p.px[t] = 0; }
-    else {
-      int fy = floordiv2(g.dy[t]), fx = floordiv2(g.dx[t]);
-      p.oy[t] = (short)fy; p.ox[t] = (short)fx; p.py[t] = (short)(g.dy[t] - 2 * fy); p.px[t] = (short)(g.dx[t] - 2 * fx);
+  for (int i = 0; i < ncls; ++i) {
+    p.oy0[i] = cls[i].oy0; p.ox0[i] = cls[i].ox0; p.ntaps[i] = cls[i].ntaps;
+    for (int t = 0; t < cls[i].ntaps; ++t) {
+      if (g.si == 1) { p.oy[i][t] = (short)cls[i].dy[t]; p.ox[i][t] = (short)cls[i].dx[t]; p.py[i][t] = 0; p.px[i][t] = 0; }
+      else {
+        int fy = floordiv2(cls[i].dy[t]), fx = floordiv2(cls[i].dx[t]);
+        p.oy[i][t] = (short)fy; p.ox[i][t] = (short)fx; p.py[i][t] = (short)(cls[i].dy[t] - 2 * fy); p.px[i][t] = (short)(cls[i].dx[t] - 2 * fx);
+      }
     }
   }
   // ---- tensor maps ----
-  CUtensorMap mapA, mapB;
+  CUtensorMap mapA;
+  TcMaps maps;
+  memset(&maps, 0, sizeof(maps));
   const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
   CUresult r;
   if (g.si == 1) {
@@ -303,29 +329,35 @@ bool k_tapconv_tc(St st, const TapGeom& g, const float* in, const float* bp, flo
                  swz_of(p.KB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   }
   if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r); return false; }
-  {
-    const cuuint64_t ktot = (cuuint64_t)g.ntaps * g.Ci;
+  double flops = 0;
+  for (int i = 0; i < ncls; ++i) {
+    const cuuint64_t ktot = (cuuint64_t)cls[i].ntaps * g.Ci;
     cuuint64_t dims[2] = {ktot, (cuuint64_t)g.Co};
     cuuint64_t strides[1] = {ktot * 4};
     cuuint32_t box[2] = {(cuuint32_t)p.KB, (cuuint32_t)p.BN};
-    r = g_encode(&mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)bp, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    r = g_encode(&maps.b[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)bp[i], dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
                  swz_of(p.KB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r); return false; }
+    flops += 2.0 * g.N * g.Hg * g.Wg * cls[i].ntaps * g.Ci * g.Co;
   }
-  if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r); return false; }
 
   const size_t smem = 1024 + (size_t)p.nstage * stage + (2 * p.nstage + 1) * sizeof(uint64_t) + 16;
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(tapconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
+    if (cudaFuncSetAttribute(tapconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) != cudaSuccess) {
       if (err) *err = "cudaFuncSetAttribute(smem) failed";
       return false;
     }
     configured = true;
   }
-  dim3 grid((unsigned)(tiles_b * p.tiles_y * p.tiles_x), (unsigned)ntiles_n);
-  tapconv_tc_kernel<<<grid, TC_THREADS, smem, st.s>>>(mapA, mapB, p, out);
-  DSR_LAUNCHED(st, "tapconv_tc", 2.0 * g.N * g.Hg * g.Wg * g.ntaps * g.Ci * g.Co, WORK_FLOPS);
+  dim3 grid((unsigned)(tiles_b * p.tiles_y * p.tiles_x), (unsigned)ntiles_n, (unsigned)ncls);
+  tapconv_tc_kernel<<<grid, TC_THREADS, smem, st.s>>>(mapA, maps, p, out);
+  DSR_LAUNCHED(st, "tapconv_tc", flops, WORK_FLOPS);
   return true;
+}
+
+bool k_tapconv_tc(St st, const TapGeom& g, const float* in, const float* bp, float* out, int act, float negval, std::string* err) {
+  return k_tapconv_tc_multi(st, &g, 1, &bp, in, out, act, negval, err);
 }
 
 

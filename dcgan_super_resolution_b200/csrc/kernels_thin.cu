@@ -216,3 +216,204 @@ bool k_wgrad_thin(St st, const WgradGeom& g, const float* P, const float* Q, flo
   k_wgrad_reduce(st, scratch, nb, g.Cp, g.Cq, g.ntaps, grad_master);
   return true;
 }
+
+// =====================================================================================================================
+// thin-INPUT convolution (Ci <= 4): FC 1->64 forward, conv 16->1 dgrad, D's first conv (train-gray.lua:105,116, train.lua:99,121)
+//   out[n, gy*so+oy0, gx*so+ox0, co] = act( sum_t sum_ci in[n, gy*si+dy_t, gx*si+dx_t, ci] * W[t][ci][co] )
+// Pure output-write streaming: a thread owns one output pixel x 4 couts, the <= 16 x Ci input scalars come through L1,
+// the (tiny) weights live in shared memory.  All sub-pixel classes in one launch (blockIdx.y).
+// =====================================================================================================================
+struct ThinInCls { int Hg, Wg, oy0, ox0, ntaps; short dy[16], dx[16]; const float* wp; };
+struct ThinIn {
+  int N, Hi, Wi, Ci, Ho, Wo, Co, si, so, ncls, act;
+  float neg;
+  ThinInCls c[4];
+};
+
+__device__ __forceinline__ float thin_act(float v, int act, float neg) {
+  switch (act) {
+    case ACT_RELU: return v > 0.f ? v : 0.f;
+    case ACT_LRELU: return v > 0.f ? v : v * neg;
+    case ACT_TANH: return tanhf(v);
+    case ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+    default: return v;
+  }
+}
+
+template <int CI>
+__global__ void __launch_bounds__(256) thin_in_kernel(const ThinIn p, const float* __restrict__ in, float* __restrict__ out) {
+  extern __shared__ __align__(16) float sw[];                  // [t][ci][Co]
+  const ThinInCls& c = p.c[blockIdx.y];
+  const int wn = c.ntaps * CI * p.Co;
+  for (int i = threadIdx.x; i < wn; i += 256) sw[i] = c.wp[i];
+  __syncthreads();
+  const int V = p.Co >> 2;                                      // float4 lanes per pixel
+  const int64_t total = (int64_t)p.N * c.Hg * c.Wg * V;
+  for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
+    const int v = (int)(idx % V);
+    int64_t pix = idx / V;
+    const int gx = (int)(pix % c.Wg); pix /= c.Wg;
+    const int gy = (int)(pix % c.Hg);
+    const int n = (int)(pix / c.Hg);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int t = 0; t < c.ntaps; ++t) {
+      const int iy = gy * p.si + c.dy[t], ix = gx * p.si + c.dx[t];
+      if (iy < 0 || iy >= p.Hi || ix < 0 || ix >= p.Wi) continue;
+      const float* ip = in + ((int64_t)(n * p.Hi + iy) * p.Wi + ix) * CI;
+#pragma unroll
+      for (int ci = 0; ci < CI; ++ci) {
+        const float x = __ldg(ip + ci);
+        const float4 w = *reinterpret_cast<const float4*>(&sw[(t * CI + ci) * p.Co + v * 4]);
+        acc.x = fmaf(x, w.x, acc.x); acc.y = fmaf(x, w.y, acc.y); acc.z = fmaf(x, w.z, acc.z); acc.w = fmaf(x, w.w, acc.w);
+      }
+    }
+    acc.x = thin_act(acc.x, p.act, p.neg); acc.y = thin_act(acc.y, p.act, p.neg);
+    acc.z = thin_act(acc.z, p.act, p.neg); acc.w = thin_act(acc.w, p.act, p.neg);
+    float* o = out + ((int64_t)(n * p.Ho + gy * p.so + c.oy0) * p.Wo + gx * p.so + c.ox0) * p.Co + v * 4;
+    *reinterpret_cast<float4*>(o) = acc;
+  }
+}
+
+bool thin_in_supported(const TapGeom* cls, int ncls) {
+  if (ncls < 1 || ncls > 4) return false;
+  const TapGeom& g = cls[0];
+  if (g.Ci < 1 || g.Ci > 4 || g.Co % 4 || g.Co < 4) return false;
+  for (int i = 0; i < ncls; ++i)
+    if (cls[i].ntaps > 16 || (size_t)cls[i].ntaps * g.Ci * g.Co * sizeof(float) > 96 * 1024) return false;
+  return true;
+}
+
+// wp[i]: SIMT pack [t][ci][co] of class i
+bool k_tapconv_thin_in(St st, const TapGeom* cls, int ncls, const float* const* wp, const float* in, float* out, int act, float neg) {
+  if (!thin_in_supported(cls, ncls)) return false;
+  const TapGeom& g = cls[0];
+  ThinIn p;
+  memset(&p, 0, sizeof(p));
+  p.N = g.N; p.Hi = g.Hi; p.Wi = g.Wi; p.Ci = g.Ci; p.Ho = g.Ho; p.Wo = g.Wo; p.Co = g.Co; p.si = g.si; p.so = g.so; p.ncls = ncls;
+  p.act = act; p.neg = neg;
+  size_t smem = 0;
+  int64_t maxtot = 0;
+  double bytes = 0;
+  for (int i = 0; i < ncls; ++i) {
+    p.c[i].Hg = cls[i].Hg; p.c[i].Wg = cls[i].Wg; p.c[i].oy0 = cls[i].oy0; p.c[i].ox0 = cls[i].ox0; p.c[i].ntaps = cls[i].ntaps;
+    for (int t = 0; t < cls[i].ntaps; ++t) { p.c[i].dy[t] = (short)cls[i].dy[t]; p.c[i].dx[t] = (short)cls[i].dx[t]; }
+    p.c[i].wp = wp[i];
+    smem = std::max(smem, (size_t)cls[i].ntaps * g.Ci * g.Co * sizeof(float));
+    maxtot = std::max<int64_t>(maxtot, (int64_t)g.N * cls[i].Hg * cls[i].Wg * (g.Co / 4));
+    bytes += 4.0 * g.N * cls[i].Hg * cls[i].Wg * g.Co;
+  }
+  if (maxtot <= 0) return true;
+  bytes += 4.0 * g.N * g.Hi * g.Wi * g.Ci;
+  int64_t nb = std::min<int64_t>((maxtot + 255) / 256, NSM * 8);
+  dim3 grid((unsigned)std::max<int64_t>(nb, 1), (unsigned)ncls);
+  static bool attr[5] = {false, false, false, false, false};
+#define THIN_IN_LAUNCH(CI)                                                                                         \
+  do {                                                                                                             \
+    if (!attr[CI] && smem > 48 * 1024) {                                                                           \
+      cudaFuncSetAttribute(thin_in_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);            \
+      attr[CI] = true;                                                                                             \
+    }                                                                                                              \
+    thin_in_kernel<CI><<<grid, 256, smem, st.s>>>(p, in, out);                                                     \
+  } while (0)
+  switch (g.Ci) {
+    case 1: THIN_IN_LAUNCH(1); break;
+    case 2: THIN_IN_LAUNCH(2); break;
+    case 3: THIN_IN_LAUNCH(3); break;
+    default: THIN_IN_LAUNCH(4); break;
+  }
+#undef THIN_IN_LAUNCH
+  DSR_LAUNCHED(st, "tapconv_thin_in", bytes, WORK_BYTES);
+  return true;
+}
+
+// =====================================================================================================================
+// thin-OUTPUT convolution (Co <= 4): D's final 512->1 conv, G's last conv 16->1 / 12->3 (train.lua:111,133), and the dgrad
+// of every thin-input layer.  One pass over the input: WPP warps per output pixel split the K = ntaps*Ci contraction
+// (float4 over ci, coalesced), warp shuffle + shared-memory reduction, activation fused.
+// =====================================================================================================================
+struct ThinOut {
+  int N, Hi, Wi, Ci, Ho, Wo, Co, Hg, Wg, si, so, oy0, ox0, ntaps, act, wpp;
+  float neg;
+  short dy[DSR_MAX_TAPS], dx[DSR_MAX_TAPS];
+};
+
+template <int CO>
+__global__ void __launch_bounds__(256) thin_out_kernel(const ThinOut p, const float* __restrict__ in, const float* __restrict__ wp,
+                                                        float* __restrict__ out) {
+  __shared__ float red[8][CO];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ppb = 8 / p.wpp;                                    // pixels per block
+  const int sub = warp % p.wpp;                                 // this warp's slice of K
+  const int64_t npix = (int64_t)p.N * p.Hg * p.Wg;
+  const int V = p.Ci >> 2;                                      // float4 per tap
+  const int KV = p.ntaps * V;
+  for (int64_t base = (int64_t)blockIdx.x * ppb; base < npix; base += (int64_t)gridDim.x * ppb) {
+    const int64_t pix = base + warp / p.wpp;
+    float acc[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+    int gx = 0, gy = 0, n = 0;
+    const bool pv = pix < npix;
+    if (pv) {
+      int64_t q = pix;
+      gx = (int)(q % p.Wg); q /= p.Wg;
+      gy = (int)(q % p.Hg);
+      n = (int)(q / p.Hg);
+      for (int kv = sub * 32 + lane; kv < KV; kv += 32 * p.wpp) {
+        const int t = kv / V, c4 = kv - t * V;
+        const int iy = gy * p.si + p.dy[t], ix = gx * p.si + p.dx[t];
+        if (iy < 0 || iy >= p.Hi || ix < 0 || ix >= p.Wi) continue;
+        const float4 x = __ldg(reinterpret_cast<const float4*>(in + ((int64_t)(n * p.Hi + iy) * p.Wi + ix) * p.Ci + c4 * 4));
+        const float* w = wp + (int64_t)(t * p.Ci + c4 * 4) * CO;      // [k][co]
+#pragma unroll
+        for (int c = 0; c < CO; ++c)
+          acc[c] = fmaf(x.x, __ldg(w + c), fmaf(x.y, __ldg(w + CO + c), fmaf(x.z, __ldg(w + 2 * CO + c), fmaf(x.w, __ldg(w + 3 * CO + c), acc[c]))));
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < CO; ++c) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    }
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < CO; ++c) red[warp][c] = acc[c];
+    }
+    __syncthreads();
+    if (pv && sub == 0 && lane < CO) {
+      float s = 0.f;
+      for (int j = 0; j < p.wpp; ++j) s += red[warp + j][lane];
+      out[((int64_t)(n * p.Ho + gy * p.so + p.oy0) * p.Wo + gx * p.so + p.ox0) * p.Co + lane] = thin_act(s, p.act, p.neg);
+    }
+    __syncthreads();
+  }
+}
+
+bool thin_out_supported(const TapGeom& g) { return g.Co >= 1 && g.Co <= 4 && g.Ci % 4 == 0 && g.Ci >= 4 && g.ntaps >= 1; }
+
+bool k_tapconv_thin_out(St st, const TapGeom& g, const float* in, const float* wp, float* out, int act, float neg) {
+  if (!thin_out_supported(g)) return false;
+  ThinOut p;
+  memset(&p, 0, sizeof(p));
+  p.N = g.N; p.Hi = g.Hi; p.Wi = g.Wi; p.Ci = g.Ci; p.Ho = g.Ho; p.Wo = g.Wo; p.Co = g.Co; p.Hg = g.Hg; p.Wg = g.Wg;
+  p.si = g.si; p.so = g.so; p.oy0 = g.oy0; p.ox0 = g.ox0; p.ntaps = g.ntaps; p.act = act; p.neg = neg;
+  for (int t = 0; t < g.ntaps; ++t) { p.dy[t] = (short)g.dy[t]; p.dx[t] = (short)g.dx[t]; }
+  const int64_t npix = (int64_t)g.N * g.Hg * g.Wg;
+  if (npix <= 0) return true;
+  const int KV = g.ntaps * (g.Ci / 4);
+  // warps per pixel: enough lanes for K, and enough blocks for the machine when there are few pixels
+  int wpp = 1;
+  while (wpp < 8 && (KV > 64 * wpp) && (npix * wpp < (int64_t)NSM * 64)) wpp <<= 1;
+  p.wpp = wpp;
+  const int ppb = 8 / wpp;
+  int64_t nb = std::min<int64_t>((npix + ppb - 1) / ppb, NSM * 16);
+  switch (g.Co) {
+    case 1: thin_out_kernel<1><<<(unsigned)nb, 256, 0, st.s>>>(p, in, wp, out); break;
+    case 2: thin_out_kernel<2><<<(unsigned)nb, 256, 0, st.s>>>(p, in, wp, out); break;
+    case 3: thin_out_kernel<3><<<(unsigned)nb, 256, 0, st.s>>>(p, in, wp, out); break;
+    default: thin_out_kernel<4><<<(unsigned)nb, 256, 0, st.s>>>(p, in, wp, out); break;
+  }
+  DSR_LAUNCHED(st, "tapconv_thin_out", 4.0 * ((double)g.N * g.Hi * g.Wi * g.Ci + (double)npix * g.Co), WORK_BYTES);
+  return true;
+}
