@@ -288,23 +288,28 @@ struct ConvPlan {
     for (auto* v : {&fwd, &dgrad})
       for (auto& c : *v)
         if (c.g.ntaps > 0) {
-          const bool thin = c.A <= 4 || c.B <= 4;          // streaming kernels read the [t][a][b] pack
-          if (c.bp && !thin) k_pack_taps_tc(st, master, c.bp, c.g.ntaps, c.tapidx_dev, c.A, c.B, c.sa, c.sb);
-          else k_pack_taps(st, master, c.wp, c.g.ntaps, c.tapidx_dev, c.A, c.B, c.sa, c.sb);
+          // the streaming kernels (1..4-channel side) read the [t][a][b] pack; a thin-OUTPUT class keeps both packs
+          // (few pixels -> streaming reduction, many pixels -> tensor-core kernels)
+          if (c.bp && c.A > 4) k_pack_taps_tc(st, master, c.bp, c.g.ntaps, c.tapidx_dev, c.A, c.B, c.sa, c.sb);
+          if (!c.bp || c.A <= 4 || c.B <= 4) k_pack_taps(st, master, c.wp, c.g.ntaps, c.tapidx_dev, c.A, c.B, c.sa, c.sb);
         }
   }
   void collect_jobs(std::vector<PackJob>& jobs, const float* master, int64_t& total) {
     for (auto* v : {&fwd, &dgrad})
       for (auto& c : *v)
         if (c.g.ntaps > 0) {
-          const bool thin = c.A <= 4 || c.B <= 4;
           PackJob j;
           j.src = master; j.tapidx = c.tapidx_dev; j.ntaps = c.g.ntaps; j.A = c.A; j.B = c.B; j.sa = c.sa; j.sb = c.sb;
-          j.tc = (c.bp && !thin) ? 1 : 0;
-          j.dst = j.tc ? c.bp : c.wp;
-          j.begin = total;
-          total += (int64_t)c.g.ntaps * c.A * c.B;
-          jobs.push_back(j);
+          if (c.bp && c.A > 4) {
+            j.tc = 1; j.dst = c.bp; j.begin = total;
+            total += (int64_t)c.g.ntaps * c.A * c.B;
+            jobs.push_back(j);
+          }
+          if (!c.bp || c.A <= 4 || c.B <= 4) {
+            j.tc = 0; j.dst = c.wp; j.begin = total;
+            total += (int64_t)c.g.ntaps * c.A * c.B;
+            jobs.push_back(j);
+          }
         }
   }
   static void run_classes(dcgansr_ctx* ctx, std::vector<TapClass>& v, const float* in, float* out, int N, int act, float neg) {
@@ -325,7 +330,7 @@ struct ConvPlan {
       TapGeom gs[4];
       const float* bps[4];
       bool all_tc = true;
-      for (size_t i = 0; i < v.size(); ++i) { gs[i] = v[i].g; gs[i].N = N; bps[i] = v[i].bp; all_tc = all_tc && v[i].bp && v[i].A > 4 && v[i].B > 4; }
+      for (size_t i = 0; i < v.size(); ++i) { gs[i] = v[i].g; gs[i].N = N; bps[i] = v[i].bp; all_tc = all_tc && v[i].bp && v[i].A > 4; }
       if (all_tc && halo_tapconv_supported(gs, (int)v.size())) {
         std::string e;
         if (k_tapconv_halo(ctx->st(), gs, (int)v.size(), bps, in, out, act, neg, &e)) return;
@@ -345,7 +350,7 @@ struct ConvPlan {
       if (c.g.Hg <= 0 || c.g.Wg <= 0) continue;
       TapGeom g = c.g;
       g.N = N;
-      if (c.bp && c.A > 4 && c.B > 4) {
+      if (c.bp && c.A > 4) {
         std::string e;
         if (k_tapconv_tc(ctx->st(), g, in, c.bp, out, act, neg, &e)) continue;
         ctx->err = "tcgen05 path: " + e;       // surfaced by the caller's CKLAST / status

@@ -10,6 +10,8 @@
 //             reduced in fixed order (deterministic), added into the Torch7-layout master gradient.
 #include "common.h"
 
+#include <algorithm>
+
 #define NSM 148
 
 // ------------------------------------------------------------------------------------------
@@ -396,21 +398,32 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradGeom g, const floa
   }
 }
 
-// grad_master[cp*(Cq*T) + cq*T + t] += sum_s scratch[s][cp][t*Cq + cq]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ scratch, int S, int Cp, int Cq, int T,
-                                    float* __restrict__ grad_master) {
-  int64_t total = (int64_t)Cp * Cq * T;
-  int64_t stride = (int64_t)gridDim.x * blockDim.x;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    // i indexes scratch layout [cp][t][cq] (coalesced reads)
-    int cq = (int)(i % Cq);
-    int64_t r = i / Cq;
-    int t = (int)(r % T);
-    int cp = (int)(r / T);
+// grad_master[cp*(Cq*T) + cq*T + t] += sum_s scratch[s][cp][t*Cq + cq]          (fixed order: deterministic)
+// A block owns one cp and a chunk of its T*Cq row.  The S partials are summed by 4 split groups (s = g, g+4, ...) over 64
+// element lanes, combined through shared memory in fixed order, and the (t,cq) -> (cq,t) transposition to the Torch7
+// layout happens there too, so both the scratch reads and the master-gradient read-modify-write are coalesced.
+#define WR_CHUNK_MAX 2048
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ scratch, int S, int Cp, int Cq, int T, int ncq,
+                                                           float* __restrict__ grad_master) {
+  __shared__ float part[4][WR_CHUNK_MAX];
+  const int row = T * Cq;                               // elements per cp
+  const int nchunk = (Cq + ncq - 1) / ncq;
+  const int cp = blockIdx.x / nchunk, cq0 = (blockIdx.x % nchunk) * ncq;
+  const int nc = min(ncq, Cq - cq0);                    // cq range of this block
+  const int n = nc * T;
+  const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const int64_t total = (int64_t)Cp * row;
+  // read order (t major, cq minor): coalesced along cq; stored transposed ([cq][t]) in shared memory
+  for (int e = lane; e < n; e += 64) {
+    const int t = e / nc, c = e - t * nc;
+    const float* src = scratch + (int64_t)cp * row + (int64_t)t * Cq + cq0 + c;
     float a = 0.f;
-    for (int s = 0; s < S; ++s) a += scratch[(int64_t)s * total + i];
-    grad_master[(int64_t)cp * Cq * T + (int64_t)cq * T + t] += a;
+    for (int s = grp; s < S; s += 4) a += src[(int64_t)s * total];
+    part[grp][c * T + t] = a;
   }
+  __syncthreads();
+  float* dst = grad_master + (int64_t)cp * row + (int64_t)cq0 * T;
+  for (int o = threadIdx.x; o < n; o += 256) dst[o] += ((part[0][o] + part[1][o]) + part[2][o]) + part[3][o];
 }
 
 void k_wgrad_simt(St st, const WgradGeom& g, const float* P, const float* Q, float* grad_master,
@@ -428,10 +441,13 @@ void k_wgrad_simt(St st, const WgradGeom& g, const float* P, const float* Q, flo
 }
 
 void k_wgrad_reduce(St st, const float* scratch, int S, int Cp, int Cq, int T, float* grad_master) {
-  int64_t total = (int64_t)Cp * Cq * T;
-  int64_t blocks = (total + 255) / 256;
-  if (blocks > NSM * 8) blocks = NSM * 8;
-  if (blocks < 1) blocks = 1;
-  wgrad_reduce_kernel<<<(int)blocks, 256, 0, st.s>>>(scratch, S, Cp, Cq, T, grad_master);
+  const int64_t row = (int64_t)T * Cq, total = row * Cp;
+  if (total <= 0) return;
+  // cq values per block: <= 2048 elements of shared memory, and enough blocks for the machine when the gradient is
+  // small (thin layers: few elements, hundreds of partials)
+  int ncq = std::max(1, std::min(Cq, WR_CHUNK_MAX / T));
+  while (ncq > 4 && (int64_t)Cp * ((Cq + ncq - 1) / ncq) < 2 * NSM) ncq = (ncq + 1) / 2;
+  const int64_t nchunk = (Cq + ncq - 1) / ncq;
+  wgrad_reduce_kernel<<<(unsigned)(Cp * nchunk), 256, 0, st.s>>>(scratch, S, Cp, Cq, T, ncq, grad_master);
   DSR_LAUNCHED(st, "wgrad_reduce", 4.0 * total * (S + 2), WORK_BYTES);
 }

@@ -27,6 +27,7 @@ struct ThinWg {
   int cs, ts;                 // fat pixels of a class: (a*cs + cy, b*cs + cx); thin pixel = (a*ts + oy, b*ts + ox)
   int ncls, Ha, Wa;           // class grid extents (upper bound; fy < Hf / fx < Wf is checked)
   int V, PS;                  // float4 lanes per pixel (pow2 >= Cf/4), pixel slots per block
+  int seg, nseg;              // a work item = `seg` class pixels of one fat row (rows are split when there are few of them)
   int T, Cp, Cq, fat_is_p;
   int npairs[THIN_MAXCLS];
   short cy[THIN_MAXCLS], cx[THIN_MAXCLS];
@@ -72,16 +73,20 @@ static bool thin_wg_cfg(const WgradGeom& g, ThinWg& w) {
   while (v < w.Cf / 4) v <<= 1;
   w.V = v; w.PS = 256 / v;
   w.Ha = (w.Hf + w.cs - 1) / w.cs; w.Wa = (w.Wf + w.cs - 1) / w.cs;
+  // split rows into segments while there are fewer items than thread slots on the machine
+  w.seg = w.Wa; w.nseg = 1;
+  // (splitting rows into segments was measured: the per-block reduction then outweighs the extra parallelism)
   // block reduction buffer: (pairs per group <= 16 / Ct ... 16) * Ct * V float4 <= 40 KB
   const int grp = w.Ct == 1 ? 16 : (w.Ct == 2 ? 8 : 4);
   if ((size_t)grp * w.Ct * w.V * 4 * sizeof(float) > 40 * 1024) return false;
   return true;
 }
 
+// blocks per class: every SM full (3 resident blocks at <= 80 registers), never more items than there are
 static int thin_wg_blocks(const ThinWg& w) {
-  const int64_t rows = (int64_t)w.N * w.Ha;
-  int64_t nb = (rows + w.PS - 1) / w.PS;
-  const int64_t cap = std::max(1, NSM * 4 / w.ncls);
+  const int64_t items = (int64_t)w.N * w.Ha * w.nseg;
+  int64_t nb = (items + w.PS - 1) / w.PS;
+  const int64_t cap = std::max(1, NSM * 3 / w.ncls);
   return (int)std::max<int64_t>(1, std::min(nb, cap));
 }
 
@@ -112,8 +117,10 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(const ThinWg w, const f
 #pragma unroll
     for (int c = 0; c < CT; ++c) acc[j][c] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  const int64_t rows = (int64_t)w.N * w.Ha;
-  for (int64_t row = (int64_t)blockIdx.x * w.PS + slot; row < rows; row += (int64_t)gridDim.x * w.PS) {
+  const int64_t items = (int64_t)w.N * w.Ha * w.nseg;
+  for (int64_t item = (int64_t)blockIdx.x * w.PS + slot; item < items; item += (int64_t)gridDim.x * w.PS) {
+    const int64_t row = item / w.nseg;
+    const int bbeg = (int)(item % w.nseg) * w.seg, bend = min(nb, bbeg + w.seg);
     const int n = (int)(row / w.Ha), a = (int)(row % w.Ha);
     const int fy = a * w.cs + cy;
     if (fy >= w.Hf || !lane_ok) continue;
@@ -133,11 +140,11 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(const ThinWg w, const f
       }
     }
     constexpr int UNR = 4;
-    for (int b0 = 0; b0 < nb; b0 += UNR) {
+    for (int b0 = bbeg; b0 < bend; b0 += UNR) {
       float4 f[UNR];
 #pragma unroll
       for (int u = 0; u < UNR; ++u)
-        f[u] = b0 + u < nb ? __ldg(reinterpret_cast<const float4*>(frow + (int64_t)(b0 + u) * fstep)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        f[u] = b0 + u < bend ? __ldg(reinterpret_cast<const float4*>(frow + (int64_t)(b0 + u) * fstep)) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < MAXP; ++j) {
         if (j < np && trow[j]) {
@@ -225,7 +232,7 @@ bool k_wgrad_thin(St st, const WgradGeom& g, const float* P, const float* Q, flo
 // =====================================================================================================================
 struct ThinInCls { int Hg, Wg, oy0, ox0, ntaps; short dy[16], dx[16]; const float* wp; };
 struct ThinIn {
-  int N, Hi, Wi, Ci, Ho, Wo, Co, si, so, ncls, act;
+  int N, Hi, Wi, Ci, Ho, Wo, Co, si, so, ncls, act, vpad, seg, nseg;
   float neg;
   ThinInCls c[4];
 };
@@ -240,45 +247,62 @@ __device__ __forceinline__ float thin_act(float v, int act, float neg) {
   }
 }
 
-template <int CI>
+template <int CI, int NT>
 __global__ void __launch_bounds__(256) thin_in_kernel(const ThinIn p, const float* __restrict__ in, float* __restrict__ out) {
   extern __shared__ __align__(16) float sw[];                  // [t][ci][Co]
   const ThinInCls& c = p.c[blockIdx.y];
   const int wn = c.ntaps * CI * p.Co;
   for (int i = threadIdx.x; i < wn; i += 256) sw[i] = c.wp[i];
   __syncthreads();
-  const int V = p.Co >> 2;                                      // float4 lanes per pixel
-  const int64_t total = (int64_t)p.N * c.Hg * c.Wg * V;
-  for (int64_t idx = (int64_t)blockIdx.x * 256 + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * 256) {
-    const int v = (int)(idx % V);
-    int64_t pix = idx / V;
-    const int gx = (int)(pix % c.Wg); pix /= c.Wg;
-    const int gy = (int)(pix % c.Hg);
-    const int n = (int)(pix / c.Hg);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int t = 0; t < c.ntaps; ++t) {
-      const int iy = gy * p.si + c.dy[t], ix = gx * p.si + c.dx[t];
-      if (iy < 0 || iy >= p.Hi || ix < 0 || ix >= p.Wi) continue;
-      const float* ip = in + ((int64_t)(n * p.Hi + iy) * p.Wi + ix) * CI;
+  // threads = [row slot][float4 lane over couts]; a slot walks one grid row (n, gy) at a time along gx
+  const int V = p.Co >> 2;
+  const int VP = p.vpad;                                        // pow2 >= V, divides 256
+  const int v = threadIdx.x % VP, slot = threadIdx.x / VP, PS = 256 / VP;
+  if (v >= V) return;
+  const float4* wv = reinterpret_cast<const float4*>(sw) + v;  // + (t*CI + ci) * V
+  const int items = p.N * c.Hg * p.nseg;                       // (row, gx segment)
+  for (int item = blockIdx.x * PS + slot; item < items; item += gridDim.x * PS) {
+    const int row = item / p.nseg, gx0 = (item - row * p.nseg) * p.seg, gx1 = min(c.Wg, gx0 + p.seg);
+    const int n = row / c.Hg, gy = row - n * c.Hg;
+    const float* ir[NT];
+    int dxs[NT];
 #pragma unroll
-      for (int ci = 0; ci < CI; ++ci) {
-        const float x = __ldg(ip + ci);
-        const float4 w = *reinterpret_cast<const float4*>(&sw[(t * CI + ci) * p.Co + v * 4]);
-        acc.x = fmaf(x, w.x, acc.x); acc.y = fmaf(x, w.y, acc.y); acc.z = fmaf(x, w.z, acc.z); acc.w = fmaf(x, w.w, acc.w);
+    for (int t = 0; t < NT; ++t) {
+      ir[t] = nullptr;
+      dxs[t] = 0;
+      if (t < c.ntaps) {
+        const int iy = gy * p.si + c.dy[t];
+        dxs[t] = c.dx[t];
+        if (iy >= 0 && iy < p.Hi) ir[t] = in + ((int64_t)(n * p.Hi + iy) * p.Wi) * CI;
       }
     }
-    acc.x = thin_act(acc.x, p.act, p.neg); acc.y = thin_act(acc.y, p.act, p.neg);
-    acc.z = thin_act(acc.z, p.act, p.neg); acc.w = thin_act(acc.w, p.act, p.neg);
-    float* o = out + ((int64_t)(n * p.Ho + gy * p.so + c.oy0) * p.Wo + gx * p.so + c.ox0) * p.Co + v * 4;
-    *reinterpret_cast<float4*>(o) = acc;
+    const int ostep = p.so * p.Co;
+    float* o = out + ((int64_t)(n * p.Ho + gy * p.so + c.oy0) * p.Wo + c.ox0) * p.Co + v * 4 + (int64_t)gx0 * ostep;
+    for (int gx = gx0; gx < gx1; ++gx, o += ostep) {
+      float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int t = 0; t < NT; ++t) {
+        const int ix = gx * p.si + dxs[t];
+        if (ir[t] && ix >= 0 && ix < p.Wi) {
+#pragma unroll
+          for (int ci = 0; ci < CI; ++ci) {
+            const float x = __ldg(ir[t] + ix * CI + ci);
+            const float4 w = wv[(t * CI + ci) * V];
+            acc.x = fmaf(x, w.x, acc.x); acc.y = fmaf(x, w.y, acc.y); acc.z = fmaf(x, w.z, acc.z); acc.w = fmaf(x, w.w, acc.w);
+          }
+        }
+      }
+      acc.x = thin_act(acc.x, p.act, p.neg); acc.y = thin_act(acc.y, p.act, p.neg);
+      acc.z = thin_act(acc.z, p.act, p.neg); acc.w = thin_act(acc.w, p.act, p.neg);
+      *reinterpret_cast<float4*>(o) = acc;
+    }
   }
 }
 
 bool thin_in_supported(const TapGeom* cls, int ncls) {
   if (ncls < 1 || ncls > 4) return false;
   const TapGeom& g = cls[0];
-  if (g.Ci < 1 || g.Ci > 4 || g.Co % 4 || g.Co < 4) return false;
+  if (g.Ci < 1 || g.Ci > 4 || g.Co % 4 || g.Co < 4 || g.Co > 1024) return false;
   for (int i = 0; i < ncls; ++i)
     if (cls[i].ntaps > 16 || (size_t)cls[i].ntaps * g.Ci * g.Co * sizeof(float) > 96 * 1024) return false;
   return true;
@@ -305,23 +329,36 @@ bool k_tapconv_thin_in(St st, const TapGeom* cls, int ncls, const float* const* 
   }
   if (maxtot <= 0) return true;
   bytes += 4.0 * g.N * g.Hi * g.Wi * g.Ci;
-  int64_t nb = std::min<int64_t>((maxtot + 255) / 256, NSM * 8);
-  dim3 grid((unsigned)std::max<int64_t>(nb, 1), (unsigned)ncls);
-  static bool attr[5] = {false, false, false, false, false};
-#define THIN_IN_LAUNCH(CI)                                                                                         \
+  int vp = 1;
+  while (vp < g.Co / 4) vp <<= 1;
+  p.vpad = vp;
+  int maxrows = 1, maxt = 1;
+  for (int i = 0; i < ncls; ++i) { maxrows = std::max(maxrows, g.N * cls[i].Hg); maxt = std::max(maxt, cls[i].ntaps); }
+  const int PS = 256 / vp;
+  // split rows into gx segments while there are fewer work items than thread slots on the machine
+  int maxw = 1;
+  for (int i = 0; i < ncls; ++i) maxw = std::max(maxw, cls[i].Wg);
+  p.seg = maxw; p.nseg = 1;
+  while (p.seg > 4 && (int64_t)maxrows * p.nseg * ncls < (int64_t)NSM * 8 * PS) { p.seg = (p.seg + 1) / 2; p.nseg = (maxw + p.seg - 1) / p.seg; }
+  dim3 grid((unsigned)std::min((maxrows * p.nseg + PS - 1) / PS, NSM * 8), (unsigned)ncls);
+#define THIN_IN_LAUNCH(CI, NT)                                                                                     \
   do {                                                                                                             \
-    if (!attr[CI] && smem > 48 * 1024) {                                                                           \
-      cudaFuncSetAttribute(thin_in_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);            \
-      attr[CI] = true;                                                                                             \
-    }                                                                                                              \
-    thin_in_kernel<CI><<<grid, 256, smem, st.s>>>(p, in, out);                                                     \
+    if (smem > 48 * 1024) cudaFuncSetAttribute(thin_in_kernel<CI, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); \
+    thin_in_kernel<CI, NT><<<grid, 256, smem, st.s>>>(p, in, out);                                                 \
+  } while (0)
+#define THIN_IN_NT(CI)                                    \
+  do {                                                    \
+    if (maxt <= 4) THIN_IN_LAUNCH(CI, 4);                 \
+    else if (maxt <= 9) THIN_IN_LAUNCH(CI, 9);            \
+    else THIN_IN_LAUNCH(CI, 16);                          \
   } while (0)
   switch (g.Ci) {
-    case 1: THIN_IN_LAUNCH(1); break;
-    case 2: THIN_IN_LAUNCH(2); break;
-    case 3: THIN_IN_LAUNCH(3); break;
-    default: THIN_IN_LAUNCH(4); break;
+    case 1: THIN_IN_NT(1); break;
+    case 2: THIN_IN_NT(2); break;
+    case 3: THIN_IN_NT(3); break;
+    default: THIN_IN_NT(4); break;
   }
+#undef THIN_IN_NT
 #undef THIN_IN_LAUNCH
   DSR_LAUNCHED(st, "tapconv_thin_in", bytes, WORK_BYTES);
   return true;
@@ -390,7 +427,11 @@ __global__ void __launch_bounds__(256) thin_out_kernel(const ThinOut p, const fl
   }
 }
 
-bool thin_out_supported(const TapGeom& g) { return g.Co >= 1 && g.Co <= 4 && g.Ci % 4 == 0 && g.Ci >= 4 && g.ntaps >= 1; }
+// only where the contraction is long and the pixels are few (D's final 512 -> 1 conv: 64 outputs of K = 8192); with many
+// pixels the GEMM kernels' tiling of the input wins (a warp-per-pixel reduction re-reads every input pixel per tap)
+bool thin_out_supported(const TapGeom& g) {
+  return g.Co >= 1 && g.Co <= 4 && g.Ci % 4 == 0 && g.Ci >= 4 && g.ntaps >= 1 && (int64_t)g.N * g.Hg * g.Wg <= NSM * 32;
+}
 
 bool k_tapconv_thin_out(St st, const TapGeom& g, const float* in, const float* wp, float* out, int act, float neg) {
   if (!thin_out_supported(g)) return false;

@@ -87,8 +87,17 @@ def tf32_oracle(act_round=trunc_tf32, thin_exact=True):
     names = ("conv2d_fwd", "conv2d_dgrad", "conv2d_wgrad", "fullconv2d_fwd", "fullconv2d_dgrad", "fullconv2d_wgrad")
     orig = {k: getattr(_ops, k) for k in names}
 
-    def tc(c):
-        return (not thin_exact) or c % 8 == 0
+    def tc2(cin, cout, npix):
+        """True when the library runs this contraction on the tensor cores: contraction channels a multiple of 8, and not
+        one of the streaming fp32 kernels (thin input: <= 4 contraction channels; thin output: <= 4 output channels with
+        few pixels -- kernels_thin.cu:thin_out_supported)."""
+        if not thin_exact:
+            return True
+        if cin % 8 or cin <= 4:
+            return False
+        if cout <= 4 and cin % 4 == 0 and npix <= 148 * 32:
+            return False
+        return True
 
     def r(x, on):
         return act_round(x) if on else x
@@ -96,16 +105,36 @@ def tf32_oracle(act_round=trunc_tf32, thin_exact=True):
     def w_(w, on):
         return rna_tf32(w) if on else w
 
-    # forward contracts over cin, dgrad over cout, wgrad over pixels (tensor cores need both channel counts >= 8, % 4)
-    _ops.conv2d_fwd = lambda x, w, s, p: orig["conv2d_fwd"](r(x, tc(w.shape[1])), w_(w, tc(w.shape[1])), s, p)
-    _ops.conv2d_dgrad = lambda dy, w, xs, s, p: orig["conv2d_dgrad"](r(dy, tc(w.shape[0])), w_(w, tc(w.shape[0])), xs, s, p)
-    _ops.conv2d_wgrad = lambda x, dy, ws, s, p: orig["conv2d_wgrad"](r(x, _wg(ws)), r(dy, _wg(ws)), ws, s, p)
-    _ops.fullconv2d_fwd = lambda x, w, s, p, adj=0: orig["fullconv2d_fwd"](r(x, tc(w.shape[0])), w_(w, tc(w.shape[0])), s, p, adj)
-    _ops.fullconv2d_dgrad = lambda dy, w, s, p: orig["fullconv2d_dgrad"](r(dy, tc(w.shape[1])), w_(w, tc(w.shape[1])), s, p)
-    _ops.fullconv2d_wgrad = lambda x, dy, ws, s, p: orig["fullconv2d_wgrad"](r(x, _wg(ws)), r(dy, _wg(ws)), ws, s, p)
-
     def _wg(ws):
         return (not thin_exact) or (ws[0] % 4 == 0 and ws[1] % 4 == 0 and ws[0] >= 8 and ws[1] >= 8)
+
+    # forward contracts over cin, dgrad over cout, wgrad over pixels; npix = pixels of the iterated grid (per class)
+    def conv_fwd(x, w, s, p):
+        ho = (x.shape[2] + 2 * p - w.shape[2]) // s + 1
+        wo = (x.shape[3] + 2 * p - w.shape[3]) // s + 1
+        on = tc2(w.shape[1], w.shape[0], x.shape[0] * ho * wo)
+        return orig["conv2d_fwd"](r(x, on), w_(w, on), s, p)
+
+    def conv_dgrad(dy, w, xs, s, p):
+        on = tc2(w.shape[0], w.shape[1], xs[0] * -(-xs[2] // s) * -(-xs[3] // s))
+        return orig["conv2d_dgrad"](r(dy, on), w_(w, on), xs, s, p)
+
+    def full_fwd(x, w, s, p, adj=0):
+        on = tc2(w.shape[0], w.shape[1], x.shape[0] * x.shape[2] * x.shape[3])
+        return orig["fullconv2d_fwd"](r(x, on), w_(w, on), s, p, adj)
+
+    def full_dgrad(dy, w, s, p):
+        hi = (dy.shape[2] + 2 * p - w.shape[2]) // s + 1
+        wi = (dy.shape[3] + 2 * p - w.shape[3]) // s + 1
+        on = tc2(w.shape[1], w.shape[0], dy.shape[0] * hi * wi)
+        return orig["fullconv2d_dgrad"](r(dy, on), w_(w, on), s, p)
+
+    _ops.conv2d_fwd = conv_fwd
+    _ops.conv2d_dgrad = conv_dgrad
+    _ops.conv2d_wgrad = lambda x, dy, ws, s, p: orig["conv2d_wgrad"](r(x, _wg(ws)), r(dy, _wg(ws)), ws, s, p)
+    _ops.fullconv2d_fwd = full_fwd
+    _ops.fullconv2d_dgrad = full_dgrad
+    _ops.fullconv2d_wgrad = lambda x, dy, ws, s, p: orig["fullconv2d_wgrad"](r(x, _wg(ws)), r(dy, _wg(ws)), ws, s, p)
 
     try:
         yield
