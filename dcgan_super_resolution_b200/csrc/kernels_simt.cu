@@ -411,19 +411,25 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
   const int cp = blockIdx.x / nchunk, cq0 = (blockIdx.x % nchunk) * ncq;
   const int nc = min(ncq, Cq - cq0);                    // cq range of this block
   const int n = nc * T;
-  const int lane = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  // 4 split groups x 64 element lanes when there are enough partials, else all 256 threads on elements
+  const int G = S >= 4 ? 4 : 1, E = 256 / G;
+  const int lane = threadIdx.x % E, grp = threadIdx.x / E;
   const int64_t total = (int64_t)Cp * row;
   // read order (t major, cq minor): coalesced along cq; stored transposed ([cq][t]) in shared memory
-  for (int e = lane; e < n; e += 64) {
+  for (int e = lane; e < n; e += E) {
     const int t = e / nc, c = e - t * nc;
     const float* src = scratch + (int64_t)cp * row + (int64_t)t * Cq + cq0 + c;
     float a = 0.f;
-    for (int s = grp; s < S; s += 4) a += src[(int64_t)s * total];
+    for (int s = grp; s < S; s += G) a += src[(int64_t)s * total];
     part[grp][c * T + t] = a;
   }
   __syncthreads();
   float* dst = grad_master + (int64_t)cp * row + (int64_t)cq0 * T;
-  for (int o = threadIdx.x; o < n; o += 256) dst[o] += ((part[0][o] + part[1][o]) + part[2][o]) + part[3][o];
+  if (S >= 4) {
+    for (int o = threadIdx.x; o < n; o += 256) dst[o] += ((part[0][o] + part[1][o]) + part[2][o]) + part[3][o];
+  } else {
+    for (int o = threadIdx.x; o < n; o += 256) dst[o] += part[0][o];
+  }
 }
 
 void k_wgrad_simt(St st, const WgradGeom& g, const float* P, const float* Q, float* grad_master,

@@ -564,21 +564,43 @@ static bool wg_tc_cfg(const WgradGeom& g, WgTcCfg& c) {
   p.ntiles = tiles_b * p.tiles_y * p.tiles_x;
   p.atoms_p = 128 / p.kbp;
   const int cq32 = (g.Cq + 31) / 32 * 32;
-  p.n_mma = std::min(cq32, 256);
+  const int mtiles = (g.Cp + 127) / 128;
+  // Work decomposition: (cq slice n_mma) x (taps per CTA TG) x (pixel splits S).  Splitting the OUTPUT (smaller n_mma / TG)
+  // costs re-reads of the P tile through L2; splitting the pixels costs S partial copies of the gradient that
+  // wgrad_reduce has to stream.  A tf32 MMA costs max(64, N/2) tensor cycles, so N = 128 slices lose nothing.
+  double best = 1e30;
+  int best_n = 0, best_tg = 0, best_s = 1;
+  for (int n_mma = std::min(cq32, 256); n_mma >= 32; n_mma >>= 1) {
+    if (n_mma > cq32) continue;
+    const int q_tiles = (g.Cq + n_mma - 1) / n_mma;
+    for (int tg = std::max(1, std::min(g.ntaps, 512 / n_mma)); tg >= 1; tg >>= 1) {
+      const int other = ((g.ntaps + tg - 1) / tg) * mtiles * q_tiles;
+      for (int S = 1; S <= p.ntiles; S <<= 1) {
+        const double ctas = (double)other * S;
+        const double waves = std::max(1.0, ctas / NSM);
+        const double tiles_cta = (double)(p.ntiles + S - 1) / S;
+        const double mma = tiles_cta * tg * (p.KPIX / 8) * std::max(64.0, n_mma / 2.0);                    // tensor cycles per CTA
+        const double l2 = tiles_cta * (128.0 * p.KPIX * 4 + (double)tg * n_mma * p.KPIX * 4) / 48.0;       // ~48 B/clk/SM from L2
+        const double red = (S + 2.0) * g.Cp * g.Cq * g.ntaps * 4.0 / 2000.0;                               // ~2 KB/clk chip-wide
+        const double est = std::max(mma, l2) * waves + 3000.0 + red;
+        if (est < best) { best = est; best_n = n_mma; best_tg = tg; best_s = S; }
+        if (ctas >= 2 * NSM) break;
+      }
+    }
+  }
+  if (best_n == 0) return false;
+  p.n_mma = best_n;
   p.q_tiles = (g.Cq + p.n_mma - 1) / p.n_mma;
   p.atoms_q = (p.n_mma + p.kbq - 1) / p.kbq;
-  p.TG = std::max(1, std::min(g.ntaps, 512 / p.n_mma));
+  p.TG = best_tg;
   c.tap_groups = (g.ntaps + p.TG - 1) / p.TG;
   p.tmem_cols = std::max(32, pow2_ge(p.TG * p.n_mma));
   p.p_stage_bytes = p.atoms_p * p.KPIX * p.kbp * 4;          // 128 channels x KPIX pixels x 4 B = 32 KB
   p.q_stage_bytes = (p.atoms_q * p.KPIX * p.kbq * 4 + 1023) / 1024 * 1024;
   p.np_stage = 2;
   p.nq_stage = std::max(2, std::min(8, (120 * 1024) / p.q_stage_bytes));
-  const int mtiles = (g.Cp + 127) / 128;
   c.z = mtiles * p.q_tiles;
-  const int other = c.tap_groups * c.z;
-  int S = std::max(1, (NSM * 2 + other - 1) / other);
-  S = std::min(S, p.ntiles);
+  int S = std::min(best_s, p.ntiles);
   p.tiles_per_split = (p.ntiles + S - 1) / S;
   c.S = (p.ntiles + p.tiles_per_split - 1) / p.tiles_per_split;
   p.split_stride = (long long)g.Cp * g.ntaps * g.Cq;
