@@ -184,7 +184,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--precision", default=os.environ.get("DCGANSR_PRECISION", "tf32"), choices=["strict", "tf32"])
-    ap.add_argument("--graph", type=int, default=0)
+    ap.add_argument("--graph", type=int, default=1, help="replay the step as a CUDA graph (one cached graph per staged batch)")
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--sync-bn", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -281,7 +281,7 @@ def main():
 
     # ---------------- per-kernel profile (extra steps, same stream, CUDA events per launch) --------
     prof = []
-    if args.profile_steps > 0 and not args.graph:
+    if args.profile_steps > 0:                       # eager launches with per-launch events (the graph is bypassed while profiling)
         ctx.profile_begin()
         for i in range(args.profile_steps):
             dsr.train_step_staged(ctx, G, D, scfg, i % NPOOL, B)
