@@ -18,10 +18,13 @@ struct Prof {
   std::vector<cudaEvent_t> pool;     // pool[0] = begin marker, pool[i+1] recorded after launch i
   std::vector<ProfRec> recs;
 };
+// per-context device workspace of the tensor-core kernels (split-K partial tiles + self-resetting arrival counters)
+struct TcWorkspace { float* part = nullptr; size_t part_bytes = 0; int* counters = nullptr; int ncounters = 0; };
 struct St {
   cudaStream_t s;
   int64_t* launches;
   Prof* prof;
+  TcWorkspace* ws = nullptr;
 };
 static inline void dsr_launched(const St& st, const char* name, double work, int kind) {
   if (st.launches) ++*st.launches;

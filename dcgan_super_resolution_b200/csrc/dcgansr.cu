@@ -29,6 +29,7 @@
 // errors
 // ------------------------------------------------------------------------------------------
 static thread_local std::string t_err;
+#define NSM_WS 160      // split-K workspace: one 128 x 128 partial tile per resident CTA
 
 struct NcclApi {
   void* h = nullptr;
@@ -75,7 +76,8 @@ struct dcgansr_ctx {
   cudaEvent_t graph_ev[2] = {nullptr, nullptr};
   uint64_t graph_seq = 0;
   Prof prof;
-  St st() { return St{stream, &launches, &prof}; }
+  TcWorkspace tcws;
+  St st() { return St{stream, &launches, &prof, &tcws}; }
   int world() const { return cfg.world_size > 1 && comm ? cfg.world_size : 1; }
 };
 
@@ -626,6 +628,13 @@ int dcgansr_ctx_create(const dcgansr_cfg* cfg, dcgansr_ctx** out) {
   }
   dcgansr_ctx* ctx = new dcgansr_ctx();
   ctx->cfg = *cfg;
+  if (cfg->precision == DCGANSR_FAST_TF32) {
+    ctx->tcws.part_bytes = (size_t)NSM_WS * 128 * 128 * sizeof(float);
+    ctx->tcws.ncounters = 4096;
+    CK(ctx, cudaMalloc((void**)&ctx->tcws.part, ctx->tcws.part_bytes));
+    CK(ctx, cudaMalloc((void**)&ctx->tcws.counters, ctx->tcws.ncounters * sizeof(int)));
+    CK(ctx, cudaMemset(ctx->tcws.counters, 0, ctx->tcws.ncounters * sizeof(int)));
+  }
   if (ctx->cfg.world_size < 1) ctx->cfg.world_size = 1;
   CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CK(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
@@ -647,6 +656,8 @@ void dcgansr_ctx_destroy(dcgansr_ctx* ctx) {
   for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
   if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
   for (float* p : ctx->slots) if (p) cudaFree(p);
+  if (ctx->tcws.part) cudaFree(ctx->tcws.part);
+  if (ctx->tcws.counters) cudaFree(ctx->tcws.counters);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
   if (ctx->tmp) cudaFree(ctx->tmp);
   if (ctx->label_vec) cudaFree(ctx->label_vec);

@@ -609,8 +609,11 @@ bool k_tapconv_halo(St st, const TapGeom* classes, int ncls, const float* const*
   }
   dim3 grid((unsigned)c.grid_x, (unsigned)c.nsplit);
   tapconv_halo_kernel<<<grid, 32 * (9 + p.ngrp), c.smem, st.s>>>(mapA, maps, c.tab, p, out);
-  double flops = 0;
-  for (int i = 0; i < ncls; ++i) flops += 2.0 * g.N * g.Hg * g.Wg * classes[i].ntaps * g.Ci * g.Co;
-  DSR_LAUNCHED(st, "tapconv_halo", flops, WORK_FLOPS);
+  // HBM-bound by construction (input and output once, weights resident): the roofline work of a launch is its
+  // algorithmic bytes = input + output + weights (fp32)
+  double wbytes = 0;
+  for (int i = 0; i < ncls; ++i) wbytes += 4.0 * classes[i].ntaps * g.Ci * g.Co;
+  const double bytes = 4.0 * ((double)g.N * g.Hi * g.Wi * g.Ci + (double)g.N * g.Ho * g.Wo * g.Co) + wbytes;
+  DSR_LAUNCHED(st, "tapconv_halo", bytes, WORK_BYTES);
   return true;
 }

@@ -98,7 +98,8 @@ struct TcParams {
   int so, si, Ci;
   int TW, TH, TB, tiles_x, tiles_y;
   int KB, kchunks, BN, nstage;
-  int ncls, oy0[TC_MAXCLS], ox0[TC_MAXCLS], ntaps[TC_MAXCLS];      // sub-pixel classes: blockIdx.z
+  int ncls, oy0[TC_MAXCLS], ox0[TC_MAXCLS], ntaps[TC_MAXCLS];      // sub-pixel classes: blockIdx.z / ksplit
+  int ksplit;                                                      // K splits per tile: blockIdx.z % ksplit
   int a_stage_bytes, b_stage_bytes, tmem_cols;
   int act;
   float neg;
@@ -111,7 +112,7 @@ struct TcMaps { CUtensorMap b[TC_MAXCLS]; };
 
 __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                 const __grid_constant__ TcMaps mapsB, const TcParams p,
-                                                                float* __restrict__ out) {
+                                                                float* __restrict__ out, float* __restrict__ part, int* __restrict__ counters) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [A stages][B stages][barriers]
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -122,11 +123,16 @@ __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_con
   uint64_t* empty = bars + p.nstage;
   uint64_t* tmem_full = bars + 2 * p.nstage;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * p.nstage + 1);
+  int* s_last = reinterpret_cast<int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int cls = blockIdx.z;
+  const int cls = blockIdx.z / p.ksplit, split = blockIdx.z % p.ksplit;
   const int ntaps = p.ntaps[cls];
-  const int nk = ntaps * p.kchunks;
+  const int nk_all = ntaps * p.kchunks;
+  // this CTA's range of K blocks (split-K: small grids with a long contraction use all SMs; the partial tiles are summed in
+  // fixed order by the last CTA of the tile to arrive)
+  const int kb_beg = (int)((long long)nk_all * split / p.ksplit), kb_end = (int)((long long)nk_all * (split + 1) / p.ksplit);
+  const int nk = kb_end - kb_beg;
 
   // tile coordinates
   int tile = blockIdx.x;
@@ -158,20 +164,18 @@ __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_con
       int s = 0;
       uint32_t ph = 0;
       const uint32_t bytes = (uint32_t)(128 * p.KB * 4 + p.BN * p.KB * 4);
-      int kb = 0;
-      for (int t = 0; t < ntaps; ++t) {
-        for (int c = 0; c < p.kchunks; ++c, ++kb) {
-          mbar_wait(smem_u32(&empty[s]), ph ^ 1);
-          const uint32_t fb = smem_u32(&full[s]);
-          mbar_expect_tx(fb, bytes);
-          const uint32_t da = smem_u32(sA + (size_t)s * p.a_stage_bytes);
-          if (p.si == 1)
-            tma_load_4d(da, &mapA, fb, c * p.KB, gx0 + p.ox[cls][t], gy0 + p.oy[cls][t], b0);
-          else
-            tma_load_5d(da, &mapA, fb, p.px[cls][t] * p.Ci + c * p.KB, gx0 + p.ox[cls][t], p.py[cls][t], gy0 + p.oy[cls][t], b0);
-          tma_load_2d(smem_u32(sB + (size_t)s * p.b_stage_bytes), &mapsB.b[cls], fb, (t * p.kchunks + c) * p.KB, n0);
-          if (++s == p.nstage) { s = 0; ph ^= 1; }
-        }
+      for (int kb = kb_beg; kb < kb_end; ++kb) {
+        const int t = kb / p.kchunks, c = kb - t * p.kchunks;
+        mbar_wait(smem_u32(&empty[s]), ph ^ 1);
+        const uint32_t fb = smem_u32(&full[s]);
+        mbar_expect_tx(fb, bytes);
+        const uint32_t da = smem_u32(sA + (size_t)s * p.a_stage_bytes);
+        if (p.si == 1)
+          tma_load_4d(da, &mapA, fb, c * p.KB, gx0 + p.ox[cls][t], gy0 + p.oy[cls][t], b0);
+        else
+          tma_load_5d(da, &mapA, fb, p.px[cls][t] * p.Ci + c * p.KB, gx0 + p.ox[cls][t], p.py[cls][t], gy0 + p.oy[cls][t], b0);
+        tma_load_2d(smem_u32(sB + (size_t)s * p.b_stage_bytes), &mapsB.b[cls], fb, kb * p.KB, n0);
+        if (++s == p.nstage) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -204,15 +208,57 @@ __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_con
     const int b = r / (p.TW * p.TH);
     const int n = b0 + b, gy = gy0 + h, gx = gx0 + w;
     const bool valid = n < p.N && gy < p.Hg && gx < p.Wg;
+    bool valid_any = true;
     float* orow = nullptr;
     if (valid) orow = out + ((int64_t)(n * p.Ho + gy * p.so + p.oy0[cls]) * p.Wo + gx * p.so + p.ox0[cls]) * p.Co;
     mbar_wait(smem_u32(tmem_full), 0);
     tc_fence_after();
     const bool vec = (p.Co & 3) == 0, vec8 = (p.Co & 7) == 0;
-    for (int c0 = 0; c0 < p.BN; c0 += 16) {
+    const float* psrc = nullptr;                 // split-K: the tile's partials, read back by the last CTA
+    if (p.ksplit > 1) {
+      const long long tile_lin = ((long long)cls * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+      float* prow = part + ((tile_lin * p.ksplit + split) * 128 + r) * p.BN;
+      for (int c0 = 0; c0 < p.BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          __stcg(reinterpret_cast<float4*>(prow + c0 + j), make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                                                        __uint_as_float(v[j + 3])));
+      }
+      __threadfence();
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (threadIdx.x == 64) {
+        const int old = atomicAdd(&counters[tile_lin], 1);
+        const int last = old == p.ksplit - 1;
+        if (last) counters[tile_lin] = 0;          // self-resetting: ready for the next launch
+        *s_last = last;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (!*s_last) valid_any = false;
+      else { __threadfence(); psrc = part + (tile_lin * p.ksplit * 128 + r) * p.BN; }
+    }
+    for (int c0 = 0; valid_any && c0 < p.BN; c0 += 16) {
       uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
-      tmem_ld_wait();
+      if (psrc) {
+        float a[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = 0.f;
+        for (int sp = 0; sp < p.ksplit; ++sp) {     // fixed order: deterministic
+          const float* src = psrc + (long long)sp * 128 * p.BN + c0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 x = __ldcg(reinterpret_cast<const float4*>(src + j));
+            a[j] += x.x; a[j + 1] += x.y; a[j + 2] += x.z; a[j + 3] += x.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(a[j]);
+      } else {
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld_wait();
+      }
       if (valid) {
         const int co = n0 + c0;
         if (vec8) {
@@ -297,6 +343,19 @@ bool k_tapconv_tc_multi(St st, const TapGeom* cls, int ncls, const float* const*
   const int budget = nctas <= NSM ? 200 * 1024 : 96 * 1024;
   p.nstage = std::max(2, std::min(8, budget / stage));
   p.tmem_cols = std::max(32, pow2_ge(p.BN));
+  // split-K when the grid leaves most SMs idle and the contraction is long
+  p.ksplit = 1;
+  {
+    int nk_min = 1 << 30;
+    for (int i = 0; i < ncls; ++i) nk_min = std::min(nk_min, cls[i].ntaps * p.kchunks);
+    // (measured on the discriminator layers: pays at <= 1/4 of the SMs, loses at 1/2 -- the partial-tile round trip)
+    if (st.ws && st.ws->part && nctas * 4 <= NSM && nk_min >= 16 && !getenv("DCGANSR_NO_SPLITK")) {
+      int ks = (int)std::min<long long>(NSM / nctas, 8);
+      ks = std::min(ks, nk_min / 8);
+      while (ks > 1 && ((size_t)nctas * ks * 128 * p.BN * sizeof(float) > st.ws->part_bytes || nctas > st.ws->ncounters)) --ks;
+      p.ksplit = std::max(1, ks);
+    }
+  }
   p.act = act; p.neg = negval;
   for (int i = 0; i < ncls; ++i) {
     p.oy0[i] = cls[i].oy0; p.ox0[i] = cls[i].ox0; p.ntaps[i] = cls[i].ntaps;
@@ -341,7 +400,7 @@ bool k_tapconv_tc_multi(St st, const TapGeom* cls, int ncls, const float* const*
     flops += 2.0 * g.N * g.Hg * g.Wg * cls[i].ntaps * g.Ci * g.Co;
   }
 
-  const size_t smem = 1024 + (size_t)p.nstage * stage + (2 * p.nstage + 1) * sizeof(uint64_t) + 16;
+  const size_t smem = 1024 + (size_t)p.nstage * stage + (2 * p.nstage + 1) * sizeof(uint64_t) + 32;
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(tapconv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024) != cudaSuccess) {
@@ -350,8 +409,8 @@ bool k_tapconv_tc_multi(St st, const TapGeom* cls, int ncls, const float* const*
     }
     configured = true;
   }
-  dim3 grid((unsigned)(tiles_b * p.tiles_y * p.tiles_x), (unsigned)ntiles_n, (unsigned)ncls);
-  tapconv_tc_kernel<<<grid, TC_THREADS, smem, st.s>>>(mapA, maps, p, out);
+  dim3 grid((unsigned)(tiles_b * p.tiles_y * p.tiles_x), (unsigned)ntiles_n, (unsigned)(ncls * p.ksplit));
+  tapconv_tc_kernel<<<grid, TC_THREADS, smem, st.s>>>(mapA, maps, p, out, st.ws ? st.ws->part : nullptr, st.ws ? st.ws->counters : nullptr);
   DSR_LAUNCHED(st, "tapconv_tc", flops, WORK_FLOPS);
   return true;
 }

@@ -327,7 +327,9 @@ bool k_wgrad_halo(St st, const WgradGeom& g, const float* P, const float* Q, flo
   }
   dim3 grid((unsigned)c.S, (unsigned)c.mtiles);
   wgrad_halo_kernel<<<grid, WH_THREADS, c.smem, st.s>>>(mapP, mapQ, c.tab, p, scratch);
-  DSR_LAUNCHED(st, "wgrad_halo", 2.0 * g.N * g.Hp * g.Wp * g.Cp * g.Cq * g.ntaps, WORK_FLOPS);
+  // HBM-bound by construction (P and Q read once): algorithmic bytes = both activations + the gradient
+  DSR_LAUNCHED(st, "wgrad_halo", 4.0 * ((double)g.N * g.Hp * g.Wp * g.Cp + (double)g.N * g.Hq * g.Wq * g.Cq + (double)g.Cp * g.Cq * g.ntaps),
+               WORK_BYTES);
   k_wgrad_reduce(st, scratch, c.S, g.Cp, g.Cq, g.ntaps, grad_master);
   return true;
 }
