@@ -219,7 +219,8 @@ def main():
     if world > 1:
         parallel.exchange_unique_id(ctx, dist, device=torch.device("cuda", local_rank))
     G = dsr.Sequential.from_specs(cfg["G"]).cuda(ctx, (cfg["nc"], cfg["hr"] // 2, cfg["hr"] // 2), B)
-    D = dsr.Sequential.from_specs(cfg["D"]).cuda(ctx, (cfg["nc"], cfg["hr"], cfg["hr"]), B)
+    # D holds 2B samples: the step then runs D(real) and D(fake) as one grouped pass (dcgansr.cu:step_body)
+    D = dsr.Sequential.from_specs(cfg["D"]).cuda(ctx, (cfg["nc"], cfg["hr"], cfg["hr"]), 2 * B)
     G.set_params(init.weights_init(cfg["G"], 4321))
     D.set_params(init.weights_init(cfg["D"], 8765))
     scfg = dsr.make_step_cfg(**cfg["step"])

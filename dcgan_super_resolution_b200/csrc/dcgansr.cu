@@ -472,41 +472,49 @@ static void net_pack_all(dcgansr_net* net) {
 }
 
 // forward on device buffers (in: NHWC).  Caches every module output: last forward wins.
-static int net_forward_dev(dcgansr_net* net, const float* in, int B) {
+// groups > 1: the batch holds `groups` independent minibatches of B samples each (the fused step runs D(real) and D(fake)
+// as ONE pass over 2B samples): convolutions see groups*B samples, every BatchNorm normalises each group with its own
+// statistics and updates the running statistics group after group -- exactly what `groups` separate forwards would do.
+static int net_forward_dev(dcgansr_net* net, const float* in, int B, int groups = 1) {
   dcgansr_ctx* ctx = net->ctx;
   St st = ctx->st();
   const float* cur = in;
   const bool sync = ctx->cfg.sync_bn && ctx->world() > 1;
+  const int NB = B * groups;
   for (auto& m : net->mods) {
     switch (m.kind) {
       case DCGANSR_UPNEAREST:
-        k_upnearest_fwd(st, cur, m.out, B, m.hin, m.win, m.cin, m.L.scale);
+        k_upnearest_fwd(st, cur, m.out, NB, m.hin, m.win, m.cin, m.L.scale);
         cur = m.out;
         break;
       case DCGANSR_CONV:
       case DCGANSR_FULLCONV:
-        m.conv->forward(ctx, cur, m.out, B, m.fused_act, m.fused_neg);
+        m.conv->forward(ctx, cur, m.out, NB, m.fused_act, m.fused_neg);
         cur = m.out;
         break;
       case DCGANSR_BN: {
         int64_t P = (int64_t)B * m.hin * m.win;
         int C = m.cin;
-        k_bn_stats(st, cur, P, C, net->bn_partials, net->bn_sums);
-        double n_total = (double)P;
-        if (sync) {
-          if (int rc = nccl_allreduce(ctx, net->bn_sums, 2 * C, ncclDouble, ctx->stream)) return rc;
-          n_total *= ctx->world();
+        for (int g = 0; g < groups; ++g) {
+          const float* xg = cur + (int64_t)g * P * C;
+          float* smean = m.save_mean + (int64_t)g * 2 * net->nbn;
+          float* sinv = m.save_invstd + (int64_t)g * 2 * net->nbn;
+          k_bn_stats(st, xg, P, C, net->bn_partials, net->bn_sums);
+          double n_total = (double)P;
+          if (sync) {
+            if (int rc = nccl_allreduce(ctx, net->bn_sums, 2 * C, ncclDouble, ctx->stream)) return rc;
+            n_total *= ctx->world();
+          }
+          k_bn_finalize(st, net->bn_sums, C, n_total, m.L.eps, m.L.momentum, smean, sinv, net->bn_rmean + m.bn_off, net->bn_rvar + m.bn_off);
+          k_bn_apply_act(st, xg, m.out + (int64_t)g * P * C, P, C, net->params + m.p_off, net->params + m.p_off + C, smean, sinv,
+                         m.fused_act, m.fused_neg);
         }
-        k_bn_finalize(st, net->bn_sums, C, n_total, m.L.eps, m.L.momentum, m.save_mean, m.save_invstd,
-                      net->bn_rmean + m.bn_off, net->bn_rvar + m.bn_off);
-        k_bn_apply_act(st, cur, m.out, P, C, net->params + m.p_off, net->params + m.p_off + C, m.save_mean, m.save_invstd,
-                       m.fused_act, m.fused_neg);
         cur = m.out;
         break;
       }
       case DCGANSR_RELU: case DCGANSR_LRELU: case DCGANSR_TANH: case DCGANSR_SIGMOID:
         if (!m.fused_into_prev) {
-          k_act(st, cur, m.out, (int64_t)B * m.cin * m.hin * m.win, m.act, m.L.negval);
+          k_act(st, cur, m.out, (int64_t)NB * m.cin * m.hin * m.win, m.act, m.L.negval);
           cur = m.out;
         }
         break;
@@ -514,27 +522,31 @@ static int net_forward_dev(dcgansr_net* net, const float* in, int B) {
     }
   }
   net->last_out = cur;
-  net->last_batch = B;
+  net->last_batch = NB;
   CKLAST(ctx);
   return 0;
 }
 
 // backward walk.  acc: accumulate parameter gradients (net:backward) or not (net:updateGradInput).
 // Returns the gradient w.r.t. the net input in *dx_out (nullptr when need_dx is false).
+// groups / goff: the cached activations hold several B-sample groups (see net_forward_dev); this walk covers groups
+// [goff, goff + groups): `in` and `dy` point at the first sample of group goff, cached module outputs are offset likewise.
 static int net_backward_dev(dcgansr_net* net, const float* in, const float* dy, int B, bool acc, bool need_dx,
-                            const float** dx_out) {
+                            const float** dx_out, int groups = 1, int goff = 0) {
   dcgansr_ctx* ctx = net->ctx;
   St st = ctx->st();
   const bool sync = ctx->cfg.sync_bn && ctx->world() > 1;
   const float* cur = dy;
+  const int NB = B * groups;
   if (dx_out) *dx_out = nullptr;
   for (int i = (int)net->mods.size() - 1; i >= 0; --i) {
     Mod& m = net->mods[i];
-    const float* inp = i > 0 ? net->mods[i - 1].out : in;
+    const float* inp = i > 0 ? net->mods[i - 1].out + (int64_t)goff * B * m.cin * m.hin * m.win : in;
+    const float* mout = m.out ? m.out + (int64_t)goff * B * m.cout * m.hout * m.wout : nullptr;
     switch (m.kind) {
       case DCGANSR_UPNEAREST: {
         float* t = net->other(cur);
-        k_upnearest_bwd(st, cur, t, B, m.hin, m.win, m.cin, m.L.scale);
+        k_upnearest_bwd(st, cur, t, NB, m.hin, m.win, m.cin, m.L.scale);
         cur = t;
         break;
       }
@@ -542,39 +554,45 @@ static int net_backward_dev(dcgansr_net* net, const float* in, const float* dy, 
       case DCGANSR_FULLCONV: {
         if (m.fused_act != ACT_NONE) {
           float* t = net->own(cur);
-          k_act_bwd(st, m.out, cur, t, (int64_t)B * m.cout * m.hout * m.wout, m.fused_act, m.fused_neg);
+          k_act_bwd(st, mout, cur, t, (int64_t)NB * m.cout * m.hout * m.wout, m.fused_act, m.fused_neg);
           cur = t;
         }
-        if (acc) m.conv->wgrad_run(ctx, inp, cur, net->grads + m.p_off, B, net->wscratch, net->wscratch_bytes);
+        if (acc) m.conv->wgrad_run(ctx, inp, cur, net->grads + m.p_off, NB, net->wscratch, net->wscratch_bytes);
         if (i == net->first_param_mod && !need_dx) { CKLAST(ctx); return 0; }
         float* t = net->other(cur);
-        m.conv->dgrad_run(ctx, cur, t, B);
+        m.conv->dgrad_run(ctx, cur, t, NB);
         cur = t;
         break;
       }
       case DCGANSR_BN: {
         int64_t P = (int64_t)B * m.hin * m.win;
         int C = m.cin;
-        float* g = net->own(cur);
-        k_bn_bwd_reduce(st, cur, m.fused_act != ACT_NONE ? m.out : nullptr, inp, g, P, C, m.save_mean, m.save_invstd,
-                        m.fused_act, m.fused_neg, net->bn_partials, net->bn_sums);
-        if (acc) k_bn_bwd_param(st, net->bn_sums, C, net->grads + m.p_off, net->grads + m.p_off + C);
-        const double* tot = net->bn_sums;
-        double n_total = (double)P;
-        if (sync) {
-          CK(ctx, cudaMemcpyAsync(net->bn_sums_total, net->bn_sums, 2 * C * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-          if (int rc = nccl_allreduce(ctx, net->bn_sums_total, 2 * C, ncclDouble, ctx->stream)) return rc;
-          tot = net->bn_sums_total;
-          n_total *= ctx->world();
+        float* gall = net->own(cur);
+        for (int gi = 0; gi < groups; ++gi) {
+          const int64_t off = (int64_t)gi * P * C;
+          const float* smean = m.save_mean + (int64_t)(goff + gi) * 2 * net->nbn;
+          const float* sinv = m.save_invstd + (int64_t)(goff + gi) * 2 * net->nbn;
+          float* g = gall + off;
+          k_bn_bwd_reduce(st, cur + off, m.fused_act != ACT_NONE ? mout + off : nullptr, inp + off, g, P, C, smean, sinv,
+                          m.fused_act, m.fused_neg, net->bn_partials, net->bn_sums);
+          if (acc) k_bn_bwd_param(st, net->bn_sums, C, net->grads + m.p_off, net->grads + m.p_off + C);
+          const double* tot = net->bn_sums;
+          double n_total = (double)P;
+          if (sync) {
+            CK(ctx, cudaMemcpyAsync(net->bn_sums_total, net->bn_sums, 2 * C * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+            if (int rc = nccl_allreduce(ctx, net->bn_sums_total, 2 * C, ncclDouble, ctx->stream)) return rc;
+            tot = net->bn_sums_total;
+            n_total *= ctx->world();
+          }
+          k_bn_bwd_apply(st, g, inp + off, g, P, C, net->params + m.p_off, smean, sinv, tot, n_total);
         }
-        k_bn_bwd_apply(st, g, inp, g, P, C, net->params + m.p_off, m.save_mean, m.save_invstd, tot, n_total);
-        cur = g;
+        cur = gall;
         break;
       }
       case DCGANSR_RELU: case DCGANSR_LRELU: case DCGANSR_TANH: case DCGANSR_SIGMOID:
         if (!m.fused_into_prev) {
           float* t = net->own(cur);
-          k_act_bwd(st, m.out, cur, t, (int64_t)B * m.cin * m.hin * m.win, m.act, m.L.negval);
+          k_act_bwd(st, mout, cur, t, (int64_t)NB * m.cin * m.hin * m.win, m.act, m.L.negval);
           cur = t;
         }
         break;
@@ -899,7 +917,7 @@ int dcgansr_net_create(dcgansr_ctx* ctx, const dcgansr_layer* layers, int n_laye
   auto A = [&](float** p, int64_t n) { if (e == cudaSuccess) e = dalloc(p, n); };
   A(&net->params, np4); A(&net->grads, np4); A(&net->adam_m, np4); A(&net->adam_v, np4);
   A(&net->adam_step, 4);
-  A(&net->bn_rmean, net->nbn); A(&net->bn_rvar, net->nbn); A(&net->bn_save, 2 * net->nbn);
+  A(&net->bn_rmean, net->nbn); A(&net->bn_rvar, net->nbn); A(&net->bn_save, 4 * net->nbn);          // (mean, invstd) x 2 sample groups
   if (e == cudaSuccess) e = cudaMalloc((void**)&net->adam_t, sizeof(int64_t));
   if (e == cudaSuccess) e = cudaMemset(net->adam_t, 0, sizeof(int64_t));
   int64_t B = max_batch;
@@ -916,7 +934,7 @@ int dcgansr_net_create(dcgansr_ctx* ctx, const dcgansr_layer* layers, int n_laye
     if (m.kind == DCGANSR_BN) {
       maxC = std::max(maxC, m.cin);
       maxP = std::max(maxP, B * m.hin * m.win);
-      m.save_mean = net->bn_save + m.bn_off;
+      m.save_mean = net->bn_save + m.bn_off;                      // group g: + g * 2 * nbn
       m.save_invstd = net->bn_save + net->nbn + m.bn_off;
     }
     if (m.conv) {
@@ -1116,29 +1134,56 @@ static int step_body(dcgansr_ctx* ctx, dcgansr_net* G, dcgansr_net* D, const dcg
 
   // ---------------- fDx (train.lua:208-253) ----------------
   CK(ctx, cudaMemsetAsync(D->grads, 0, D->nparams * sizeof(float), ctx->stream));
-  if (int rc = net_forward_dev(D, real, B)) return rc;
-  k_loss(st, lossk, D->last_out, dcount, nullptr, per, cfg->real_label, n_total, ctx->d_losses + 0, D->gbuf[0]);
-  if (int rc = net_backward_dev(D, real, D->gbuf[0], B, true, false, &dxd)) return rc;
+  const bool paired = D->max_batch >= 2 * B && !getenv("DCGANSR_NO_PAIRED_D");
+  const float* fake = nullptr;
+  int fake_group = 0;
+  if (!paired) {
+    if (int rc = net_forward_dev(D, real, B)) return rc;
+    k_loss(st, lossk, D->last_out, dcount, nullptr, per, cfg->real_label, n_total, ctx->d_losses + 0, D->gbuf[0]);
+    if (int rc = net_backward_dev(D, real, D->gbuf[0], B, true, false, &dxd)) return rc;
 
-  k_avgpool2(st, real, ctx->lr_buf, B, D->in_h, D->in_w, D->in_c);                  // train.lua:225-230
-  if (int rc = net_forward_dev(G, ctx->lr_buf, B)) return rc;                       // :233-234
-  const float* fake = G->last_out;
-  const float* lvec = nullptr;
-  if (cfg->pixel_label) {                                                           // :237-239,245
-    k_pixel_mse(st, real, fake, ctx->label_vec, B, (int64_t)D->in_c * D->in_h * D->in_w, cfg->pixel_div);
-    lvec = ctx->label_vec;
+    k_avgpool2(st, real, ctx->lr_buf, B, D->in_h, D->in_w, D->in_c);                  // train.lua:225-230
+    if (int rc = net_forward_dev(G, ctx->lr_buf, B)) return rc;                       // :233-234
+    fake = G->last_out;
+    const float* lvec = nullptr;
+    if (cfg->pixel_label) {                                                           // :237-239,245
+      k_pixel_mse(st, real, fake, ctx->label_vec, B, (int64_t)D->in_c * D->in_h * D->in_w, cfg->pixel_div);
+      lvec = ctx->label_vec;
+    }
+    if (int rc = net_forward_dev(D, fake, B)) return rc;                              // :242-243
+    k_loss(st, lossk, D->last_out, dcount, lvec, per, cfg->fake_label, n_total, ctx->d_losses + 1, D->gbuf[0]);
+    if (int rc = net_backward_dev(D, fake, D->gbuf[0], B, true, false, &dxd)) return rc;
+  } else {
+    // D(real) and D(fake) as ONE pass over [real; fake] (D was created for >= 2B samples): the generator forward does not
+    // depend on D, so it moves first; convolutions then run once on 2B samples (these layers are latency / L2-bound at
+    // B samples), BatchNorm keeps per-minibatch statistics (groups = 2) and updates the running statistics real-then-fake,
+    // gradients accumulate over both halves exactly as the two reference backward calls do (train.lua:218-248).
+    k_avgpool2(st, real, ctx->lr_buf, B, D->in_h, D->in_w, D->in_c);
+    if (int rc = net_forward_dev(G, ctx->lr_buf, B)) return rc;
+    const int64_t isz = (int64_t)B * D->in_c * D->in_h * D->in_w;
+    if (real != D->in_buf) CK(ctx, cudaMemcpyAsync(D->in_buf, real, isz * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(D->in_buf + isz, G->last_out, isz * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    fake = D->in_buf + isz;
+    fake_group = 1;
+    const float* lvec = nullptr;
+    if (cfg->pixel_label) {
+      k_pixel_mse(st, D->in_buf, fake, ctx->label_vec, B, (int64_t)D->in_c * D->in_h * D->in_w, cfg->pixel_div);
+      lvec = ctx->label_vec;
+    }
+    if (int rc = net_forward_dev(D, D->in_buf, B, 2)) return rc;
+    k_loss(st, lossk, D->last_out, dcount, nullptr, per, cfg->real_label, n_total, ctx->d_losses + 0, D->gbuf[0]);
+    k_loss(st, lossk, D->last_out + dcount, dcount, lvec, per, cfg->fake_label, n_total, ctx->d_losses + 1, D->gbuf[0] + dcount);
+    if (int rc = net_backward_dev(D, D->in_buf, D->gbuf[0], B, true, false, &dxd, 2, 0)) return rc;
   }
-  if (int rc = net_forward_dev(D, fake, B)) return rc;                              // :242-243
-  k_loss(st, lossk, D->last_out, dcount, lvec, per, cfg->fake_label, n_total, ctx->d_losses + 1, D->gbuf[0]);
-  if (int rc = net_backward_dev(D, fake, D->gbuf[0], B, true, false, &dxd)) return rc;
   if (int rc = allreduce_grads(ctx, D)) return rc;
   if (int rc = net_adam_dev(D, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps)) return rc;   // optim.adam(fDx) :280
 
   // ---------------- fGx (train.lua:256-272) ----------------
   CK(ctx, cudaMemsetAsync(G->grads, 0, G->nparams * sizeof(float), ctx->stream));
   // stale netD.output (pre-Adam forward on fake), post-Adam weights in the dgrad walk
-  k_loss(st, lossk, D->last_out, dcount, nullptr, per, cfg->gen_label, n_total, ctx->d_losses + 2, D->gbuf[0]);
-  if (int rc = net_backward_dev(D, fake, D->gbuf[0], B, false, true, &dxd)) return rc;  // netD:updateGradInput :268
+  const float* dout_fake = D->last_out + (int64_t)fake_group * dcount;
+  k_loss(st, lossk, dout_fake, dcount, nullptr, per, cfg->gen_label, n_total, ctx->d_losses + 2, D->gbuf[0]);
+  if (int rc = net_backward_dev(D, fake, D->gbuf[0], B, false, true, &dxd, 1, fake_group)) return rc;  // netD:updateGradInput :268
   const float* dummy = nullptr;
   if (int rc = net_backward_dev(G, ctx->lr_buf, dxd, B, true, false, &dummy)) return rc; // netG:backward :270
   if (int rc = allreduce_grads(ctx, G)) return rc;

@@ -88,8 +88,8 @@ __device__ __forceinline__ float act_grad(float y, float dy, int act, float neg)
   }
 }
 
-__global__ void act_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t count, int act, float neg) {
-  int64_t n4 = count >> 2;
+__global__ void act_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t count, int act, float neg, int vec) {
+  int64_t n4 = vec ? count >> 2 : 0;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const float4* x4 = reinterpret_cast<const float4*>(x);
@@ -104,8 +104,8 @@ __global__ void act_kernel(const float* __restrict__ x, float* __restrict__ y, i
 }
 
 __global__ void act_bwd_kernel(const float* __restrict__ y, const float* __restrict__ dy, float* __restrict__ dx,
-                               int64_t count, int act, float neg) {
-  int64_t n4 = count >> 2;
+                               int64_t count, int act, float neg, int vec) {
+  int64_t n4 = vec ? count >> 2 : 0;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const float4* y4 = reinterpret_cast<const float4*>(y);
@@ -129,12 +129,15 @@ static inline int ew_grid(int64_t count) {
 
 void k_act(St st, const float* x, float* y, int64_t count, int act, float negval) {
   if (count <= 0) return;
-  act_kernel<<<ew_grid(count), 256, 0, st.s>>>(x, y, count, act, negval);
+  // float4 path only for 16-byte aligned tensors (a sample-group offset into a 1-channel tensor is not)
+  const int vec = (((uintptr_t)x | (uintptr_t)y) & 15) == 0;
+  act_kernel<<<ew_grid(count), 256, 0, st.s>>>(x, y, count, act, negval, vec);
   DSR_LAUNCHED(st, "act", 8.0 * count, WORK_BYTES);
 }
 void k_act_bwd(St st, const float* y, const float* dy, float* dx, int64_t count, int act, float negval) {
   if (count <= 0) return;
-  act_bwd_kernel<<<ew_grid(count), 256, 0, st.s>>>(y, dy, dx, count, act, negval);
+  const int vec = (((uintptr_t)y | (uintptr_t)dy | (uintptr_t)dx) & 15) == 0;
+  act_bwd_kernel<<<ew_grid(count), 256, 0, st.s>>>(y, dy, dx, count, act, negval, vec);
   DSR_LAUNCHED(st, "act_bwd", 12.0 * count, WORK_BYTES);
 }
 

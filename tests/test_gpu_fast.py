@@ -156,7 +156,7 @@ def test_fast_step_losses_close_to_oracle(ctx_fast):
     with tf32_oracle(trunc_tf32):
         _, _, eerr, etrace = oracle_step()
     G = dsr.Sequential.from_specs(case["G"]).cuda(ctx_fast, (1, 32, 32), 4)
-    D = dsr.Sequential.from_specs(case["D"]).cuda(ctx_fast, (1, 64, 64), 4)
+    D = dsr.Sequential.from_specs(case["D"]).cuda(ctx_fast, (1, 64, 64), 8)      # 2B: paired D(real)+D(fake) pass
     G.set_params(oracle_net(case["G"], 4321).get_flat_params().numpy().astype(np.float32))
     D.set_params(oracle_net(case["D"], 8765).get_flat_params().numpy().astype(np.float32))
     err = dsr.train_step(ctx_fast, G, D, dsr.make_step_cfg(**case["step"]), real)

@@ -84,11 +84,12 @@ STEP_CASES = {
 }
 
 
-def _build(ctx, case, use_oracle_dtype=torch.float64):
+def _build(ctx, case, use_oracle_dtype=torch.float64, paired=False):
+    """paired: create D for 2B samples, which makes the fused step run D(real) and D(fake) as ONE grouped pass."""
     nc, hr, B = case["nc"], case["hr"], case["batch"]
     oG, oD = oracle_net(case["G"], 4321, use_oracle_dtype), oracle_net(case["D"], 8765, use_oracle_dtype)
     G = dsr.Sequential.from_specs(case["G"]).cuda(ctx, (nc, hr // 2, hr // 2), B)
-    D = dsr.Sequential.from_specs(case["D"]).cuda(ctx, (nc, hr, hr), B)
+    D = dsr.Sequential.from_specs(case["D"]).cuda(ctx, (nc, hr, hr), 2 * B if paired else B)
     G.set_params(oG.get_flat_params().numpy().astype(np.float32))
     D.set_params(oD.get_flat_params().numpy().astype(np.float32))
     return oG, oD, G, D
@@ -99,8 +100,9 @@ def _sync_from_oracle(net, onet, st):
     net.set_adam_state(st.m.numpy().astype(np.float32), st.v.numpy().astype(np.float32), st.t)
 
 
+@pytest.mark.parametrize("paired", [False, True])
 @pytest.mark.parametrize("name", sorted(STEP_CASES))
-def test_train_step_parity(ctx, name):
+def test_train_step_parity(ctx, name, paired):
     """Every step starts from the oracle's exact state (parameters + Adam moments), so each iteration is an
     independent single-step parity check at t = 1..4 (bias correction, accumulated moments).
 
@@ -110,7 +112,7 @@ def test_train_step_parity(ctx, name):
     in at least 3 of the 4 iterations; the remaining one must still be within a 5e-2 sanity bound.  Execution is
     deterministic, so this is not a flaky allowance."""
     case = STEP_CASES[name]
-    oG, oD, G, D = _build(ctx, case)
+    oG, oD, G, D = _build(ctx, case, paired=paired)
     B, nc, hr = case["batch"], case["nc"], case["hr"]
     ocfg = ostep_cfg(case["step"])
     cfg = dsr.make_step_cfg(**case["step"])
@@ -132,6 +134,11 @@ def test_train_step_parity(ctx, name):
         m, v, t = D.get_adam_state()
         eM = rel_err(m, stD.m.numpy())
         assert t == it + 1
+        if D.num_bn_channels():
+            rm, rv = D.get_bn_running()
+            orm = torch.cat([m.running_mean for m in oD.bn_modules()]).numpy()
+            orv = torch.cat([m.running_var for m in oD.bn_modules()]).numpy()
+            assert rel_err(rm, orm) <= 1e-4 and rel_err(rv, orv) <= 1e-4, (name, it, "BN running statistics")
         report.append((it, eD, eG, pD, pG, eM))
         assert max(eD, eG) <= 5e-2 and max(pD, pG) <= 1e-3, (name, report)
         strict_ok += (max(eD, eG, eM) <= 5 * STRICT_TOL and max(pD, pG) <= STRICT_TOL)
@@ -196,7 +203,7 @@ def test_staged_and_graph_step_match_host_step(ctx):
 
 
 def _trajectory(ctx, case, steps):
-    oG, oD, G, D = _build(ctx, case, torch.float32)
+    oG, oD, G, D = _build(ctx, case, torch.float32, paired=True)
     B, nc, hr = case["batch"], case["nc"], case["hr"]
     ocfg = ostep_cfg(case["step"])
     cfg = dsr.make_step_cfg(**case["step"])
