@@ -34,7 +34,7 @@ netD:add(nn.SpatialConvolution(ndf * 4, ndf * 8, 4, 4, 2, 2, 1, 1)):add(nn.Spati
 netD:add(nn.SpatialConvolution(ndf * 8, 1, 4, 4)):add(nn.Sigmoid()):add(nn.View(1):setNumInputDims(3))
 
 netG:cuda(ctx, {nc, opt.fineSize / 2, opt.fineSize / 2}, opt.batchSize)      -- replaces :cuda() / cudnn.convert (:168-180)
-netD:cuda(ctx, {nc, opt.fineSize, opt.fineSize}, opt.batchSize)
+netD:cuda(ctx, {nc, opt.fineSize, opt.fineSize}, 2 * opt.batchSize)              -- 2B samples: D(real) and D(fake) run as one grouped pass
 dsr.weights_init(netG); dsr.weights_init(netD)                               -- netG:apply(weights_init) (:42-51)
 
 -- criterion = nn.MSECriterion(); labels .001 / per-sample pixel MSE / 0  (train-gray.lua:140,232,265,282)
