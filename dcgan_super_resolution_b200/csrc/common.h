@@ -100,6 +100,13 @@ void k_bn_bwd_reduce(St st, const float* dy, const float* y, const float* x, flo
 void k_bn_bwd_param(St st, const double* sums_local, int C, float* dgamma, float* dbeta);
 void k_bn_bwd_apply(St st, const float* g, const float* x, float* dx, int64_t P, int C, const float* gamma,
                     const float* mean, const float* invstd, const double* sums_total, double n_total);
+// grouped + fused BatchNorm of the training step (no cross-rank statistics): see kernels_bw.cu
+void k_bn_fwd_grouped(St st, const float* x, float* y, int64_t P, int C, int groups, const float* gamma, const float* beta,
+                      float* save_mean, float* save_invstd, int64_t sstride, float* running_mean, float* running_var, float eps,
+                      float momentum, int act, float negval, double* partials);
+void k_bn_bwd_grouped(St st, const float* dy, const float* y, const float* x, float* dx, int64_t P, int C, int groups,
+                      const float* gamma, const float* save_mean, const float* save_invstd, int64_t sstride, int act, float negval,
+                      double* partials, double* sums, float* dgamma, float* dbeta);
 void k_upnearest_fwd(St st, const float* x, float* y, int N, int H, int W, int C, int scale);
 void k_upnearest_bwd(St st, const float* dy, float* dx, int N, int H, int W, int C, int scale);
 void k_avgpool2(St st, const float* x, float* y, int N, int H, int W, int C);

@@ -495,6 +495,13 @@ static int net_forward_dev(dcgansr_net* net, const float* in, int B, int groups 
       case DCGANSR_BN: {
         int64_t P = (int64_t)B * m.hin * m.win;
         int C = m.cin;
+        if (!sync) {
+          k_bn_fwd_grouped(st, cur, m.out, P, C, groups, net->params + m.p_off, net->params + m.p_off + C, m.save_mean, m.save_invstd,
+                           2 * net->nbn, net->bn_rmean + m.bn_off, net->bn_rvar + m.bn_off, m.L.eps, m.L.momentum, m.fused_act, m.fused_neg,
+                           net->bn_partials);
+          cur = m.out;
+          break;
+        }
         for (int g = 0; g < groups; ++g) {
           const float* xg = cur + (int64_t)g * P * C;
           float* smean = m.save_mean + (int64_t)g * 2 * net->nbn;
@@ -568,6 +575,14 @@ static int net_backward_dev(dcgansr_net* net, const float* in, const float* dy, 
         int64_t P = (int64_t)B * m.hin * m.win;
         int C = m.cin;
         float* gall = net->own(cur);
+        if (!sync) {
+          k_bn_bwd_grouped(st, cur, m.fused_act != ACT_NONE ? mout : nullptr, inp, gall, P, C, groups, net->params + m.p_off,
+                           m.save_mean + (int64_t)goff * 2 * net->nbn, m.save_invstd + (int64_t)goff * 2 * net->nbn, 2 * net->nbn,
+                           m.fused_act, m.fused_neg, net->bn_partials, net->bn_sums, acc ? net->grads + m.p_off : nullptr,
+                           acc ? net->grads + m.p_off + C : nullptr);
+          cur = gall;
+          break;
+        }
         for (int gi = 0; gi < groups; ++gi) {
           const int64_t off = (int64_t)gi * P * C;
           const float* smean = m.save_mean + (int64_t)(goff + gi) * 2 * net->nbn;
@@ -955,8 +970,8 @@ int dcgansr_net_create(dcgansr_ctx* ctx, const dcgansr_layer* layers, int n_laye
     for (auto& m : net->mods)
       if (m.kind == DCGANSR_BN) rows = std::max<int64_t>(rows, (int64_t)bn_partial_rows(B * m.hin * m.win, m.cin) * 2 * m.cin);
     float* tmpf = nullptr;
-    A(&tmpf, std::max<int64_t>(rows, 2) * 2); net->bn_partials = (double*)tmpf; tmpf = nullptr;
-    A(&tmpf, (int64_t)maxC * 4 + 4); net->bn_sums = (double*)tmpf; tmpf = nullptr;
+    A(&tmpf, std::max<int64_t>(rows, 2) * 2 * 2); net->bn_partials = (double*)tmpf; tmpf = nullptr;     // x 2 sample groups
+    A(&tmpf, (int64_t)maxC * 4 * 2 + 4); net->bn_sums = (double*)tmpf; tmpf = nullptr;
     A(&tmpf, (int64_t)maxC * 4 + 4); net->bn_sums_total = (double*)tmpf;
   }
   net->wscratch_bytes = wsc;
@@ -971,7 +986,7 @@ int dcgansr_net_create(dcgansr_ctx* ctx, const dcgansr_layer* layers, int n_laye
     int64_t total = 0;
     for (auto& m : net->mods)
       if (m.conv) m.conv->collect_jobs(jobs, net->params + m.p_off, total);
-    if (!jobs.empty()) {
+    if (!jobs.empty() && jobs.size() <= 128) {
       PackJob sentinel = jobs.back();
       sentinel.begin = total;
       jobs.push_back(sentinel);

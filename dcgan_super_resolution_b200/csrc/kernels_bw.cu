@@ -200,9 +200,10 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
                                                        int64_t ppb, double* __restrict__ partials) {
   int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   int CV = C / VEC;
+  x += (int64_t)blockIdx.y * P * C;                               // sample group
   int64_t p0 = (int64_t)blockIdx.x * ppb;
   int64_t p1 = p0 + ppb < P ? p0 + ppb : P;
-  double* prow = partials + (int64_t)blockIdx.x * 2 * C;
+  double* prow = partials + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C;
   for (int cv0 = 0; cv0 < CV; cv0 += TX) {
     int cv = cv0 + tx;
     double a[2 * VEC];
@@ -282,7 +283,9 @@ template <int VEC>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t total_v, int CV,
                                                        const float* __restrict__ gamma, const float* __restrict__ beta,
                                                        const float* __restrict__ mean, const float* __restrict__ invstd,
-                                                       int act, float neg) {
+                                                       int act, float neg, int64_t sstride) {
+  x += (int64_t)blockIdx.y * total_v * VEC; y += (int64_t)blockIdx.y * total_v * VEC;      // sample group
+  mean += (int64_t)blockIdx.y * sstride; invstd += (int64_t)blockIdx.y * sstride;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_v; i += stride) {
     int cv = (int)(i % CV);
@@ -308,26 +311,32 @@ void k_bn_apply_act(St st, const float* x, float* y, int64_t P, int C, const flo
                     const float* mean, const float* invstd, int act, float negval) {
   if (C % 4 == 0) {
     int64_t tv = P * (C / 4);
-    bn_apply_kernel<4><<<ew_grid(tv * 4), 256, 0, st.s>>>(x, y, tv, C / 4, gamma, beta, mean, invstd, act, negval);
+    bn_apply_kernel<4><<<ew_grid(tv * 4), 256, 0, st.s>>>(x, y, tv, C / 4, gamma, beta, mean, invstd, act, negval, 0);
   } else {
     int64_t tv = P * C;
-    bn_apply_kernel<1><<<ew_grid(tv * 4), 256, 0, st.s>>>(x, y, tv, C, gamma, beta, mean, invstd, act, negval);
+    bn_apply_kernel<1><<<ew_grid(tv * 4), 256, 0, st.s>>>(x, y, tv, C, gamma, beta, mean, invstd, act, negval, 0);
   }
   DSR_LAUNCHED(st, "bn_apply_act", 8.0 * P * C, WORK_BYTES);
 }
 
 // backward reductions: g = dy * act'(y) ; sum g, sum g * xhat
 template <int VEC>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ y,
-                                                            const float* __restrict__ x, float* __restrict__ g_out, int64_t P,
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* dy, const float* __restrict__ y,
+                                                            const float* __restrict__ x, float* g_out /* may alias dy */, int64_t P,
                                                             int C, int TX, int TY, int64_t ppb, const float* __restrict__ mean,
                                                             const float* __restrict__ invstd, int act, float neg,
-                                                            double* __restrict__ partials) {
+                                                            double* __restrict__ partials, int64_t sstride) {
   int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   int CV = C / VEC;
+  {
+    const int64_t go = (int64_t)blockIdx.y * P * C;               // sample group
+    dy += go; x += go; g_out += go;
+    if (y) y += go;
+    mean += (int64_t)blockIdx.y * sstride; invstd += (int64_t)blockIdx.y * sstride;
+  }
   int64_t p0 = (int64_t)blockIdx.x * ppb;
   int64_t p1 = p0 + ppb < P ? p0 + ppb : P;
-  double* prow = partials + (int64_t)blockIdx.x * 2 * C;
+  double* prow = partials + ((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * 2 * C;
   for (int cv0 = 0; cv0 < CV; cv0 += TX) {
     int cv = cv0 + tx;
     double a[2 * VEC];
@@ -375,9 +384,9 @@ void k_bn_bwd_reduce(St st, const float* dy, const float* y, const float* x, flo
                      const float* mean, const float* invstd, int act, float negval, double* partials, double* sums) {
   BnCfg c = bn_cfg(P, C);
   if (c.vec == 4)
-    bn_bwd_reduce_kernel<4><<<c.nb, 256, 0, st.s>>>(dy, y, x, g_out, P, C, c.TX, c.TY, c.ppb, mean, invstd, act, negval, partials);
+    bn_bwd_reduce_kernel<4><<<c.nb, 256, 0, st.s>>>(dy, y, x, g_out, P, C, c.TX, c.TY, c.ppb, mean, invstd, act, negval, partials, 0);
   else
-    bn_bwd_reduce_kernel<1><<<c.nb, 256, 0, st.s>>>(dy, y, x, g_out, P, C, c.TX, c.TY, c.ppb, mean, invstd, act, negval, partials);
+    bn_bwd_reduce_kernel<1><<<c.nb, 256, 0, st.s>>>(dy, y, x, g_out, P, C, c.TX, c.TY, c.ppb, mean, invstd, act, negval, partials, 0);
   DSR_LAUNCHED(st, "bn_bwd_reduce", (act != ACT_NONE ? 16.0 : 12.0) * P * C, WORK_BYTES);
   colsum_kernel<<<(2 * C + 31) / 32, dim3(32, 8), 0, st.s>>>(partials, c.nb, 2 * C, sums);
   DSR_LAUNCHED(st, "bn_colsum", 16.0 * c.nb * C, WORK_BYTES);
@@ -396,11 +405,13 @@ void k_bn_bwd_param(St st, const double* sums_local, int C, float* dgamma, float
 
 // dx = (g - sum_g/n - xhat * sum_gxhat/n) * gamma * invstd      (in place on g allowed)
 template <int VEC>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restrict__ g, const float* __restrict__ x,
-                                                           float* __restrict__ dx, int64_t total_v, int CV, int C,
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* g, const float* __restrict__ x,
+                                                           float* dx /* may alias g (in place) */, int64_t total_v, int CV, int C,
                                                            const float* __restrict__ gamma, const float* __restrict__ mean,
                                                            const float* __restrict__ invstd, const double* __restrict__ sums,
-                                                           double n_total) {
+                                                           double n_total, int64_t sstride) {
+  g += (int64_t)blockIdx.y * total_v * VEC; x += (int64_t)blockIdx.y * total_v * VEC; dx += (int64_t)blockIdx.y * total_v * VEC;
+  mean += (int64_t)blockIdx.y * sstride; invstd += (int64_t)blockIdx.y * sstride; sums += (int64_t)blockIdx.y * 2 * C;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_v; i += stride) {
     int cv = (int)(i % CV);
@@ -433,12 +444,120 @@ void k_bn_bwd_apply(St st, const float* g, const float* x, float* dx, int64_t P,
                     const float* mean, const float* invstd, const double* sums_total, double n_total) {
   if (C % 4 == 0) {
     int64_t tv = P * (C / 4);
-    bn_bwd_apply_kernel<4><<<ew_grid(tv * 4), 256, 0, st.s>>>(g, x, dx, tv, C / 4, C, gamma, mean, invstd, sums_total, n_total);
+    bn_bwd_apply_kernel<4><<<ew_grid(tv * 4), 256, 0, st.s>>>(g, x, dx, tv, C / 4, C, gamma, mean, invstd, sums_total, n_total, 0);
   } else {
     int64_t tv = P * C;
-    bn_bwd_apply_kernel<1><<<ew_grid(tv * 4), 256, 0, st.s>>>(g, x, dx, tv, C, C, gamma, mean, invstd, sums_total, n_total);
+    bn_bwd_apply_kernel<1><<<ew_grid(tv * 4), 256, 0, st.s>>>(g, x, dx, tv, C, C, gamma, mean, invstd, sums_total, n_total, 0);
   }
   DSR_LAUNCHED(st, "bn_bwd_apply", 12.0 * P * C, WORK_BYTES);
+}
+
+// ------------------------------------------------------------------------------------------
+// Grouped, fused BatchNorm (the fused training step; no cross-rank statistics): `groups` independent minibatches of P
+// pixels each sit back to back in x.  Forward = 3 launches for all groups (partials, column sums + finalize, apply),
+// backward = 3 (reduce, column sums + parameter gradients, apply) instead of 4 per group.  All sums in fixed order.
+// ------------------------------------------------------------------------------------------
+__global__ void bn_fwd_tail_kernel(const double* __restrict__ partials, int nb, int C, int groups, double n_total, float eps,
+                                   float momentum, float* __restrict__ save_mean, float* __restrict__ save_invstd, int64_t sstride,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var) {
+  __shared__ double red[2][8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  for (int g = 0; g < groups; ++g) {                    // sequential: the running statistics see group 0 first
+    const double* pg = partials + (int64_t)g * nb * 2 * C;
+    double a1 = 0.0, a2 = 0.0;
+    if (c < C)
+      for (int b = threadIdx.y; b < nb; b += 8) { a1 += pg[(int64_t)b * 2 * C + c]; a2 += pg[(int64_t)b * 2 * C + C + c]; }
+    red[0][threadIdx.y][threadIdx.x] = a1;
+    red[1][threadIdx.y][threadIdx.x] = a2;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+      double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) { s1 += red[0][r][threadIdx.x]; s2 += red[1][r][threadIdx.x]; }
+      double mean = s1 / n_total;
+      double var = s2 / n_total - mean * mean;
+      if (var < 0.0) var = 0.0;
+      double invstd = 1.0 / sqrt(var + (double)eps);
+      save_mean[(int64_t)g * sstride + c] = (float)mean;
+      save_invstd[(int64_t)g * sstride + c] = (float)invstd;
+      if (running_mean) {
+        double unb = n_total > 1.0 ? var * (n_total / (n_total - 1.0)) : var;
+        running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * mean);
+        running_var[c] = (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * unb);
+      }
+    }
+    __syncthreads();
+  }
+}
+
+void k_bn_fwd_grouped(St st, const float* x, float* y, int64_t P, int C, int groups, const float* gamma, const float* beta,
+                      float* save_mean, float* save_invstd, int64_t sstride, float* running_mean, float* running_var, float eps,
+                      float momentum, int act, float negval, double* partials) {
+  BnCfg c = bn_cfg(P, C);
+  dim3 grid(c.nb, groups);
+  if (c.vec == 4) bn_stats_kernel<4><<<grid, 256, 0, st.s>>>(x, P, C, c.TX, c.TY, c.ppb, partials);
+  else bn_stats_kernel<1><<<grid, 256, 0, st.s>>>(x, P, C, c.TX, c.TY, c.ppb, partials);
+  DSR_LAUNCHED(st, "bn_stats", 4.0 * P * C * groups, WORK_BYTES);
+  bn_fwd_tail_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st.s>>>(partials, c.nb, C, groups, (double)P, eps, momentum, save_mean, save_invstd,
+                                                               sstride, running_mean, running_var);
+  DSR_LAUNCHED(st, "bn_fwd_tail", 16.0 * c.nb * C * groups, WORK_BYTES);
+  if (C % 4 == 0) {
+    int64_t tv = P * (C / 4);
+    bn_apply_kernel<4><<<dim3(ew_grid(tv * 4), groups), 256, 0, st.s>>>(x, y, tv, C / 4, gamma, beta, save_mean, save_invstd, act, negval, sstride);
+  } else {
+    int64_t tv = P * C;
+    bn_apply_kernel<1><<<dim3(ew_grid(tv * 4), groups), 256, 0, st.s>>>(x, y, tv, C, gamma, beta, save_mean, save_invstd, act, negval, sstride);
+  }
+  DSR_LAUNCHED(st, "bn_apply_act", 8.0 * P * C * groups, WORK_BYTES);
+}
+
+// sums[g][2C] = column sums of group g's partial rows; dbeta += sum_g sums[g][c], dgamma += sum_g sums[g][C + c]
+__global__ void bn_bwd_tail_kernel(const double* __restrict__ partials, int nb, int C, int groups, double* __restrict__ sums,
+                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+  __shared__ double red[2][8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  for (int g = 0; g < groups; ++g) {
+    const double* pg = partials + (int64_t)g * nb * 2 * C;
+    double a1 = 0.0, a2 = 0.0;
+    if (c < C)
+      for (int b = threadIdx.y; b < nb; b += 8) { a1 += pg[(int64_t)b * 2 * C + c]; a2 += pg[(int64_t)b * 2 * C + C + c]; }
+    red[0][threadIdx.y][threadIdx.x] = a1;
+    red[1][threadIdx.y][threadIdx.x] = a2;
+    __syncthreads();
+    if (threadIdx.y == 0 && c < C) {
+      double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+      for (int r = 0; r < 8; ++r) { s1 += red[0][r][threadIdx.x]; s2 += red[1][r][threadIdx.x]; }
+      sums[(int64_t)g * 2 * C + c] = s1;
+      sums[(int64_t)g * 2 * C + C + c] = s2;
+      // the reference accumulates group after group in fp32 (two backward calls): same order here
+      if (dbeta) dbeta[c] += (float)s1;
+      if (dgamma) dgamma[c] += (float)s2;
+    }
+    __syncthreads();
+  }
+}
+
+void k_bn_bwd_grouped(St st, const float* dy, const float* y, const float* x, float* dx, int64_t P, int C, int groups,
+                      const float* gamma, const float* save_mean, const float* save_invstd, int64_t sstride, int act, float negval,
+                      double* partials, double* sums, float* dgamma, float* dbeta) {
+  BnCfg c = bn_cfg(P, C);
+  dim3 grid(c.nb, groups);
+  if (c.vec == 4)
+    bn_bwd_reduce_kernel<4><<<grid, 256, 0, st.s>>>(dy, y, x, dx, P, C, c.TX, c.TY, c.ppb, save_mean, save_invstd, act, negval, partials, sstride);
+  else
+    bn_bwd_reduce_kernel<1><<<grid, 256, 0, st.s>>>(dy, y, x, dx, P, C, c.TX, c.TY, c.ppb, save_mean, save_invstd, act, negval, partials, sstride);
+  DSR_LAUNCHED(st, "bn_bwd_reduce", (act != ACT_NONE ? 16.0 : 12.0) * P * C * groups, WORK_BYTES);
+  bn_bwd_tail_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st.s>>>(partials, c.nb, C, groups, sums, dgamma, dbeta);
+  DSR_LAUNCHED(st, "bn_bwd_tail", 16.0 * c.nb * C * groups, WORK_BYTES);
+  if (C % 4 == 0) {
+    int64_t tv = P * (C / 4);
+    bn_bwd_apply_kernel<4><<<dim3(ew_grid(tv * 4), groups), 256, 0, st.s>>>(dx, x, dx, tv, C / 4, C, gamma, save_mean, save_invstd, sums, (double)P, sstride);
+  } else {
+    int64_t tv = P * C;
+    bn_bwd_apply_kernel<1><<<dim3(ew_grid(tv * 4), groups), 256, 0, st.s>>>(dx, x, dx, tv, C, C, gamma, save_mean, save_invstd, sums, (double)P, sstride);
+  }
+  DSR_LAUNCHED(st, "bn_bwd_apply", 12.0 * P * C * groups, WORK_BYTES);
 }
 
 // ------------------------------------------------------------------------------------------

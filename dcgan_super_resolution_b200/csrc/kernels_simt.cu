@@ -42,16 +42,20 @@ void k_pack_taps(St st, const float* master, float* wp, int ntaps, const int* ta
 // ------------------------------------------------------------------------------------------
 // all weight packs of a net in ONE launch (after every Adam step): jobs[j] covers flat elements [begin_j, begin_{j+1})
 // ------------------------------------------------------------------------------------------
+#define PACK_MAXJOBS 128
 __global__ void pack_all_kernel(const PackJob* __restrict__ jobs, int njobs, int64_t total) {
+  __shared__ int64_t sbeg[PACK_MAXJOBS + 1];
+  for (int i = threadIdx.x; i <= njobs && i <= PACK_MAXJOBS; i += blockDim.x) sbeg[i] = jobs[i].begin;     // jobs[njobs] = sentinel
+  __syncthreads();
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     int lo = 0, hi = njobs - 1;
     while (lo < hi) {                       // last job with begin <= i
       int mid = (lo + hi + 1) >> 1;
-      if (jobs[mid].begin <= i) lo = mid; else hi = mid - 1;
+      if (sbeg[mid] <= i) lo = mid; else hi = mid - 1;
     }
     const PackJob& j = jobs[lo];
-    const int64_t l = i - j.begin;
+    const int64_t l = i - sbeg[lo];
     if (j.tc) {                             // K-major tensor-core pack bp[b][t*A + a], TF32-rounded
       int a = (int)(l % j.A);
       int64_t r = l / j.A;
@@ -71,7 +75,7 @@ __global__ void pack_all_kernel(const PackJob* __restrict__ jobs, int njobs, int
   }
 }
 void k_pack_all(St st, const PackJob* jobs_dev, int njobs, int64_t total) {
-  if (njobs <= 0 || total <= 0) return;
+  if (njobs <= 0 || total <= 0 || njobs > PACK_MAXJOBS) return;
   int64_t blocks = (total + 255) / 256;
   if (blocks > NSM * 8) blocks = NSM * 8;
   pack_all_kernel<<<(int)blocks, 256, 0, st.s>>>(jobs_dev, njobs, total);

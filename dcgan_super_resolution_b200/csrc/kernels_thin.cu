@@ -213,7 +213,7 @@ bool k_wgrad_thin(St st, const WgradGeom& g, const float* P, const float* Q, flo
     thin_wgrad_kernel<CT, MP><<<grid, 256, 0, st.s>>>(w, fat, thin, scratch);   \
   } while (0)
   switch (w.Ct) {
-    case 1: if (maxp <= 4) THIN_LAUNCH(1, 4); else THIN_LAUNCH(1, 16); break;
+    case 1: if (maxp <= 4 || !getenv("DCGANSR_THIN16")) THIN_LAUNCH(1, 4); else THIN_LAUNCH(1, 16); break;
     case 2: if (maxp <= 4) THIN_LAUNCH(2, 4); else THIN_LAUNCH(2, 8); break;
     case 3: THIN_LAUNCH(3, 4); break;
     default: THIN_LAUNCH(4, 4); break;
