@@ -74,6 +74,8 @@ struct dcgansr_ctx {
   std::vector<GraphEntry> graphs;
   bool tc_failed = false;
   cudaEvent_t graph_ev[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> bucket_ev;      // one per gradient bucket in flight (main -> comm stream hand-over)
+  int buckets_in_flight = 0;               // all-reduces issued on comm_stream and not yet joined
   uint64_t graph_seq = 0;
   Prof prof;
   TcWorkspace tcws;
@@ -411,6 +413,7 @@ struct Mod {
   ConvPlan* conv = nullptr;
   int64_t p_off = -1, p_cnt = 0;
   int64_t bn_off = -1;
+  int bucket = -1;               // conv modules: index of the gradient bucket [this conv, following BN ...)
   float* out = nullptr;
   bool owns_out = false;
   int fused_act = ACT_NONE;      // activation fused into this CONV / BN module
@@ -534,12 +537,38 @@ static int net_forward_dev(dcgansr_net* net, const float* in, int B, int groups 
   return 0;
 }
 
+// Gradient buckets overlapped with the backward walk (data parallel): as soon as a convolution's wgrad (and the BatchNorm
+// that follows it in the net, already visited by the backward walk) has produced its slice of the flat gradient vector,
+// that slice is all-reduced on the communication stream while the main stream goes on with the next dgrad / wgrad.
+static int bucket_allreduce_async(dcgansr_ctx* ctx, dcgansr_net* net, int bucket) {
+  if (bucket < 0 || bucket >= (int)net->buckets.size() || net->buckets[bucket].second <= 0) return 0;
+  const int k = ctx->buckets_in_flight;
+  while ((int)ctx->bucket_ev.size() <= k) {
+    cudaEvent_t e;
+    CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->bucket_ev.push_back(e);
+  }
+  CK(ctx, cudaEventRecord(ctx->bucket_ev[k], ctx->stream));
+  CK(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->bucket_ev[k], 0));
+  if (int rc = nccl_allreduce(ctx, net->grads + net->buckets[bucket].first, net->buckets[bucket].second, ncclFloat, ctx->comm_stream)) return rc;
+  ++ctx->buckets_in_flight;
+  return 0;
+}
+// main stream waits for every bucket issued so far
+static int bucket_join(dcgansr_ctx* ctx) {
+  if (ctx->buckets_in_flight == 0) return 0;
+  CK(ctx, cudaEventRecord(ctx->ev_c2m, ctx->comm_stream));
+  CK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_c2m, 0));
+  ctx->buckets_in_flight = 0;
+  return 0;
+}
+
 // backward walk.  acc: accumulate parameter gradients (net:backward) or not (net:updateGradInput).
 // Returns the gradient w.r.t. the net input in *dx_out (nullptr when need_dx is false).
 // groups / goff: the cached activations hold several B-sample groups (see net_forward_dev); this walk covers groups
 // [goff, goff + groups): `in` and `dy` point at the first sample of group goff, cached module outputs are offset likewise.
 static int net_backward_dev(dcgansr_net* net, const float* in, const float* dy, int B, bool acc, bool need_dx,
-                            const float** dx_out, int groups = 1, int goff = 0) {
+                            const float** dx_out, int groups = 1, int goff = 0, bool reduce_buckets = false) {
   dcgansr_ctx* ctx = net->ctx;
   St st = ctx->st();
   const bool sync = ctx->cfg.sync_bn && ctx->world() > 1;
@@ -565,6 +594,8 @@ static int net_backward_dev(dcgansr_net* net, const float* in, const float* dy, 
           cur = t;
         }
         if (acc) m.conv->wgrad_run(ctx, inp, cur, net->grads + m.p_off, NB, net->wscratch, net->wscratch_bytes);
+        if (acc && reduce_buckets && m.bucket >= 0)
+          if (int rc = bucket_allreduce_async(ctx, net, m.bucket)) return rc;
         if (i == net->first_param_mod && !need_dx) { CKLAST(ctx); return 0; }
         float* t = net->other(cur);
         m.conv->dgrad_run(ctx, cur, t, NB);
@@ -699,6 +730,7 @@ void dcgansr_ctx_destroy(dcgansr_ctx* ctx) {
   if (ctx->h_losses) cudaFreeHost(ctx->h_losses);
   for (cudaEvent_t e : ctx->prof.pool) cudaEventDestroy(e);
   for (cudaEvent_t e : ctx->graph_ev) if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : ctx->bucket_ev) cudaEventDestroy(e);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
   if (ctx->ev_c2m) cudaEventDestroy(ctx->ev_c2m);
@@ -910,13 +942,17 @@ int dcgansr_net_create(dcgansr_ctx* ctx, const dcgansr_layer* layers, int n_laye
   {
     int64_t start = 0;
     bool seen = false;
+    Mod* prev_conv = nullptr;
     for (auto& m : net->mods) {
       if (m.conv) {
-        if (seen) net->buckets.push_back({start, m.p_off - start});
-        start = m.p_off; seen = true;
+        if (seen) { prev_conv->bucket = (int)net->buckets.size(); net->buckets.push_back({start, m.p_off - start}); }
+        start = m.p_off; seen = true; prev_conv = &m;
       }
     }
-    if (net->nparams > start || !seen) net->buckets.push_back({start, net->nparams - start});
+    if (net->nparams > start || !seen) {
+      if (prev_conv) prev_conv->bucket = (int)net->buckets.size();
+      net->buckets.push_back({start, net->nparams - start});
+    }
   }
   if (!ctx) { *out = net; return 0; }
 
@@ -1125,9 +1161,14 @@ int dcgansr_net_adam(dcgansr_net* net, double lr, double beta1, double beta2, do
 }
 
 // ---- the fused step ---------------------------------------------------------------------------
-static int allreduce_grads(dcgansr_ctx* ctx, dcgansr_net* net) {
+static bool overlap_on(dcgansr_ctx* ctx) { return ctx->world() > 1 && !getenv("DCGANSR_NO_OVERLAP"); }
+
+// bucketed == true: the backward walk already issued every bucket on the communication stream -> just join
+static int allreduce_grads(dcgansr_ctx* ctx, dcgansr_net* net, bool bucketed = false) {
   if (ctx->world() <= 1) return 0;
-  if (int rc = nccl_allreduce(ctx, net->grads, net->nparams, ncclFloat, ctx->stream)) return rc;
+  if (bucketed) {
+    if (int rc = bucket_join(ctx)) return rc;
+  } else if (int rc = nccl_allreduce(ctx, net->grads, net->nparams, ncclFloat, ctx->stream)) return rc;
   if (!ctx->cfg.sync_bn && net->nbn > 0) {
     // running statistics averaged at the gradient exchange point (local batch statistics mode)
     if (int rc = nccl_allreduce(ctx, net->bn_rmean, net->nbn, ncclFloat, ctx->stream)) return rc;
@@ -1167,7 +1208,7 @@ static int step_body(dcgansr_ctx* ctx, dcgansr_net* G, dcgansr_net* D, const dcg
     }
     if (int rc = net_forward_dev(D, fake, B)) return rc;                              // :242-243
     k_loss(st, lossk, D->last_out, dcount, lvec, per, cfg->fake_label, n_total, ctx->d_losses + 1, D->gbuf[0]);
-    if (int rc = net_backward_dev(D, fake, D->gbuf[0], B, true, false, &dxd)) return rc;
+    if (int rc = net_backward_dev(D, fake, D->gbuf[0], B, true, false, &dxd, 1, 0, overlap_on(ctx))) return rc;      // second pass: grads final
   } else {
     // D(real) and D(fake) as ONE pass over [real; fake] (D was created for >= 2B samples): the generator forward does not
     // depend on D, so it moves first; convolutions then run once on 2B samples (these layers are latency / L2-bound at
@@ -1188,9 +1229,9 @@ static int step_body(dcgansr_ctx* ctx, dcgansr_net* G, dcgansr_net* D, const dcg
     if (int rc = net_forward_dev(D, D->in_buf, B, 2)) return rc;
     k_loss(st, lossk, D->last_out, dcount, nullptr, per, cfg->real_label, n_total, ctx->d_losses + 0, D->gbuf[0]);
     k_loss(st, lossk, D->last_out + dcount, dcount, lvec, per, cfg->fake_label, n_total, ctx->d_losses + 1, D->gbuf[0] + dcount);
-    if (int rc = net_backward_dev(D, D->in_buf, D->gbuf[0], B, true, false, &dxd, 2, 0)) return rc;
+    if (int rc = net_backward_dev(D, D->in_buf, D->gbuf[0], B, true, false, &dxd, 2, 0, overlap_on(ctx))) return rc;
   }
-  if (int rc = allreduce_grads(ctx, D)) return rc;
+  if (int rc = allreduce_grads(ctx, D, overlap_on(ctx))) return rc;
   if (int rc = net_adam_dev(D, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps)) return rc;   // optim.adam(fDx) :280
 
   // ---------------- fGx (train.lua:256-272) ----------------
@@ -1200,8 +1241,8 @@ static int step_body(dcgansr_ctx* ctx, dcgansr_net* G, dcgansr_net* D, const dcg
   k_loss(st, lossk, dout_fake, dcount, nullptr, per, cfg->gen_label, n_total, ctx->d_losses + 2, D->gbuf[0]);
   if (int rc = net_backward_dev(D, fake, D->gbuf[0], B, false, true, &dxd, 1, fake_group)) return rc;  // netD:updateGradInput :268
   const float* dummy = nullptr;
-  if (int rc = net_backward_dev(G, ctx->lr_buf, dxd, B, true, false, &dummy)) return rc; // netG:backward :270
-  if (int rc = allreduce_grads(ctx, G)) return rc;
+  if (int rc = net_backward_dev(G, ctx->lr_buf, dxd, B, true, false, &dummy, 1, 0, overlap_on(ctx))) return rc; // netG:backward :270
+  if (int rc = allreduce_grads(ctx, G, overlap_on(ctx))) return rc;
   if (int rc = net_adam_dev(G, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps)) return rc;   // optim.adam(fGx) :283
   if (world > 1)
     if (int rc = nccl_allreduce(ctx, ctx->d_losses, 3, ncclFloat, ctx->stream)) return rc;
@@ -1303,15 +1344,71 @@ int dcgansr_train_step(dcgansr_ctx* ctx, dcgansr_net* netG, dcgansr_net* netD, c
   if (int rc = upload_nchw(ctx, real_host, local_batch, netD->in_c, netD->in_h, netD->in_w, netD->in_buf)) return rc;
   return step_run(ctx, netG, netD, cfg, netD->in_buf, local_batch, out_losses);
 }
+#define NEED_CTX(ctx)                                                          \
+  if (!(ctx)) return fail(nullptr, DCGANSR_ERR_INVALID, "null ctx");            \
+  CK(ctx, cudaSetDevice((ctx)->cfg.device));
+
+// ---- patch extraction / re-assembly ----------------------------------------------------------
+static int patch_args_ok(dcgansr_ctx* ctx, int k, int h, int w, int patch, int line, int nper, int stride) {
+  if (k <= 0 || h <= 0 || w <= 0 || patch <= 0 || line <= 0 || nper <= 0 || stride <= 0)
+    return fail(ctx, DCGANSR_ERR_INVALID, "bad patch geometry");
+  const int rows = (nper + line - 1) / line;
+  if ((rows - 1) * stride + patch > h || (line - 1) * stride + patch > w)
+    return fail(ctx, DCGANSR_ERR_INVALID, "patches reach outside the image");
+  return 0;
+}
+int dcgansr_extract_patches(dcgansr_ctx* ctx, const float* images, float* patches, int k, int h, int w, int patch, int line, int nper,
+                            int stride) {
+  NEED_CTX(ctx);
+  if (!images || !patches) return fail(ctx, DCGANSR_ERR_INVALID, "null argument");
+  if (int rc = patch_args_ok(ctx, k, h, w, patch, line, nper, stride)) return rc;
+  Arena ar;
+  const int64_t ni = (int64_t)k * h * w, np = (int64_t)k * nper * patch * patch;
+  float *dI = ar.f(ni), *dP = ar.f(np);
+  if (!dI || !dP) return fail(ctx, DCGANSR_ERR_NOMEM, "device allocation failed");
+  CK(ctx, cudaMemcpyAsync(dI, images, ni * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  k_extract_patches(ctx->st(), dI, dP, k, h, w, patch, line, nper, stride);
+  return d2h(ctx, patches, dP, np);
+}
+int dcgansr_assemble_patches(dcgansr_ctx* ctx, const float* patches, float* images, int k, int h, int w, int patch, int line, int nper,
+                             int stride) {
+  NEED_CTX(ctx);
+  if (!images || !patches) return fail(ctx, DCGANSR_ERR_INVALID, "null argument");
+  if (int rc = patch_args_ok(ctx, k, h, w, patch, line, nper, stride)) return rc;
+  Arena ar;
+  const int64_t ni = (int64_t)k * h * w, np = (int64_t)k * nper * patch * patch;
+  float *dI = ar.f(ni), *dP = ar.f(np);
+  if (!dI || !dP) return fail(ctx, DCGANSR_ERR_NOMEM, "device allocation failed");
+  CK(ctx, cudaMemcpyAsync(dI, images, ni * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));     // uncovered pixels keep their value
+  CK(ctx, cudaMemcpyAsync(dP, patches, np * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  k_assemble_patches(ctx->st(), dP, dI, k, h, w, patch, line, nper, stride);
+  return d2h(ctx, images, dI, ni);
+}
+// images -> device -> the patches become the staged batch of `slot` (k * nper samples of 1 x patch x patch): the patch
+// scripts' real_none without the per-pixel host loop (train-gray-patch.lua:267-275)
+int dcgansr_stage_patches(dcgansr_ctx* ctx, dcgansr_net* netD, const float* images_host, int k, int h, int w, int patch, int line, int nper,
+                          int stride, int slot) {
+  if (!ctx || !netD || !images_host || slot < 0 || slot > 63) return fail(ctx, DCGANSR_ERR_INVALID, "bad stage_patches argument");
+  if (int rc = patch_args_ok(ctx, k, h, w, patch, line, nper, stride)) return rc;
+  if (netD->in_c != 1 || netD->in_h != patch || netD->in_w != patch)
+    return fail(ctx, DCGANSR_ERR_INVALID, "netD input must be 1 x patch x patch");
+  CK(ctx, cudaSetDevice(ctx->cfg.device));
+  if ((int)ctx->slots.size() <= slot) { ctx->slots.resize(slot + 1, nullptr); ctx->slot_bytes.resize(slot + 1, 0); }
+  const size_t pbytes = (size_t)k * nper * patch * patch * sizeof(float), ibytes = (size_t)k * h * w * sizeof(float);
+  if (int rc = ensure(ctx, &ctx->slots[slot], &ctx->slot_bytes[slot], pbytes)) return rc;
+  if (int rc = ensure(ctx, &ctx->tmp, &ctx->tmp_bytes, ibytes)) return rc;
+  CK(ctx, cudaMemcpyAsync(ctx->tmp, images_host, ibytes, cudaMemcpyHostToDevice, ctx->stream));
+  k_extract_patches(ctx->st(), ctx->tmp, ctx->slots[slot], k, h, w, patch, line, nper, stride);
+  CKLAST(ctx);
+  return 0;
+}
+
 int dcgansr_generate(dcgansr_ctx* ctx, dcgansr_net* netG, const float* lr_host, int batch, float* sr_host) {
   if (!ctx || !netG || netG->ctx != ctx) return fail(ctx, DCGANSR_ERR_INVALID, "bad argument");
   return dcgansr_net_forward(netG, lr_host, batch, sr_host);
 }
 
 // ---- layer-level ops (parity tests) -----------------------------------------------------------
-#define NEED_CTX(ctx)                                                          \
-  if (!(ctx)) return fail(nullptr, DCGANSR_ERR_INVALID, "null ctx");            \
-  CK(ctx, cudaSetDevice((ctx)->cfg.device));
 
 static int conv_op(dcgansr_ctx* ctx, bool full, int what, const float* a, const float* b, float* outp, int n, int cin, int h,
                    int wd, int cout, int k, int s, int p) {

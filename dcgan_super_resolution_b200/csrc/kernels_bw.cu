@@ -457,23 +457,24 @@ void k_bn_bwd_apply(St st, const float* g, const float* x, float* dx, int64_t P,
 // pixels each sit back to back in x.  Forward = 3 launches for all groups (partials, column sums + finalize, apply),
 // backward = 3 (reduce, column sums + parameter gradients, apply) instead of 4 per group.  All sums in fixed order.
 // ------------------------------------------------------------------------------------------
+#define BN_TAIL_Y 32      // row threads per 32-channel block: the tails are latency-bound sums over <= 592 partial rows
 __global__ void bn_fwd_tail_kernel(const double* __restrict__ partials, int nb, int C, int groups, double n_total, float eps,
                                    float momentum, float* __restrict__ save_mean, float* __restrict__ save_invstd, int64_t sstride,
                                    float* __restrict__ running_mean, float* __restrict__ running_var) {
-  __shared__ double red[2][8][33];
+  __shared__ double red[2][BN_TAIL_Y][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   for (int g = 0; g < groups; ++g) {                    // sequential: the running statistics see group 0 first
     const double* pg = partials + (int64_t)g * nb * 2 * C;
     double a1 = 0.0, a2 = 0.0;
     if (c < C)
-      for (int b = threadIdx.y; b < nb; b += 8) { a1 += pg[(int64_t)b * 2 * C + c]; a2 += pg[(int64_t)b * 2 * C + C + c]; }
+      for (int b = threadIdx.y; b < nb; b += BN_TAIL_Y) { a1 += pg[(int64_t)b * 2 * C + c]; a2 += pg[(int64_t)b * 2 * C + C + c]; }
     red[0][threadIdx.y][threadIdx.x] = a1;
     red[1][threadIdx.y][threadIdx.x] = a2;
     __syncthreads();
     if (threadIdx.y == 0 && c < C) {
       double s1 = 0.0, s2 = 0.0;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) { s1 += red[0][r][threadIdx.x]; s2 += red[1][r][threadIdx.x]; }
+      for (int r = 0; r < BN_TAIL_Y; ++r) { s1 += red[0][r][threadIdx.x]; s2 += red[1][r][threadIdx.x]; }
       double mean = s1 / n_total;
       double var = s2 / n_total - mean * mean;
       if (var < 0.0) var = 0.0;
@@ -498,7 +499,7 @@ void k_bn_fwd_grouped(St st, const float* x, float* y, int64_t P, int C, int gro
   if (c.vec == 4) bn_stats_kernel<4><<<grid, 256, 0, st.s>>>(x, P, C, c.TX, c.TY, c.ppb, partials);
   else bn_stats_kernel<1><<<grid, 256, 0, st.s>>>(x, P, C, c.TX, c.TY, c.ppb, partials);
   DSR_LAUNCHED(st, "bn_stats", 4.0 * P * C * groups, WORK_BYTES);
-  bn_fwd_tail_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st.s>>>(partials, c.nb, C, groups, (double)P, eps, momentum, save_mean, save_invstd,
+  bn_fwd_tail_kernel<<<(C + 31) / 32, dim3(32, BN_TAIL_Y), 0, st.s>>>(partials, c.nb, C, groups, (double)P, eps, momentum, save_mean, save_invstd,
                                                                sstride, running_mean, running_var);
   DSR_LAUNCHED(st, "bn_fwd_tail", 16.0 * c.nb * C * groups, WORK_BYTES);
   if (C % 4 == 0) {
@@ -514,20 +515,20 @@ void k_bn_fwd_grouped(St st, const float* x, float* y, int64_t P, int C, int gro
 // sums[g][2C] = column sums of group g's partial rows; dbeta += sum_g sums[g][c], dgamma += sum_g sums[g][C + c]
 __global__ void bn_bwd_tail_kernel(const double* __restrict__ partials, int nb, int C, int groups, double* __restrict__ sums,
                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
-  __shared__ double red[2][8][33];
+  __shared__ double red[2][BN_TAIL_Y][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   for (int g = 0; g < groups; ++g) {
     const double* pg = partials + (int64_t)g * nb * 2 * C;
     double a1 = 0.0, a2 = 0.0;
     if (c < C)
-      for (int b = threadIdx.y; b < nb; b += 8) { a1 += pg[(int64_t)b * 2 * C + c]; a2 += pg[(int64_t)b * 2 * C + C + c]; }
+      for (int b = threadIdx.y; b < nb; b += BN_TAIL_Y) { a1 += pg[(int64_t)b * 2 * C + c]; a2 += pg[(int64_t)b * 2 * C + C + c]; }
     red[0][threadIdx.y][threadIdx.x] = a1;
     red[1][threadIdx.y][threadIdx.x] = a2;
     __syncthreads();
     if (threadIdx.y == 0 && c < C) {
       double s1 = 0.0, s2 = 0.0;
 #pragma unroll
-      for (int r = 0; r < 8; ++r) { s1 += red[0][r][threadIdx.x]; s2 += red[1][r][threadIdx.x]; }
+      for (int r = 0; r < BN_TAIL_Y; ++r) { s1 += red[0][r][threadIdx.x]; s2 += red[1][r][threadIdx.x]; }
       sums[(int64_t)g * 2 * C + c] = s1;
       sums[(int64_t)g * 2 * C + C + c] = s2;
       // the reference accumulates group after group in fp32 (two backward calls): same order here
@@ -548,7 +549,7 @@ void k_bn_bwd_grouped(St st, const float* dy, const float* y, const float* x, fl
   else
     bn_bwd_reduce_kernel<1><<<grid, 256, 0, st.s>>>(dy, y, x, dx, P, C, c.TX, c.TY, c.ppb, save_mean, save_invstd, act, negval, partials, sstride);
   DSR_LAUNCHED(st, "bn_bwd_reduce", (act != ACT_NONE ? 16.0 : 12.0) * P * C * groups, WORK_BYTES);
-  bn_bwd_tail_kernel<<<(C + 31) / 32, dim3(32, 8), 0, st.s>>>(partials, c.nb, C, groups, sums, dgamma, dbeta);
+  bn_bwd_tail_kernel<<<(C + 31) / 32, dim3(32, BN_TAIL_Y), 0, st.s>>>(partials, c.nb, C, groups, sums, dgamma, dbeta);
   DSR_LAUNCHED(st, "bn_bwd_tail", 16.0 * c.nb * C * groups, WORK_BYTES);
   if (C % 4 == 0) {
     int64_t tv = P * (C / 4);
@@ -772,4 +773,66 @@ __global__ void flush_kernel(float4* __restrict__ p, int64_t n4) {
 void k_flush(St st, float* buf, int64_t count) {
   flush_kernel<<<NSM * 8, 256, 0, st.s>>>(reinterpret_cast<float4*>(buf), count / 4);
   DSR_LAUNCHED(st, "l2_flush", 4.0 * count, WORK_BYTES);
+}
+
+// ------------------------------------------------------------------------------------------
+// Patch extraction / re-assembly (train-gray-patch.lua:267-273,588-595, train-gray-patch-batch.lua:258-264,
+// 434-442, train-gray-patch-batch-overlap.lua:393-399): the step right before the training path in the patch configs, a
+// scalar Lua triple loop per pixel in the reference.  Single-channel images [K][H][W]; patch i of image k takes
+//     patch[k*nper + i][a][b] = image[k][(i / line) * stride + a][(i % line) * stride + b]
+// (line, stride) = (patchSize, patchSize) in the non-overlapping scripts -- the reference divides by patchSize, which is
+// the number of patches per row only when fineSize / patchSize == patchSize -- and (overlapPatchLine, overlap) in the
+// overlapping one.  Assembly is the inverse scatter of the non-overlapping form.
+// ------------------------------------------------------------------------------------------
+__global__ void extract_patches_kernel(const float* __restrict__ img, float* __restrict__ patches, int K, int H, int W, int p,
+                                       int line, int nper, int stride) {
+  const int64_t total = (int64_t)K * nper * p * p;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += step) {
+    const int b = (int)(idx % p);
+    int64_t r = idx / p;
+    const int a = (int)(r % p); r /= p;
+    const int i = (int)(r % nper);
+    const int k = (int)(r / nper);
+    const int y = (i / line) * stride + a, x = (i % line) * stride + b;
+    patches[idx] = (y < H && x < W) ? img[((int64_t)k * H + y) * W + x] : 0.f;
+  }
+}
+__global__ void assemble_patches_kernel(const float* __restrict__ patches, float* __restrict__ img, int K, int H, int W, int p,
+                                        int line, int nper, int stride) {
+  // one thread per IMAGE pixel (gather form of the scatter: deterministic).  Where patches overlap (stride < p) the
+  // reference's sequential loop lets the LAST patch in index order win; the gather picks that same patch.
+  const int64_t total = (int64_t)K * H * W;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += step) {
+    const int x = (int)(idx % W);
+    int64_t r = idx / W;
+    const int y = (int)(r % H);
+    const int k = (int)(r / H);
+    // last (row block, col block) whose patch covers the pixel
+    int rb = y / stride, cb = x / stride;
+    const int rows = (nper + line - 1) / line;
+    if (rb > rows - 1) rb = rows - 1;
+    if (cb > line - 1) cb = line - 1;
+    float v = img[idx];
+    bool found = false;
+    for (int rr = rb; rr >= 0 && !found && rr * stride + p > y; --rr)
+      for (int cc = cb; cc >= 0 && cc * stride + p > x; --cc) {
+        const int i = rr * line + cc;
+        if (i < nper) { v = patches[(((int64_t)k * nper + i) * p + (y - rr * stride)) * p + (x - cc * stride)]; found = true; break; }
+      }
+    img[idx] = v;
+  }
+}
+void k_extract_patches(St st, const float* img, float* patches, int K, int H, int W, int p, int line, int nper, int stride) {
+  const int64_t total = (int64_t)K * nper * p * p;
+  if (total <= 0) return;
+  extract_patches_kernel<<<sc_grid(total), 256, 0, st.s>>>(img, patches, K, H, W, p, line, nper, stride);
+  DSR_LAUNCHED(st, "extract_patches", 8.0 * total, WORK_BYTES);
+}
+void k_assemble_patches(St st, const float* patches, float* img, int K, int H, int W, int p, int line, int nper, int stride) {
+  const int64_t total = (int64_t)K * H * W;
+  if (total <= 0) return;
+  assemble_patches_kernel<<<sc_grid(total), 256, 0, st.s>>>(patches, img, K, H, W, p, line, nper, stride);
+  DSR_LAUNCHED(st, "assemble_patches", 8.0 * total, WORK_BYTES);
 }

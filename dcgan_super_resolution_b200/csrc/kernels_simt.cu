@@ -55,22 +55,17 @@ __global__ void pack_all_kernel(const PackJob* __restrict__ jobs, int njobs, int
       if (sbeg[mid] <= i) lo = mid; else hi = mid - 1;
     }
     const PackJob& j = jobs[lo];
-    const int64_t l = i - sbeg[lo];
+    const uint32_t l = (uint32_t)(i - sbeg[lo]);        // a job has < 2^31 elements: 32-bit index arithmetic
+    const uint32_t A = (uint32_t)j.A, B = (uint32_t)j.B, T = (uint32_t)j.ntaps;
     if (j.tc) {                             // K-major tensor-core pack bp[b][t*A + a], TF32-rounded
-      int a = (int)(l % j.A);
-      int64_t r = l / j.A;
-      int t = (int)(r % j.ntaps);
-      int b = (int)(r / j.ntaps);
-      float v = j.src[a * j.sa + b * j.sb + j.tapidx[t]];
+      const uint32_t a = l % A, r = l / A, t = r % T, b = r / T;
+      float v = j.src[(int64_t)a * j.sa + (int64_t)b * j.sb + j.tapidx[t]];
       uint32_t u;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
       j.dst[l] = __uint_as_float(u);
     } else {                                // SIMT / streaming pack wp[t][a][b]
-      int b = (int)(l % j.B);
-      int64_t r = l / j.B;
-      int a = (int)(r % j.A);
-      int t = (int)(r / j.A);
-      j.dst[l] = j.src[a * j.sa + b * j.sb + j.tapidx[t]];
+      const uint32_t b = l % B, r = l / B, a = r % A, t = r / A;
+      j.dst[l] = j.src[(int64_t)a * j.sa + (int64_t)b * j.sb + j.tapidx[t]];
     }
   }
 }

@@ -339,3 +339,36 @@ def train_step_staged(ctx: Context, netG, netD, cfg, slot: int, batch: int, want
     L.check(ctx.lib.dcgansr_train_step_staged(ctx.h, netG.h, netD.h, C.byref(cfg), slot, batch,
                                               losses if want_losses else None), ctx.h)
     return tuple(losses) if want_losses else None
+
+
+# ---- patch extraction / re-assembly (train-gray-patch*.lua) ----------------------------------------
+def _patch_geom(fine, patch, overlap=0):
+    """(line, nper, stride) of the reference scripts: non-overlapping -> the reference's (patchSize, (fine/patch)^2, patchSize)
+    (train-gray-patch.lua:267-273), overlapping -> (overlapPatchLine, overlapPatchLine^2, overlap) (…-overlap.lua:387-399)."""
+    if overlap:
+        line = (fine - overlap) // (patch - overlap)
+        return line, line * line, overlap
+    return patch, (fine // patch) ** 2, patch
+
+
+def extract_patches(ctx: Context, images, patch: int, line: int, nper: int, stride: int):
+    a, pa = _f32(images)
+    k, h, w = a.shape
+    out = np.empty((k * nper, patch, patch), np.float32)
+    L.check(ctx.lib.dcgansr_extract_patches(ctx.h, pa, out.ctypes.data_as(C.c_void_p), k, h, w, patch, line, nper, stride), ctx.h)
+    return out
+
+
+def assemble_patches(ctx: Context, patches, images, patch: int, line: int, nper: int, stride: int):
+    p_, pp = _f32(patches)
+    out = np.array(images, dtype=np.float32, order="C", copy=True)
+    k, h, w = out.shape
+    L.check(ctx.lib.dcgansr_assemble_patches(ctx.h, pp, out.ctypes.data_as(C.c_void_p), k, h, w, patch, line, nper, stride), ctx.h)
+    return out
+
+
+def stage_patches(ctx: Context, netD: Sequential, images, patch: int, line: int, nper: int, stride: int, slot: int):
+    a, pa = _f32(images)
+    k, h, w = a.shape
+    L.check(ctx.lib.dcgansr_stage_patches(ctx.h, netD.h, pa, k, h, w, patch, line, nper, stride, slot), ctx.h)
+    return k * nper

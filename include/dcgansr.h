@@ -169,6 +169,18 @@ int dcgansr_train_step(dcgansr_ctx* ctx, dcgansr_net* netG, dcgansr_net* netD,
 int dcgansr_stage_batch(dcgansr_ctx* ctx, dcgansr_net* netD, const float* real_host, int local_batch, int slot);
 int dcgansr_train_step_staged(dcgansr_ctx* ctx, dcgansr_net* netG, dcgansr_net* netD,
                               const dcgansr_step_cfg* cfg, int slot, int local_batch, float* out_losses);
+/* Patch extraction / re-assembly on the device (train-gray-patch.lua:267-273,588-595; train-gray-patch-batch.lua:258-264,
+ * 434-442; train-gray-patch-batch-overlap.lua:393-399).  Single-channel images [k][h][w]; patch i of image j:
+ *   patches[j*nper + i][a][b] = images[j][(i / line) * stride + a][(i % line) * stride + b]
+ * (line, stride) = (patchSize, patchSize) in the non-overlapping scripts, (overlapPatchLine, overlap) in the overlapping one.
+ * assemble is the inverse scatter (where patches overlap the highest patch index wins, as in the reference loop; pixels
+ * no patch covers keep the value passed in).  stage_patches makes the patches the staged batch of `slot`. */
+int dcgansr_extract_patches(dcgansr_ctx* ctx, const float* images, float* patches, int k, int h, int w, int patch,
+                            int line, int nper, int stride);
+int dcgansr_assemble_patches(dcgansr_ctx* ctx, const float* patches, float* images, int k, int h, int w, int patch,
+                             int line, int nper, int stride);
+int dcgansr_stage_patches(dcgansr_ctx* ctx, dcgansr_net* netD, const float* images_host, int k, int h, int w, int patch,
+                          int line, int nper, int stride, int slot);
 /* netG:forward on a batch of low-res inputs (eval path, train-gray-3.lua:359-445) */
 int dcgansr_generate(dcgansr_ctx* ctx, dcgansr_net* netG, const float* lr_host, int batch, float* sr_host);
 
