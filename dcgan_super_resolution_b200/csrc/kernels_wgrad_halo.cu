@@ -42,7 +42,9 @@ struct WhParams {
   int a5d;                                 // P tile through the 5-D [y][chunk][x] map (Cp % 32 == 0) or a single zero-padded chunk
   int RA, PW, a_bytes, plane_bytes, stage_bytes, nstage, nmma, ncols, tmem_cols;
   short pl_py[WH_MAXPL], pl_px[WH_MAXPL], pl_oy0[WH_MAXPL], pl_ox0[WH_MAXPL];
-  short tap_of[WH_MAXPL][4][4];            // [plane][row shift i][col shift i2] -> tap index (or -1)
+  short tap_of[WH_MAXPL][4][4][2];         // [plane][row shift i][col shift i2][16-column half] -> tap index (or -1)
+  int packed;                              // Cq = 16, s = 2: a 128-byte row of the parity view holds BOTH column parities, so an N atom
+                                           // = (px, 16 channels) and the planes are the row parities only
   long long split_stride;
 };
 
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(WH_THREADS) wgrad_halo_kernel(const __grid_con
           for (int qs = 0; qs < p.Qs; ++qs) {
             const uint32_t dst = st + (uint32_t)p.a_bytes + (uint32_t)(pl * p.Qs + qs) * p.plane_bytes;
             if (p.s == 1) tma_load_4d(dst, &mapQ, fb, qs * 32, gx0 + p.pl_ox0[pl], gy0 + p.pl_oy0[pl], n);
-            else tma_load_5d(dst, &mapQ, fb, p.pl_px[pl] * p.Cq + qs * 32, gx0 + p.pl_ox0[pl], p.pl_py[pl], gy0 + p.pl_oy0[pl], n);
+            else tma_load_5d(dst, &mapQ, fb, p.packed ? 0 : p.pl_px[pl] * p.Cq + qs * 32, gx0 + p.pl_ox0[pl], p.pl_py[pl], gy0 + p.pl_oy0[pl], n);
           }
         if (++s == p.nstage) { s = 0; ph ^= 1u; }
       }
@@ -160,7 +162,22 @@ __global__ void __launch_bounds__(WH_THREADS) wgrad_halo_kernel(const __grid_con
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(((pl * p.Qs + qs) * p.nx + i2) * 32), v);
           tmem_ld_wait();
-          const int t = row_ok ? p.tap_of[pl][ish][i2] : -1;
+          if (p.packed) {
+            // columns = (px, 16 channels): each half belongs to a different tap (or to none)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+              const int t = row_ok ? p.tap_of[pl][ish][i2][hf] : -1;
+              if (t >= 0) {
+                float* d = drow + t * p.Cq;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                  *reinterpret_cast<float4*>(d + j) = make_float4(__uint_as_float(v[hf * 16 + j]), __uint_as_float(v[hf * 16 + j + 1]),
+                                                                  __uint_as_float(v[hf * 16 + j + 2]), __uint_as_float(v[hf * 16 + j + 3]));
+              }
+            }
+            continue;
+          }
+          const int t = row_ok ? p.tap_of[pl][ish][i2][0] : -1;
           if (t >= 0) {
             float* d = drow + t * p.Cq + qs * 32;
 #pragma unroll
@@ -194,7 +211,8 @@ static bool wh_cfg(const WgradGeom& g, WhCfg& c) {
   memset(&c.tab, 0, sizeof(c.tab));
   if (g.s != 1 && g.s != 2) return false;
   if (g.s == 2 && (g.Hq % 2 || g.Wq % 2)) return false;
-  if (g.Cq % 32 || g.Cp % 4 || g.Cp < 8 || g.ntaps < 1 || g.ntaps > DSR_MAX_TAPS) return false;
+  const bool packed = g.Cq == 16 && g.s == 2;
+  if ((g.Cq % 32 && !packed) || g.Cp % 4 || g.Cp < 8 || g.ntaps < 1 || g.ntaps > DSR_MAX_TAPS) return false;
   if (!(g.Cp % 32 == 0 || g.Cp <= 32)) return false;
   if (g.Hp < 8 || g.Wp < 8) return false;
   p.N = g.N; p.Hg = g.Hp; p.Wg = g.Wp; p.Cp = g.Cp; p.Cq = g.Cq; p.T = g.ntaps; p.s = g.s;
@@ -202,8 +220,10 @@ static bool wh_cfg(const WgradGeom& g, WhCfg& c) {
   struct Pl { int py, px, oymin, oymax, oxmin, oxmax, cnt; };
   Pl pls[WH_MAXPL];
   int npl = 0;
+  p.packed = packed ? 1 : 0;
   for (int t = 0; t < g.ntaps; ++t) {
-    const int oy = fdiv(g.dy[t], g.s), py = g.dy[t] - oy * g.s, ox = fdiv(g.dx[t], g.s), px = g.dx[t] - ox * g.s;
+    const int oy = fdiv(g.dy[t], g.s), py = g.dy[t] - oy * g.s, ox = fdiv(g.dx[t], g.s);
+    const int px = packed ? 0 : g.dx[t] - ox * g.s;         // packed: both column parities share the plane
     int f = -1;
     for (int i = 0; i < npl; ++i) if (pls[i].py == py && pls[i].px == px) f = i;
     if (f < 0) { if (npl == WH_MAXPL) return false; f = npl++; pls[f] = Pl{py, px, oy, oy, ox, ox, 0}; }
@@ -216,15 +236,16 @@ static bool wh_cfg(const WgradGeom& g, WhCfg& c) {
   for (int i = 0; i < npl; ++i) {
     if (pls[i].oymax - pls[i].oymin + 1 != p.ny || pls[i].oxmax - pls[i].oxmin + 1 != p.nx) return false;   // equal rectangles only
     p.pl_py[i] = (short)pls[i].py; p.pl_px[i] = (short)pls[i].px; p.pl_oy0[i] = (short)pls[i].oymin; p.pl_ox0[i] = (short)pls[i].oxmin;
-    for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) p.tap_of[i][a][b] = -1;
+    for (int a = 0; a < 4; ++a) for (int b = 0; b < 4; ++b) { p.tap_of[i][a][b][0] = -1; p.tap_of[i][a][b][1] = -1; }
   }
   if (p.ny > 4 || p.nx > 4) return false;
   for (int t = 0; t < g.ntaps; ++t) {
-    const int oy = fdiv(g.dy[t], g.s), py = g.dy[t] - oy * g.s, ox = fdiv(g.dx[t], g.s), px = g.dx[t] - ox * g.s;
+    const int oy = fdiv(g.dy[t], g.s), py = g.dy[t] - oy * g.s, ox = fdiv(g.dx[t], g.s), pxr = g.dx[t] - ox * g.s;
+    const int px = packed ? 0 : pxr;
     for (int i = 0; i < npl; ++i)
-      if (pls[i].py == py && pls[i].px == px) p.tap_of[i][oy - pls[i].oymin][ox - pls[i].oxmin] = (short)t;
+      if (pls[i].py == py && pls[i].px == px) p.tap_of[i][oy - pls[i].oymin][ox - pls[i].oxmin][packed ? pxr : 0] = (short)t;
   }
-  p.Qs = g.Cq / 32;
+  p.Qs = packed ? 1 : g.Cq / 32;
   p.a5d = g.Cp % 32 == 0 ? 1 : 0;
   const int Qp = (g.Cp + 31) / 32;
   p.mch = std::max(1, std::min(Qp, 4 / p.ny));           // M = ny * mch * 32 <= 128

@@ -35,6 +35,8 @@ TC_SHAPES = [
     ("conv", 1, 16, 40, 36, 8, 4, 2, 1),       # Ci = 16 through the parity view (two taps share a 128-byte row), ragged tiles
     ("full", 1, 96, 20, 12, 48, 4, 2, 1),      # train.lua G layer 2: 3 planes
     ("conv", 3, 32, 17, 19, 24, 3, 1, 1),      # stride 1, odd sizes: partial tiles in both directions
+    ("full", 2, 32, 16, 12, 16, 4, 2, 1),      # C4 G layer 4 (FC 32->16): wgrad with a 16-channel shifted tensor (packed parities)
+    ("conv", 2, 16, 32, 24, 32, 4, 2, 1),      # C4 G layer 5 (C 16->32)
 ]
 
 
