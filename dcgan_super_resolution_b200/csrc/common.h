@@ -130,7 +130,9 @@ void k_flush(St st, float* buf, int64_t count);
 void k_pack_taps(St st, const float* master, float* wp, int ntaps, const int* tapidx_dev, int A, int B,
                  int64_t sa, int64_t sb);
 // one fused pack launch per net: job j repacks master weights into dst (tc: K-major TF32 pack, else [t][a][b])
-struct PackJob { const float* src; float* dst; const int* tapidx; int ntaps, A, B, tc; int64_t sa, sb, begin; };
+// tc: 0 = [t][a][b] streaming pack, 1 = K-major TF32 pack bp[b][t*A + a] (TMA 2-D source), 2 = the same values pre-tiled and
+// pre-swizzled as the [n tile][k block][bn rows][32 floats] shared-memory images of the per-tap kernel (bulk-copy source)
+struct PackJob { const float* src; float* dst; const int* tapidx; int ntaps, A, B, tc, bn; int64_t sa, sb, begin; };
 void k_pack_all(St st, const PackJob* jobs_dev, int njobs, int64_t total);
 void k_tapconv_simt(St st, const TapGeom& g, const float* in, const float* wp, float* out, int act, float negval);
 // wgrad: accumulates into grad_master (+=) through a deterministic split-K reduction in `scratch`
@@ -157,6 +159,9 @@ bool tc_init(std::string* err);                       // resolves cuTensorMapEnc
 bool tc_tapconv_supported(const TapGeom& g);
 // K-major packed weights for the tensor-core path: Bp[b (N, padded)][t*A + a] (tf32-rounded)
 size_t tc_packed_elems(int ntaps, int A, int B);
+// pre-tiled weight images for k_tapconv_tc_multi (needs A % 32 == 0): tile rows bn = tc_bt_rows(B)
+int tc_bt_rows(int B);
+size_t tc_bt_elems(int ntaps, int A, int B);
 void k_pack_taps_tc(St st, const float* master, float* bp, int ntaps, const int* tapidx_dev, int A, int B,
                     int64_t sa, int64_t sb);
 // returns false (with err) if the launch could not be configured
@@ -174,7 +179,7 @@ bool k_wgrad_halo(St st, const WgradGeom& g, const float* P, const float* Q, flo
 // all sub-pixel classes of a module in one launch (blockIdx.z); classes must share the iterated grid
 bool tc_tapconv_multi_ok(const TapGeom* classes, int ncls);
 bool k_tapconv_tc_multi(St st, const TapGeom* classes, int ncls, const float* const* bp, const float* in, float* out, int act,
-                        float negval, std::string* err);
+                        float negval, std::string* err, const float* const* bt = nullptr);
 bool tc_wgrad_supported(const WgradGeom& g);
 size_t wgrad_tc_scratch_bytes(const WgradGeom& g);
 bool k_wgrad_tc(St st, const WgradGeom& g, const float* P, const float* Q, float* grad_master, float* scratch, size_t scratch_bytes,

@@ -171,6 +171,7 @@ struct TapClass {
   int* tapidx_dev = nullptr;
   float* wp = nullptr;       // SIMT pack  [t][A][B]
   float* bp = nullptr;       // tensor-core pack (K-major, tf32)
+  float* bt = nullptr;       // the same, pre-tiled + pre-swizzled for the per-tap kernel's bulk-copy loads (instead of bp)
   int A = 0, B = 0;
   int64_t sa = 0, sb = 0;
 };
@@ -277,6 +278,18 @@ struct ConvPlan {
           CK(ctx, cudaMemcpy(c.tapidx_dev, c.tapidx.data(), c.tapidx.size() * sizeof(int), cudaMemcpyHostToDevice));
         CK(ctx, cudaMalloc((void**)&c.wp, std::max<size_t>((size_t)c.g.ntaps * c.A * c.B, 4) * sizeof(float)));
       }
+    // class groups the weights-resident halo kernel will NOT take run on the per-tap kernel: give them the pre-tiled
+    // weight images as well (decided once, here: it only depends on the geometry, not on the batch)
+    if (fast && !getenv("DCGANSR_NO_BT"))
+      for (auto* v : {&fwd, &dgrad}) {
+        if (v->empty() || v->size() > 4) continue;
+        TapGeom gs[4];
+        bool all_tc = true;
+        for (size_t i = 0; i < v->size(); ++i) { gs[i] = (*v)[i].g; gs[i].N = 1; all_tc = all_tc && (*v)[i].bp && (*v)[i].A > 4; }
+        if (!all_tc || (*v)[0].A % 32 || !tc_tapconv_multi_ok(gs, (int)v->size()) || halo_tapconv_supported(gs, (int)v->size())) continue;
+        for (auto& c : *v)
+          CK(ctx, cudaMalloc((void**)&c.bt, std::max<size_t>(tc_bt_elems(c.g.ntaps, c.A, c.B), 4) * sizeof(float)));
+      }
     device = true;
     return 0;
   }
@@ -286,9 +299,23 @@ struct ConvPlan {
         if (c.tapidx_dev) cudaFree(c.tapidx_dev);
         if (c.wp) cudaFree(c.wp);
         if (c.bp) cudaFree(c.bp);
-        c.tapidx_dev = nullptr; c.wp = nullptr; c.bp = nullptr;
+        if (c.bt) cudaFree(c.bt);
+        c.tapidx_dev = nullptr; c.wp = nullptr; c.bp = nullptr; c.bt = nullptr;
       }
     device = false;
+  }
+  // single-class repack of the pre-tiled images (layer-level ops; nets use the fused job list)
+  static void pack_bt_one(St st, const float* master, TapClass& c) {
+    PackJob j[2];
+    j[0].src = master; j[0].dst = c.bt; j[0].tapidx = c.tapidx_dev; j[0].ntaps = c.g.ntaps; j[0].A = c.A; j[0].B = c.B; j[0].tc = 2;
+    j[0].bn = tc_bt_rows(c.B); j[0].sa = c.sa; j[0].sb = c.sb; j[0].begin = 0;
+    j[1] = j[0]; j[1].begin = (int64_t)tc_bt_elems(c.g.ntaps, c.A, c.B);
+    PackJob* dj = nullptr;
+    if (cudaMalloc((void**)&dj, sizeof(j)) != cudaSuccess) return;
+    cudaMemcpyAsync(dj, j, sizeof(j), cudaMemcpyHostToDevice, st.s);
+    k_pack_all(st, dj, 1, j[1].begin);
+    cudaStreamSynchronize(st.s);
+    cudaFree(dj);
   }
   void pack(St st, const float* master) {
     for (auto* v : {&fwd, &dgrad})
@@ -297,6 +324,7 @@ struct ConvPlan {
           // the streaming kernels (1..4-channel side) read the [t][a][b] pack; a thin-OUTPUT class keeps both packs
           // (few pixels -> streaming reduction, many pixels -> tensor-core kernels)
           if (c.bp && c.A > 4) k_pack_taps_tc(st, master, c.bp, c.g.ntaps, c.tapidx_dev, c.A, c.B, c.sa, c.sb);
+          if (c.bt) pack_bt_one(st, master, c);
           if (!c.bp || c.A <= 4 || c.B <= 4) k_pack_taps(st, master, c.wp, c.g.ntaps, c.tapidx_dev, c.A, c.B, c.sa, c.sb);
         }
   }
@@ -306,7 +334,12 @@ struct ConvPlan {
         if (c.g.ntaps > 0) {
           PackJob j;
           j.src = master; j.tapidx = c.tapidx_dev; j.ntaps = c.g.ntaps; j.A = c.A; j.B = c.B; j.sa = c.sa; j.sb = c.sb;
-          if (c.bp && c.A > 4) {
+          j.bn = 0;
+          if (c.bt) {          // per-tap kernel: pre-tiled images only (the TMA 2-D pack is not read)
+            j.tc = 2; j.dst = c.bt; j.bn = tc_bt_rows(c.B); j.begin = total;
+            total += (int64_t)tc_bt_elems(c.g.ntaps, c.A, c.B);
+            jobs.push_back(j);
+          } else if (c.bp && c.A > 4) {
             j.tc = 1; j.dst = c.bp; j.begin = total;
             total += (int64_t)c.g.ntaps * c.A * c.B;
             jobs.push_back(j);
@@ -337,16 +370,18 @@ struct ConvPlan {
       const float* bps[4];
       bool all_tc = true;
       for (size_t i = 0; i < v.size(); ++i) { gs[i] = v[i].g; gs[i].N = N; bps[i] = v[i].bp; all_tc = all_tc && v[i].bp && v[i].A > 4; }
-      if (all_tc && halo_tapconv_supported(gs, (int)v.size())) {
+      if (all_tc && !v[0].bt && halo_tapconv_supported(gs, (int)v.size())) {     // (groups with pre-tiled images belong to the per-tap kernel)
         std::string e;
         if (k_tapconv_halo(ctx->st(), gs, (int)v.size(), bps, in, out, act, neg, &e)) return;
         ctx->err = "tcgen05 halo path: " + e;
         ctx->tc_failed = true;
         return;
       }
-      if (all_tc && v.size() > 1 && tc_tapconv_multi_ok(gs, (int)v.size())) {
+      const float* bts[4];
+      for (size_t i = 0; i < v.size(); ++i) bts[i] = v[i].bt;
+      if (all_tc && tc_tapconv_multi_ok(gs, (int)v.size())) {
         std::string e;
-        if (k_tapconv_tc_multi(ctx->st(), gs, (int)v.size(), bps, in, out, act, neg, &e)) return;
+        if (k_tapconv_tc_multi(ctx->st(), gs, (int)v.size(), bps, in, out, act, neg, &e, bts)) return;
         ctx->err = "tcgen05 path: " + e;
         ctx->tc_failed = true;
         return;

@@ -57,7 +57,16 @@ __global__ void pack_all_kernel(const PackJob* __restrict__ jobs, int njobs, int
     const PackJob& j = jobs[lo];
     const uint32_t l = (uint32_t)(i - sbeg[lo]);        // a job has < 2^31 elements: 32-bit index arithmetic
     const uint32_t A = (uint32_t)j.A, B = (uint32_t)j.B, T = (uint32_t)j.ntaps;
-    if (j.tc) {                             // K-major tensor-core pack bp[b][t*A + a], TF32-rounded
+    if (j.tc == 2) {                        // pre-tiled, pre-swizzled smem images: [n tile][k block][bn rows][32 floats]
+      const uint32_t BNr = (uint32_t)j.bn, nk = T * A / 32;
+      const uint32_t c = l & 31, r = (l >> 5) % BNr, q = (l >> 5) / BNr, kb = q % nk, nt = q / nk;
+      const uint32_t kcol = ((((c >> 2) ^ (r & 7)) << 2) | (c & 3));       // SWIZZLE_128B: 16-byte chunk index ^ (row & 7)
+      const uint32_t k = kb * 32 + kcol, t = k / A, a = k - t * A, n = nt * BNr + r;
+      float v = n < B ? j.src[(int64_t)a * j.sa + (int64_t)n * j.sb + j.tapidx[t]] : 0.f;
+      uint32_t u;
+      asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+      j.dst[l] = __uint_as_float(u);
+    } else if (j.tc) {                      // K-major tensor-core pack bp[b][t*A + a], TF32-rounded
       const uint32_t a = l % A, r = l / A, t = r % T, b = r / T;
       float v = j.src[(int64_t)a * j.sa + (int64_t)b * j.sb + j.tapidx[t]];
       uint32_t u;

@@ -64,6 +64,11 @@ bool tc_tapconv_supported(const TapGeom& g) {
 // weight packing for the tensor-core path: Bp[b][t*A + a] = tf32(master[a*sa + b*sb + tapidx[t]])
 // ------------------------------------------------------------------------------------------
 size_t tc_packed_elems(int ntaps, int A, int B) { return (size_t)ntaps * A * B; }
+int tc_bt_rows(int B) { return std::min((B + 15) / 16 * 16, 128); }
+size_t tc_bt_elems(int ntaps, int A, int B) {
+  const int bn = tc_bt_rows(B);
+  return (size_t)((B + bn - 1) / bn) * ((size_t)ntaps * A / 32) * bn * 32;
+}
 
 __global__ void pack_taps_tc_kernel(const float* __restrict__ master, float* __restrict__ bp, int ntaps,
                                     const int* __restrict__ tapidx, int A, int B, int64_t sa, int64_t sb) {
@@ -100,6 +105,7 @@ struct TcParams {
   int KB, kchunks, BN, nstage;
   int ncls, oy0[TC_MAXCLS], ox0[TC_MAXCLS], ntaps[TC_MAXCLS];      // sub-pixel classes: blockIdx.z / ksplit
   int ksplit;                                                      // K splits per tile: blockIdx.z % ksplit
+  const float* bt[TC_MAXCLS];                                      // pre-tiled weight images (bulk-copy source) or null -> TMA 2-D
   int a_stage_bytes, b_stage_bytes, tmem_cols;
   int act;
   float neg;
@@ -174,7 +180,10 @@ __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_con
           tma_load_4d(da, &mapA, fb, c * p.KB, gx0 + p.ox[cls][t], gy0 + p.oy[cls][t], b0);
         else
           tma_load_5d(da, &mapA, fb, p.px[cls][t] * p.Ci + c * p.KB, gx0 + p.ox[cls][t], p.py[cls][t], gy0 + p.oy[cls][t], b0);
-        tma_load_2d(smem_u32(sB + (size_t)s * p.b_stage_bytes), &mapsB.b[cls], fb, kb * p.KB, n0);
+        if (p.bt[cls])    // one contiguous 1-D bulk copy of the whole BN x 32 tile image instead of BN 128-byte TMA rows
+          bulk_load(smem_u32(sB + (size_t)s * p.b_stage_bytes), p.bt[cls] + ((size_t)blockIdx.y * nk_all + kb) * (p.BN * 32), (uint32_t)(p.BN * 128), fb);
+        else
+          tma_load_2d(smem_u32(sB + (size_t)s * p.b_stage_bytes), &mapsB.b[cls], fb, kb * p.KB, n0);
         if (++s == p.nstage) { s = 0; ph ^= 1; }
       }
     }
@@ -317,7 +326,7 @@ bool tc_tapconv_multi_ok(const TapGeom* cls, int ncls) {
 }
 
 bool k_tapconv_tc_multi(St st, const TapGeom* cls, int ncls, const float* const* bp, const float* in, float* out, int act, float negval,
-                        std::string* err) {
+                        std::string* err, const float* const* bt) {
   if (!tc_tapconv_multi_ok(cls, ncls)) { if (err) *err = "geometry not supported by the tcgen05 path"; return false; }
   const TapGeom& g = cls[0];
   TcParams p;
@@ -358,6 +367,7 @@ bool k_tapconv_tc_multi(St st, const TapGeom* cls, int ncls, const float* const*
   }
   p.act = act; p.neg = negval;
   for (int i = 0; i < ncls; ++i) {
+    p.bt[i] = (bt && bt[i] && p.KB == 32 && p.BN == tc_bt_rows(g.Co)) ? bt[i] : nullptr;
     p.oy0[i] = cls[i].oy0; p.ox0[i] = cls[i].ox0; p.ntaps[i] = cls[i].ntaps;
     for (int t = 0; t < cls[i].ntaps; ++t) {
       if (g.si == 1) { p.oy[i][t] = (short)cls[i].dy[t]; p.ox[i][t] = (short)cls[i].dx[t]; p.py[i][t] = 0; p.px[i][t] = 0; }
