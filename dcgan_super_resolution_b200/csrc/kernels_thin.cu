@@ -230,7 +230,7 @@ bool k_wgrad_thin(St st, const WgradGeom& g, const float* P, const float* Q, flo
 // Pure output-write streaming: a thread owns one output pixel x 4 couts, the <= 16 x Ci input scalars come through L1,
 // the (tiny) weights live in shared memory.  All sub-pixel classes in one launch (blockIdx.y).
 // =====================================================================================================================
-struct ThinInCls { int Hg, Wg, oy0, ox0, ntaps; short dy[16], dx[16]; const float* wp; };
+struct ThinInCls { int Hg, Wg, oy0, ox0, ntaps, gx_lo, gx_hi; short dy[16], dx[16]; const float* wp; };
 struct ThinIn {
   int N, Hi, Wi, Ci, Ho, Wo, Co, si, so, ncls, act, vpad, seg, nseg;
   float neg;
@@ -260,12 +260,22 @@ __global__ void __launch_bounds__(256) thin_in_kernel(const ThinIn p, const floa
   const int v = threadIdx.x % VP, slot = threadIdx.x / VP, PS = 256 / VP;
   if (v >= V) return;
   const float4* wv = reinterpret_cast<const float4*>(sw) + v;  // + (t*CI + ci) * V
+  // this thread's 4 couts of every tap: in registers when they are few (<= 4 float4), else read from shared memory per use
+  constexpr bool WREG = NT * CI <= 4;      // (16 float4 of weights in registers was measured: 157 registers, slower)
+  float4 wr[WREG ? NT * CI : 1];
+  if (WREG) {
+#pragma unroll
+    for (int k = 0; k < NT * CI; ++k) wr[k] = k < c.ntaps * CI ? wv[k * V] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  // interior columns: every tap inside the image, no bounds checks
+  const int gx_lo = c.gx_lo, gx_hi = c.gx_hi;
   const int items = p.N * c.Hg * p.nseg;                       // (row, gx segment)
   for (int item = blockIdx.x * PS + slot; item < items; item += gridDim.x * PS) {
     const int row = item / p.nseg, gx0 = (item - row * p.nseg) * p.seg, gx1 = min(c.Wg, gx0 + p.seg);
     const int n = row / c.Hg, gy = row - n * c.Hg;
     const float* ir[NT];
     int dxs[NT];
+    bool clean = c.ntaps == NT;
 #pragma unroll
     for (int t = 0; t < NT; ++t) {
       ir[t] = nullptr;
@@ -274,21 +284,35 @@ __global__ void __launch_bounds__(256) thin_in_kernel(const ThinIn p, const floa
         const int iy = gy * p.si + c.dy[t];
         dxs[t] = c.dx[t];
         if (iy >= 0 && iy < p.Hi) ir[t] = in + ((int64_t)(n * p.Hi + iy) * p.Wi) * CI;
+        else clean = false;
       }
     }
     const int ostep = p.so * p.Co;
     float* o = out + ((int64_t)(n * p.Ho + gy * p.so + c.oy0) * p.Wo + c.ox0) * p.Co + v * 4 + (int64_t)gx0 * ostep;
     for (int gx = gx0; gx < gx1; ++gx, o += ostep) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (clean && gx >= gx_lo && gx <= gx_hi) {
 #pragma unroll
-      for (int t = 0; t < NT; ++t) {
-        const int ix = gx * p.si + dxs[t];
-        if (ir[t] && ix >= 0 && ix < p.Wi) {
+        for (int t = 0; t < NT; ++t) {
+          const float* ip = ir[t] + (gx * p.si + dxs[t]) * CI;
 #pragma unroll
           for (int ci = 0; ci < CI; ++ci) {
-            const float x = __ldg(ir[t] + ix * CI + ci);
-            const float4 w = wv[(t * CI + ci) * V];
+            const float x = __ldg(ip + ci);
+            const float4 w = WREG ? wr[t * CI + ci] : wv[(t * CI + ci) * V];
             acc.x = fmaf(x, w.x, acc.x); acc.y = fmaf(x, w.y, acc.y); acc.z = fmaf(x, w.z, acc.z); acc.w = fmaf(x, w.w, acc.w);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const int ix = gx * p.si + dxs[t];
+          if (ir[t] && ix >= 0 && ix < p.Wi) {
+#pragma unroll
+            for (int ci = 0; ci < CI; ++ci) {
+              const float x = __ldg(ir[t] + ix * CI + ci);
+              const float4 w = WREG ? wr[t * CI + ci] : wv[(t * CI + ci) * V];
+              acc.x = fmaf(x, w.x, acc.x); acc.y = fmaf(x, w.y, acc.y); acc.z = fmaf(x, w.z, acc.z); acc.w = fmaf(x, w.w, acc.w);
+            }
           }
         }
       }
@@ -321,7 +345,14 @@ bool k_tapconv_thin_in(St st, const TapGeom* cls, int ncls, const float* const* 
   double bytes = 0;
   for (int i = 0; i < ncls; ++i) {
     p.c[i].Hg = cls[i].Hg; p.c[i].Wg = cls[i].Wg; p.c[i].oy0 = cls[i].oy0; p.c[i].ox0 = cls[i].ox0; p.c[i].ntaps = cls[i].ntaps;
-    for (int t = 0; t < cls[i].ntaps; ++t) { p.c[i].dy[t] = (short)cls[i].dy[t]; p.c[i].dx[t] = (short)cls[i].dx[t]; }
+    int dxmin = 1 << 20, dxmax = -(1 << 20);
+    for (int t = 0; t < cls[i].ntaps; ++t) {
+      p.c[i].dy[t] = (short)cls[i].dy[t]; p.c[i].dx[t] = (short)cls[i].dx[t];
+      dxmin = std::min(dxmin, cls[i].dx[t]); dxmax = std::max(dxmax, cls[i].dx[t]);
+    }
+    // gx with every tap column inside [0, Wi): gx*si + dxmin >= 0 and gx*si + dxmax <= Wi - 1
+    p.c[i].gx_lo = dxmin < 0 ? (-dxmin + g.si - 1) / g.si : 0;
+    p.c[i].gx_hi = (g.Wi - 1 - dxmax) >= 0 ? (g.Wi - 1 - dxmax) / g.si : -1;
     p.c[i].wp = wp[i];
     smem = std::max(smem, (size_t)cls[i].ntaps * g.Ci * g.Co * sizeof(float));
     maxtot = std::max<int64_t>(maxtot, (int64_t)g.N * cls[i].Hg * cls[i].Wg * (g.Co / 4));
