@@ -418,6 +418,7 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
       if (p.acc_cols <= 512 && p.w_bytes + (size_t)want * p.stage_bytes + fixed <= HALO_SMEM_MAX) { p.nstage = want; found = true; break; }
     }
   if (!found) return false;
+  if (const char* e = getenv("DCGANSR_HALO_NSTAGE")) p.nstage = std::max(1, std::min(p.nstage, atoi(e)));      // timing experiments
   if (p.w_bytes > (1 << 20) || p.stage_bytes > (1 << 20)) return false;      // 16-bit (>> 4) offsets in the table
 
   struct Op { int a_plane, a_off, m, slot0, cl[4], tp[4]; bool init; };
