@@ -85,6 +85,8 @@ for _n in ("conv2d_fwd", "conv2d_dgrad", "conv2d_wgrad", "fullconv2d_fwd", "full
 _SIGS["dcgansr_extract_patches"] = (C.c_int, [_P, _P, _P] + [C.c_int] * 7)
 _SIGS["dcgansr_assemble_patches"] = (C.c_int, [_P, _P, _P] + [C.c_int] * 7)
 _SIGS["dcgansr_stage_patches"] = (C.c_int, [_P, _P, _P] + [C.c_int] * 8)
+_SIGS["dcgansr_psnr"] = (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 3)
+_SIGS["dcgansr_ssim"] = (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 3)
 _SIGS["dcgansr_bench_conv"] = (C.c_int, [_P] + [C.c_int] * 11 + [_F])
 _SIGS.update({
     "dcgansr_bn_fwd_train": (C.c_int, [_P] * 9 + [C.c_int] * 4 + [C.c_float, C.c_float]),

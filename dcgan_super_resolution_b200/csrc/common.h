@@ -111,6 +111,8 @@ void k_upnearest_fwd(St st, const float* x, float* y, int N, int H, int W, int C
 void k_upnearest_bwd(St st, const float* dy, float* dx, int N, int H, int W, int C, int scale);
 void k_extract_patches(St st, const float* img, float* patches, int K, int H, int W, int p, int line, int nper, int stride);
 void k_assemble_patches(St st, const float* patches, float* img, int K, int H, int W, int p, int line, int nper, int stride);
+void k_psnr(St st, const float* a, const float* b, float* out, int n, int64_t per);
+void k_ssim(St st, const float* a, const float* b, float* out, int n, int H, int W);
 void k_avgpool2(St st, const float* x, float* y, int N, int H, int W, int C);
 // criterion forward+backward fused.  label_vec (per-sample, `per` outputs each) or constant.
 // loss_out[0] = sum/n_total ; dx = dL/dx with 1/n_total scaling.  dx may be null.

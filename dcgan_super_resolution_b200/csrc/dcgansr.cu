@@ -1438,6 +1438,23 @@ int dcgansr_stage_patches(dcgansr_ctx* ctx, dcgansr_net* netD, const float* imag
   return 0;
 }
 
+// ---- evaluation metrics: calPSNR / calSSIM of train-gray-3.lua:143-221 on n single-channel image pairs ----
+static int metric_op(dcgansr_ctx* ctx, int which, const float* a, const float* b, float* out, int n, int h, int w) {
+  NEED_CTX(ctx);
+  if (!a || !b || !out || n <= 0 || h <= 0 || w <= 0) return fail(ctx, DCGANSR_ERR_INVALID, "bad argument");
+  Arena ar;
+  const int64_t ni = (int64_t)n * h * w;
+  float *dA = ar.f(ni), *dB = ar.f(ni), *dO = ar.f(n);
+  if (!dA || !dB || !dO) return fail(ctx, DCGANSR_ERR_NOMEM, "device allocation failed");
+  CK(ctx, cudaMemcpyAsync(dA, a, ni * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CK(ctx, cudaMemcpyAsync(dB, b, ni * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  if (which == 0) k_psnr(ctx->st(), dA, dB, dO, n, (int64_t)h * w);
+  else k_ssim(ctx->st(), dA, dB, dO, n, h, w);
+  return d2h(ctx, out, dO, n);
+}
+int dcgansr_psnr(dcgansr_ctx* ctx, const float* a, const float* b, float* out, int n, int h, int w) { return metric_op(ctx, 0, a, b, out, n, h, w); }
+int dcgansr_ssim(dcgansr_ctx* ctx, const float* a, const float* b, float* out, int n, int h, int w) { return metric_op(ctx, 1, a, b, out, n, h, w); }
+
 int dcgansr_generate(dcgansr_ctx* ctx, dcgansr_net* netG, const float* lr_host, int batch, float* sr_host) {
   if (!ctx || !netG || netG->ctx != ctx) return fail(ctx, DCGANSR_ERR_INVALID, "bad argument");
   return dcgansr_net_forward(netG, lr_host, batch, sr_host);

@@ -836,3 +836,78 @@ void k_assemble_patches(St st, const float* patches, float* img, int K, int H, i
   assemble_patches_kernel<<<sc_grid(total), 256, 0, st.s>>>(patches, img, K, H, W, p, line, nper, stride);
   DSR_LAUNCHED(st, "assemble_patches", 8.0 * total, WORK_BYTES);
 }
+
+// ------------------------------------------------------------------------------------------
+// Evaluation metrics of the eval sweeps: calPSNR (train-gray-3.lua:143-151) and calSSIM (:156-221) on
+// batches of single-channel H x W images.  One CTA per image pair, deterministic.
+//   PSNR: MSE = sum((a-b)^2) / (H*W);  10*log10(1/MSE), 99 when MSE == 0.
+//   SSIM: images mapped to [0,255] by (x+1)/2*255, 11x11 Gaussian (sigma 1.5, normalised), 'full' convolution (zero padded,
+//         (H+10) x (W+10) map), K1 = 0.01, K2 = 0.03, L = 255, mean of the SSIM map.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) psnr_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                                                   int64_t per) {
+  __shared__ double red[256];
+  const float* pa = a + (int64_t)blockIdx.x * per;
+  const float* pb = b + (int64_t)blockIdx.x * per;
+  double acc = 0.0;
+  for (int64_t i = threadIdx.x; i < per; i += 256) { const float d = pa[i] - pb[i]; acc += (double)(d * d); }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) { if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off]; __syncthreads(); }
+  if (threadIdx.x == 0) {
+    const double mse = red[0] / (double)per;
+    out[blockIdx.x] = mse > 0.0 ? (float)(10.0 * log(1.0 / mse) / log(10.0)) : 99.f;
+  }
+}
+void k_psnr(St st, const float* a, const float* b, float* out, int n, int64_t per) {
+  if (n <= 0) return;
+  psnr_kernel<<<n, 256, 0, st.s>>>(a, b, out, per);
+  DSR_LAUNCHED(st, "psnr", 8.0 * n * per, WORK_BYTES);
+}
+
+__global__ void __launch_bounds__(256) ssim_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out,
+                                                   int H, int W) {
+  __shared__ float g[11];
+  __shared__ double red[256];
+  if (threadIdx.x < 11) {
+    // image.gaussian(11, 1.5/11): exp(-((i - 6) / 1.5)^2 / 2), i = 1..11; 2-D window = outer product / sum = (g/sum g) x (g/sum g)
+    float s = 0.f;
+    for (int i = 0; i < 11; ++i) { const float d = ((float)(i + 1) - 6.f) / 1.5f; s += expf(-d * d / 2.f); }
+    const float d = ((float)(threadIdx.x + 1) - 6.f) / 1.5f;
+    g[threadIdx.x] = expf(-d * d / 2.f) / s;
+  }
+  __syncthreads();
+  const float* pa = a + (int64_t)blockIdx.x * H * W;
+  const float* pb = b + (int64_t)blockIdx.x * H * W;
+  const int Ho = H + 10, Wo = W + 10;
+  const float C1 = (0.01f * 255.f) * (0.01f * 255.f), C2 = (0.03f * 255.f) * (0.03f * 255.f);
+  double acc = 0.0;
+  for (int o = threadIdx.x; o < Ho * Wo; o += 256) {
+    const int oy = o / Wo, ox = o - oy * Wo;
+    float m1 = 0.f, m2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+    for (int ky = 0; ky < 11; ++ky) {
+      const int y = oy - ky;                      // full convolution: out[oy][ox] = sum_k w[k] * img[oy - ky][ox - kx]
+      if (y < 0 || y >= H) continue;
+      for (int kx = 0; kx < 11; ++kx) {
+        const int x = ox - kx;
+        if (x < 0 || x >= W) continue;
+        const float w = g[ky] * g[kx];
+        const float u = (pa[y * W + x] + 1.f) * 0.5f * 255.f, v = (pb[y * W + x] + 1.f) * 0.5f * 255.f;
+        m1 = fmaf(w, u, m1); m2 = fmaf(w, v, m2);
+        s11 = fmaf(w, u * u, s11); s22 = fmaf(w, v * v, s22); s12 = fmaf(w, u * v, s12);
+      }
+    }
+    const float m11 = m1 * m1, m22 = m2 * m2, m12 = m1 * m2;
+    const float v1 = s11 - m11, v2 = s22 - m22, v12 = s12 - m12;
+    acc += (double)(((2.f * m12 + C1) * (2.f * v12 + C2)) / ((m11 + m22 + C1) * (v1 + v2 + C2)));
+  }
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int off = 128; off > 0; off >>= 1) { if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off]; __syncthreads(); }
+  if (threadIdx.x == 0) out[blockIdx.x] = (float)(red[0] / (double)(Ho * Wo));
+}
+void k_ssim(St st, const float* a, const float* b, float* out, int n, int H, int W) {
+  if (n <= 0) return;
+  ssim_kernel<<<n, 256, 0, st.s>>>(a, b, out, H, W);
+  DSR_LAUNCHED(st, "ssim", 8.0 * n * H * W, WORK_BYTES);
+}

@@ -372,3 +372,23 @@ def stage_patches(ctx: Context, netD: Sequential, images, patch: int, line: int,
     k, h, w = a.shape
     L.check(ctx.lib.dcgansr_stage_patches(ctx.h, netD.h, pa, k, h, w, patch, line, nper, stride, slot), ctx.h)
     return k * nper
+
+
+# ---- evaluation metrics (train-gray-3.lua:143-221) ---------------------------------------------------
+def _metric(ctx: Context, fn, a, b):
+    a_, pa = _f32(a)
+    b_, pb = _f32(b)
+    n, h, w = a_.shape
+    out = np.empty(n, np.float32)
+    L.check(fn(ctx.h, pa, pb, out.ctypes.data_as(C.c_void_p), n, h, w), ctx.h)
+    return out
+
+
+def psnr(ctx: Context, a, b):
+    """calPSNR per image pair; a, b: [n][h][w]."""
+    return _metric(ctx, ctx.lib.dcgansr_psnr, a, b)
+
+
+def ssim(ctx: Context, a, b):
+    """calSSIM per image pair; a, b: [n][h][w] in [-1, 1]."""
+    return _metric(ctx, ctx.lib.dcgansr_ssim, a, b)

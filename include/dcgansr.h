@@ -181,6 +181,12 @@ int dcgansr_assemble_patches(dcgansr_ctx* ctx, const float* patches, float* imag
                              int line, int nper, int stride);
 int dcgansr_stage_patches(dcgansr_ctx* ctx, dcgansr_net* netD, const float* images_host, int k, int h, int w, int patch,
                           int line, int nper, int stride, int slot);
+/* Evaluation metrics of the eval sweeps on n single-channel h x w image pairs (host pointers, one value per pair):
+ * calPSNR (train-gray-3.lua:143-151): 10*log10(1/MSE), MSE = sum((a-b)^2)/(h*w), 99 when MSE == 0;
+ * calSSIM (train-gray-3.lua:156-221): images in [-1,1] mapped to [0,255], 11x11 Gaussian (sigma 1.5) 'full' convolution,
+ * K1 = 0.01, K2 = 0.03, L = 255, mean of the SSIM map. */
+int dcgansr_psnr(dcgansr_ctx* ctx, const float* a, const float* b, float* out, int n, int h, int w);
+int dcgansr_ssim(dcgansr_ctx* ctx, const float* a, const float* b, float* out, int n, int h, int w);
 /* netG:forward on a batch of low-res inputs (eval path, train-gray-3.lua:359-445) */
 int dcgansr_generate(dcgansr_ctx* ctx, dcgansr_net* netG, const float* lr_host, int batch, float* sr_host);
 
