@@ -46,7 +46,7 @@ def build_lib(force: bool = False, verbose: bool = False) -> str:
             continue
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc, *NVCC_FLAGS, "-c", path, "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *os.environ.get("DCGANSR_NVCC_EXTRA", "").split(), "-c", path, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -97,8 +97,14 @@ size_t thin_wgrad_scratch_bytes(const WgradGeom& g) {
   return (size_t)thin_wg_blocks(w) * g.Cp * g.Cq * g.ntaps * sizeof(float);
 }
 
+#ifndef THIN_WG_MINB
+#define THIN_WG_MINB 1
+#endif
+#ifndef THIN_WG_UNR
+#define THIN_WG_UNR 4
+#endif
 template <int CT, int MAXP>
-__global__ void __launch_bounds__(256) thin_wgrad_kernel(const ThinWg w, const float* __restrict__ fat,
+__global__ void __launch_bounds__(256, THIN_WG_MINB) thin_wgrad_kernel(const ThinWg w, const float* __restrict__ fat,
                                                           const float* __restrict__ thin, float* __restrict__ scratch) {
   __shared__ __align__(16) float4 red4[MAXP * CT * 256 > 2560 ? 2560 : MAXP * CT * 256];   // <= 40 KB: [pair][ct][V lanes]
   const int cls = blockIdx.y;
@@ -139,7 +145,7 @@ __global__ void __launch_bounds__(256) thin_wgrad_kernel(const ThinWg w, const f
         if (ty >= 0 && ty < w.Ht) trow[j] = thin + ((int64_t)(n * w.Ht + ty) * w.Wt) * CT;
       }
     }
-    constexpr int UNR = 4;
+    constexpr int UNR = THIN_WG_UNR;
     for (int b0 = bbeg; b0 < bend; b0 += UNR) {
       float4 f[UNR];
 #pragma unroll
