@@ -7,5 +7,5 @@ data-parallel plumbing (``parallel``).  Nothing here computes on the CPU.
 """
 from . import _lib, init, models, nn, parallel  # noqa: F401
 from ._lib import DcgansrError  # noqa: F401
-from .nn import (Context, Sequential, assemble_patches, extract_patches, make_step_cfg, psnr, ssim, stage_batch, stage_patches,  # noqa: F401
-                 train_step, train_step_staged)
+from .nn import (Context, Sequential, assemble_patches, extract_patches, make_step_cfg, psnr, scale_bilinear, ssim, stage_batch, stage_patches,  # noqa: F401
+                 stitch_overlap, train_step, train_step_staged)

@@ -84,6 +84,8 @@ for _n in ("conv2d_fwd", "conv2d_dgrad", "conv2d_wgrad", "fullconv2d_fwd", "full
     _SIGS["dcgansr_" + _n] = _CONV_SIG
 _SIGS["dcgansr_extract_patches"] = (C.c_int, [_P, _P, _P] + [C.c_int] * 7)
 _SIGS["dcgansr_assemble_patches"] = (C.c_int, [_P, _P, _P] + [C.c_int] * 7)
+_SIGS["dcgansr_stitch_overlap"] = (C.c_int, [_P, _P, _P] + [C.c_int] * 6)
+_SIGS["dcgansr_scale_bilinear"] = (C.c_int, [_P, _P, _P] + [C.c_int] * 5)
 _SIGS["dcgansr_stage_patches"] = (C.c_int, [_P, _P, _P] + [C.c_int] * 8)
 _SIGS["dcgansr_psnr"] = (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 3)
 _SIGS["dcgansr_ssim"] = (C.c_int, [_P, _P, _P, _P] + [C.c_int] * 3)

@@ -111,6 +111,9 @@ void k_upnearest_fwd(St st, const float* x, float* y, int N, int H, int W, int C
 void k_upnearest_bwd(St st, const float* dy, float* dx, int N, int H, int W, int C, int scale);
 void k_extract_patches(St st, const float* img, float* patches, int K, int H, int W, int p, int line, int nper, int stride);
 void k_assemble_patches(St st, const float* patches, float* img, int K, int H, int W, int p, int line, int nper, int stride);
+bool stitch_overlap_supported(int p, int L, int ov);
+void k_scale_bilinear(St st, const float* src, float* dst, int N, int H, int W, int DH, int DW);
+void k_stitch_overlap(St st, const float* patches, float* img, int K, int H, int W, int p, int L, int ov, int flags);
 void k_psnr(St st, const float* a, const float* b, float* out, int n, int64_t per);
 void k_ssim(St st, const float* a, const float* b, float* out, int n, int H, int W);
 void k_avgpool2(St st, const float* x, float* y, int N, int H, int W, int C);

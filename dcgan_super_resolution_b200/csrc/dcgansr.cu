@@ -1419,6 +1419,38 @@ int dcgansr_assemble_patches(dcgansr_ctx* ctx, const float* patches, float* imag
   k_assemble_patches(ctx->st(), dP, dI, k, h, w, patch, line, nper, stride);
   return d2h(ctx, images, dI, ni);
 }
+// minimum-error boundary cut stitching of overlapping generated patches (train-gray-patch-batch-overlap.lua:457-694)
+int dcgansr_stitch_overlap(dcgansr_ctx* ctx, const float* patches, float* images, int k, int h, int w, int patch, int overlap, int flags) {
+  NEED_CTX(ctx);
+  if (!images || !patches) return fail(ctx, DCGANSR_ERR_INVALID, "null argument");
+  if (k < 1 || h < 1 || w < 1 || patch < 1 || overlap < 2 || patch <= overlap || h != w)
+    return fail(ctx, DCGANSR_ERR_INVALID, "bad stitch geometry (square images, 2 <= overlap < patch)");
+  if ((h - overlap) % (patch - overlap) != 0) return fail(ctx, DCGANSR_ERR_INVALID, "(fineSize - overlap) must be a multiple of (patchSize - overlap)");
+  const int line = (h - overlap) / (patch - overlap);                 // overlapPatchLine (:387)
+  if (line < 1 || (line - 1) * overlap + patch > h) return fail(ctx, DCGANSR_ERR_INVALID, "patches reach outside the image");
+  if (!stitch_overlap_supported(patch, line, overlap)) return fail(ctx, DCGANSR_ERR_UNSUPPORTED, "stitch: patch <= 32, overlap <= 16, line*line*patch <= 48K");
+  Arena ar;
+  const int64_t ni = (int64_t)k * h * w, np = (int64_t)k * line * line * patch * patch;
+  float *dI = ar.f(ni), *dP = ar.f(np);
+  if (!dI || !dP) return fail(ctx, DCGANSR_ERR_NOMEM, "device allocation failed");
+  CK(ctx, cudaMemcpyAsync(dI, images, ni * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));     // uncovered pixels keep their value
+  CK(ctx, cudaMemcpyAsync(dP, patches, np * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  k_stitch_overlap(ctx->st(), dP, dI, k, h, w, patch, line, overlap, flags);
+  return d2h(ctx, images, dI, ni);
+}
+// image.scale(src, dw, dh) in its default bilinear mode, enlarging only (train-gray-3.lua:399)
+int dcgansr_scale_bilinear(dcgansr_ctx* ctx, const float* src, float* dst, int n, int h, int w, int dh, int dw) {
+  NEED_CTX(ctx);
+  if (!src || !dst || n < 1 || h < 1 || w < 1) return fail(ctx, DCGANSR_ERR_INVALID, "bad scale_bilinear argument");
+  if (dh < h || dw < w) return fail(ctx, DCGANSR_ERR_UNSUPPORTED, "scale_bilinear only enlarges (the reference's use)");
+  Arena ar;
+  const int64_t ns = (int64_t)n * h * w, nd = (int64_t)n * dh * dw;
+  float *dS = ar.f(ns), *dD = ar.f(nd);
+  if (!dS || !dD) return fail(ctx, DCGANSR_ERR_NOMEM, "device allocation failed");
+  CK(ctx, cudaMemcpyAsync(dS, src, ns * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  k_scale_bilinear(ctx->st(), dS, dD, n, h, w, dh, dw);
+  return d2h(ctx, dst, dD, nd);
+}
 // images -> device -> the patches become the staged batch of `slot` (k * nper samples of 1 x patch x patch): the patch
 // scripts' real_none without the per-pixel host loop (train-gray-patch.lua:267-275)
 int dcgansr_stage_patches(dcgansr_ctx* ctx, dcgansr_net* netD, const float* images_host, int k, int h, int w, int patch, int line, int nper,

@@ -838,6 +838,86 @@ void k_assemble_patches(St st, const float* patches, float* img, int K, int H, i
 }
 
 // ------------------------------------------------------------------------------------------
+// Overlap stitching by a minimum-error boundary cut (train-gray-patch-batch-overlap.lua:457-694).
+// The reference walks the L x L patches in index order and every patch rewrites its whole p x p footprint, so the value of
+// an image pixel is decided by the LAST patch covering it, (x, y) = (min(L-1, r/ov), min(L-1, c/ov)), and by that patch's
+// last write: the left seam when y > 0, else the top seam when x > 0, else a plain copy.  All seams read generated pixels
+// only, never stitched output, so they are independent: one CTA per image, one thread per seam for the (p x ov)-cell
+// programme (float64 tables like the reference's DoubleTensors -> identical cuts), then one gather per pixel.
+// Top-seam costs are taken against patch i-1 (reference quirk, :557) unless flags & 1.
+// ------------------------------------------------------------------------------------------
+#define STITCH_MAXP 32
+#define STITCH_MAXOV 16
+__global__ void __launch_bounds__(256) stitch_overlap_kernel(const float* __restrict__ patches, float* __restrict__ img, int H, int W,
+                                                             int p, int L, int ov, int flags) {
+  extern __shared__ unsigned char s_idx[];                 // [L*L][p]: pixels taken from the neighbour on each line of the seam
+  const int n = L * L;
+  const float* P = patches + (int64_t)blockIdx.x * n * p * p;
+  double path[STITCH_MAXP * STITCH_MAXOV];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int x = i / L, y = i % L;
+    if (i == 0) continue;
+    const bool left = y != 0;
+    const float* cur = P + (int64_t)i * p * p;
+    const float* nb = P + (int64_t)((left || !(flags & 1)) ? i - 1 : i - L) * p * p;
+    // line = the direction the cut runs along (rows for a left seam, columns for a top seam); cross = across the strip
+    const int sl = left ? p : 1, sc = left ? 1 : p, noff = left ? p - ov : (p - ov) * p;
+    for (int b = 0; b < ov; ++b) path[b] = fabs((double)nb[noff + b * sc] - (double)cur[b * sc]);
+    for (int a = 1; a < p; ++a)
+      for (int b = 0; b < ov; ++b) {
+        const double* pr = path + (a - 1) * ov;
+        double m = pr[b];
+        if (b > 0) m = fmin(m, pr[b - 1]);
+        if (b < ov - 1) m = fmin(m, pr[b + 1]);
+        path[a * ov + b] = fabs((double)nb[noff + a * sl + b * sc] - (double)cur[a * sl + b * sc]) + m;
+      }
+    unsigned char* idx = s_idx + i * p;
+    int k = 0;
+    {
+      const double* pr = path + (p - 1) * ov;
+      double m = pr[0];
+      for (int b = 1; b < ov; ++b) m = fmin(m, pr[b]);
+      for (int b = 0; b < ov; ++b) if (pr[b] == m) k = b;            // the last minimum wins
+    }
+    idx[p - 1] = (unsigned char)(k + 1);
+    for (int a = p - 2; a >= 0; --a) {
+      const double* pr = path + a * ov;
+      if (k == 0) k = (pr[0] <= pr[1]) ? 0 : 1;
+      else if (k == ov - 1) k = (pr[ov - 1] <= pr[ov - 2]) ? ov - 1 : ov - 2;
+      else {
+        const double m3 = fmin(pr[k], fmin(pr[k - 1], pr[k + 1]));
+        k = (pr[k] == m3) ? k : (pr[k + 1] == m3) ? k + 1 : k - 1;
+      }
+      idx[a] = (unsigned char)(k + 1);
+    }
+    (void)x;
+  }
+  __syncthreads();
+  float* out = img + (int64_t)blockIdx.x * H * W;
+  const int cover = (L - 1) * ov + p;
+  for (int px = threadIdx.x; px < H * W; px += blockDim.x) {
+    const int r = px / W, c = px % W;
+    if (r >= cover || c >= cover) continue;                 // no patch reaches here: keeps the caller's value
+    const int x = min(L - 1, r / ov), y = min(L - 1, c / ov);
+    const int a = r - x * ov, b = c - y * ov, i = x * L + y;
+    const float* cur = P + (int64_t)i * p * p;
+    float v;
+    if (y != 0) v = (b < s_idx[i * p + a]) ? P[(int64_t)(i - 1) * p * p + a * p + (p - ov + b)] : cur[a * p + b];
+    else if (x != 0) v = (a < s_idx[i * p + b]) ? P[(int64_t)(i - L) * p * p + (p - ov + a) * p + b] : cur[a * p + b];
+    else v = cur[a * p + b];
+    out[px] = v;
+  }
+}
+bool stitch_overlap_supported(int p, int L, int ov) {
+  return p <= STITCH_MAXP && ov <= STITCH_MAXOV && ov >= 2 && p > ov && L >= 1 && (size_t)L * L * p <= 48 * 1024;
+}
+void k_stitch_overlap(St st, const float* patches, float* img, int K, int H, int W, int p, int L, int ov, int flags) {
+  if (K <= 0) return;
+  stitch_overlap_kernel<<<K, 256, (size_t)L * L * p, st.s>>>(patches, img, H, W, p, L, ov, flags);
+  DSR_LAUNCHED(st, "stitch_overlap", 4.0 * K * ((double)H * W + (double)L * L * p * p), WORK_BYTES);
+}
+
+// ------------------------------------------------------------------------------------------
 // Evaluation metrics of the eval sweeps: calPSNR (train-gray-3.lua:143-151) and calSSIM (:156-221) on
 // batches of single-channel H x W images.  One CTA per image pair, deterministic.
 //   PSNR: MSE = sum((a-b)^2) / (H*W);  10*log10(1/MSE), 99 when MSE == 0.
@@ -910,4 +990,48 @@ void k_ssim(St st, const float* a, const float* b, float* out, int n, int H, int
   if (n <= 0) return;
   ssim_kernel<<<n, 256, 0, st.s>>>(a, b, out, H, W);
   DSR_LAUNCHED(st, "ssim", 8.0 * n * H * W, WORK_BYTES);
+}
+
+// ------------------------------------------------------------------------------------------
+// image.scale(..., 'bilinear') for enlarging sizes: the eval sweeps' baseline (train-gray-3.lua:399).  Separable, end points
+// aligned, width pass then height pass with a float32 intermediate -- evaluated here per output pixel with the same
+// operations in the same order (no fused multiply-add: the CPU code has none).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void lin_coord(int d, int src_len, int dst_len, int& i, float& f, bool& copy) {
+  if (dst_len == src_len || src_len == 1) { i = (src_len == 1) ? 0 : d; f = 0.f; copy = true; return; }
+  if (d == dst_len - 1) { i = src_len - 1; f = 0.f; copy = true; return; }
+  const float scale = __fdiv_rn((float)(src_len - 1), (float)(dst_len - 1));
+  const float sf = __fmul_rn((float)d, scale);
+  i = (int)sf;
+  f = __fsub_rn(sf, (float)i);
+  copy = false;
+}
+__device__ __forceinline__ float lin_mix(float a, float b, float f) {
+  return __fadd_rn(__fmul_rn(__fsub_rn(1.f, f), a), __fmul_rn(f, b));
+}
+__global__ void scale_bilinear_kernel(const float* __restrict__ src, float* __restrict__ dst, int N, int H, int W, int DH, int DW) {
+  const int64_t total = (int64_t)N * DH * DW;
+  const int64_t step = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += step) {
+    const int x = (int)(idx % DW);
+    const int64_t r = idx / DW;
+    const int y = (int)(r % DH);
+    const float* s = src + (r / DH) * H * W;
+    int xi, yi; float fx, fy; bool cx, cy;
+    lin_coord(x, W, DW, xi, fx, cx);
+    lin_coord(y, H, DH, yi, fy, cy);
+    const float t0 = cx ? s[yi * W + xi] : lin_mix(s[yi * W + xi], s[yi * W + xi + 1], fx);
+    float v = t0;
+    if (!cy) {
+      const float t1 = cx ? s[(yi + 1) * W + xi] : lin_mix(s[(yi + 1) * W + xi], s[(yi + 1) * W + xi + 1], fx);
+      v = lin_mix(t0, t1, fy);
+    }
+    dst[idx] = v;
+  }
+}
+void k_scale_bilinear(St st, const float* src, float* dst, int N, int H, int W, int DH, int DW) {
+  const int64_t total = (int64_t)N * DH * DW;
+  if (total <= 0) return;
+  scale_bilinear_kernel<<<sc_grid(total), 256, 0, st.s>>>(src, dst, N, H, W, DH, DW);
+  DSR_LAUNCHED(st, "scale_bilinear", 4.0 * (total + (double)N * H * W), WORK_BYTES);
 }

@@ -367,6 +367,20 @@ def assemble_patches(ctx: Context, patches, images, patch: int, line: int, nper:
     return out
 
 
+def stitch_overlap(ctx: Context, patches, fine: int, patch: int, overlap: int, fix_top_cost: bool = False):
+    """Minimum-error boundary cut stitching (train-gray-patch-batch-overlap.lua:457-694).  patches: [k*L*L][patch][patch] with
+    L = (fine - overlap) / (patch - overlap); returns [k][fine][fine] (zeros where no patch reaches, like the reference)."""
+    p_, pp = _f32(patches)
+    line = (fine - overlap) // (patch - overlap) if patch > overlap else 0
+    if line < 1 or p_.ndim != 3 or p_.shape[0] % (line * line) != 0:
+        raise ValueError("patches must be [k*L*L][patch][patch]")
+    k = p_.shape[0] // (line * line)
+    out = np.zeros((k, fine, fine), np.float32)
+    L.check(ctx.lib.dcgansr_stitch_overlap(ctx.h, pp, out.ctypes.data_as(C.c_void_p), k, fine, fine, patch, overlap,
+                                           1 if fix_top_cost else 0), ctx.h)
+    return out
+
+
 def stage_patches(ctx: Context, netD: Sequential, images, patch: int, line: int, nper: int, stride: int, slot: int):
     a, pa = _f32(images)
     k, h, w = a.shape
@@ -392,3 +406,12 @@ def psnr(ctx: Context, a, b):
 def ssim(ctx: Context, a, b):
     """calSSIM per image pair; a, b: [n][h][w] in [-1, 1]."""
     return _metric(ctx, ctx.lib.dcgansr_ssim, a, b)
+
+
+def scale_bilinear(ctx: Context, images, dst_h: int, dst_w: int):
+    """image.scale(img, dst_w, dst_h) (bilinear, enlarging) per image; images: [n][h][w]  (train-gray-3.lua:399)."""
+    a_, pa = _f32(images)
+    n, h, w = a_.shape
+    out = np.empty((n, dst_h, dst_w), np.float32)
+    L.check(ctx.lib.dcgansr_scale_bilinear(ctx.h, pa, out.ctypes.data_as(C.c_void_p), n, h, w, dst_h, dst_w), ctx.h)
+    return out

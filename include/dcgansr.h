@@ -181,12 +181,25 @@ int dcgansr_assemble_patches(dcgansr_ctx* ctx, const float* patches, float* imag
                              int line, int nper, int stride);
 int dcgansr_stage_patches(dcgansr_ctx* ctx, dcgansr_net* netD, const float* images_host, int k, int h, int w, int patch,
                           int line, int nper, int stride, int slot);
+/* Overlap stitching (train-gray-patch-batch-overlap.lua:457-694): k images' worth of generated patches
+ * [k * line * line][patch][patch], line = (h - overlap) / (patch - overlap) (:387), patch i at (i / line, i % line) * overlap,
+ * are joined along minimum-error boundary cuts (dynamic programme over |neighbour - current| on each overlap strip, float64
+ * cost tables as in the reference) into images [k][h][w]; pixels no patch covers keep the value passed in (the reference
+ * starts from zeros).  The patch order, tie-breaking and the fact that an interior patch's left seam overwrites its top
+ * seam follow the reference.  flags bit 0: take the top-seam cost against the patch above (i - line) instead of the
+ * reference's patch i - 1 (:557). */
+int dcgansr_stitch_overlap(dcgansr_ctx* ctx, const float* patches, float* images, int k, int h, int w, int patch,
+                           int overlap, int flags);
 /* Evaluation metrics of the eval sweeps on n single-channel h x w image pairs (host pointers, one value per pair):
  * calPSNR (train-gray-3.lua:143-151): 10*log10(1/MSE), MSE = sum((a-b)^2)/(h*w), 99 when MSE == 0;
  * calSSIM (train-gray-3.lua:156-221): images in [-1,1] mapped to [0,255], 11x11 Gaussian (sigma 1.5) 'full' convolution,
  * K1 = 0.01, K2 = 0.03, L = 255, mean of the SSIM map. */
 int dcgansr_psnr(dcgansr_ctx* ctx, const float* a, const float* b, float* out, int n, int h, int w);
 int dcgansr_ssim(dcgansr_ctx* ctx, const float* a, const float* b, float* out, int n, int h, int w);
+/* The sweeps' bilinear baseline: image.scale(src, dw, dh) in its default 'bilinear' mode (train-gray-3.lua:399) on n
+ * single-channel h x w images -> dh x dw.  Separable linear interpolation, end points aligned, rows first, float32
+ * intermediate (upstream torch/image).  Only enlarging sizes (dh >= h, dw >= w). */
+int dcgansr_scale_bilinear(dcgansr_ctx* ctx, const float* src, float* dst, int n, int h, int w, int dh, int dw);
 /* netG:forward on a batch of low-res inputs (eval path, train-gray-3.lua:359-445) */
 int dcgansr_generate(dcgansr_ctx* ctx, dcgansr_net* netG, const float* lr_host, int batch, float* sr_host);
 

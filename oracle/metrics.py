@@ -50,3 +50,34 @@ def ssim(a, b):
     s12 = convolve_full(x * y, w) - mu1_mu2
     m = ((2 * mu1_mu2 + C1) * (2 * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s1 + s2 + C2))
     return float(m.mean())
+
+
+def scale_bilinear(img, dst_h, dst_w):
+    """image.scale(src, W, H) in its default 'bilinear' mode, the eval sweeps' baseline (train-gray-3.lua:399,
+    train-gray-patch-batch-overlap.lua:424 -- the `bilinear` argument there is an unset global, i.e. the default).  Upstream
+    torch/image (un-vendored) scales the rows then the columns, each a 1-D linear interpolation with the END POINTS ALIGNED:
+    for dst_len > src_len, scale = (src_len-1)/(dst_len-1), dst[d] = (1-f)*src[i] + f*src[i+1] with i = floor(d*scale),
+    f = d*scale - i, and the last sample copied; float32 arithmetic with a float32 intermediate image.  Only enlarging (or
+    equal) sizes are restated: that is all the reference uses."""
+    src = np.asarray(img, np.float32)
+    assert src.ndim == 2 and dst_h >= src.shape[0] and dst_w >= src.shape[1]
+
+    def lin(x, dst_len):                       # along the last axis
+        src_len = x.shape[-1]
+        if dst_len == src_len:
+            return x.copy()
+        out = np.empty(x.shape[:-1] + (dst_len,), np.float32)
+        if src_len == 1:
+            out[...] = x
+            return out
+        scale = np.float32(src_len - 1) / np.float32(dst_len - 1)
+        d = np.arange(dst_len - 1, dtype=np.float32)
+        sf = d * scale
+        si = sf.astype(np.int64)
+        f = sf - si.astype(np.float32)
+        out[..., :-1] = (np.float32(1) - f) * x[..., si] + f * x[..., si + 1]
+        out[..., -1] = x[..., -1]
+        return out
+
+    tmp = lin(src, dst_w)                      # width first (rows of the source)
+    return lin(tmp.T.copy(), dst_h).T.copy()

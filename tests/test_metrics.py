@@ -34,3 +34,34 @@ def test_gpu_psnr_ssim(ctx, shape):
         assert abs(p[i] - om.psnr(a[i], b[i])) <= 1e-4 * max(1.0, abs(om.psnr(a[i], b[i])))
         assert abs(s[i] - om.ssim(a[i], b[i])) <= 2e-5
     assert p[0] == 99.0 and abs(s[0] - 1.0) <= 2e-6
+
+
+def test_oracle_scale_bilinear_properties():
+    """End points aligned, exact on linear ramps, identity at equal size, agrees with torch's align_corners=True bilinear
+    (an independent implementation of the same definition) to float32 rounding."""
+    import torch
+    import torch.nn.functional as F
+    x = rng(3).uniform(0, 1, (32, 32)).astype(np.float32)
+    y = om.scale_bilinear(x, 64, 64)
+    assert y.shape == (64, 64) and y.dtype == np.float32
+    assert y[0, 0] == x[0, 0] and y[-1, -1] == x[-1, -1] and y[0, -1] == x[0, -1] and y[-1, 0] == x[-1, 0]
+    assert np.array_equal(om.scale_bilinear(x, 32, 32), x)
+    ref = F.interpolate(torch.from_numpy(x)[None, None].double(), size=(64, 64), mode="bilinear", align_corners=True)[0, 0].numpy()
+    assert np.abs(y - ref).max() < 1e-5
+    ramp = np.tile(np.linspace(0, 1, 8, dtype=np.float32), (4, 1))
+    up = om.scale_bilinear(ramp, 4, 15)
+    assert np.abs(up - np.tile(np.linspace(0, 1, 15), (4, 1))).max() < 1e-6
+    assert om.scale_bilinear(np.full((1, 1), 0.25, np.float32), 3, 5).tolist() == [[0.25] * 5] * 3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("geom", [(2, 32, 32, 64, 64), (1, 4, 4, 8, 8), (3, 5, 7, 9, 20), (1, 6, 6, 6, 11), (2, 1, 3, 4, 3)])
+def test_gpu_scale_bilinear_bit_exact(ctx, geom):
+    import dcgan_super_resolution_b200 as dsr
+    n, h, w, dh, dw = geom
+    x = rng(hash(geom) % 2**31).uniform(-1, 1, (n, h, w)).astype(np.float32)
+    got = dsr.scale_bilinear(ctx, x, dh, dw)
+    want = np.stack([om.scale_bilinear(x[i], dh, dw) for i in range(n)])
+    assert np.array_equal(got, want)
+    with pytest.raises(dsr.DcgansrError):
+        dsr.scale_bilinear(ctx, x, h - 1 if h > 1 else 0, dw)
