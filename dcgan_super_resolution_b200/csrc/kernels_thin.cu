@@ -18,6 +18,7 @@
 #include <algorithm>
 
 #define NSM 148
+template <int A> struct ActC { static constexpr int value = A; };   // compile-time int carried through a generic lambda
 #define THIN_MAXP 16      // (tap, thin pixel) pairs per class
 #define THIN_MAXCLS 4
 
@@ -69,13 +70,18 @@ static bool thin_wg_cfg(const WgradGeom& g, ThinWg& w) {
     w.npairs[0] = g.ntaps;
   }
   if (w.Cf % 4 || w.Cf < 4 || w.Cf > 1024 || w.Ct < 1 || w.Ct > 4) return false;
+  if ((int64_t)w.N * ((w.Hf + w.cs - 1) / w.cs) * 64 >= (1ll << 31)) return false;      // 32-bit item index (rows x segments)
   int v = 1;
   while (v < w.Cf / 4) v <<= 1;
   w.V = v; w.PS = 256 / v;
   w.Ha = (w.Hf + w.cs - 1) / w.cs; w.Wa = (w.Wf + w.cs - 1) / w.cs;
   // split rows into segments while there are fewer items than thread slots on the machine
+  // split rows into segments while there are fewer work items than thread slots on the machine (3 resident blocks per SM)
+  // (splitting rows into segments to fill the machine was measured twice, before and after the interior fast path: slower both
+  //  times -- C 16->1 wgrad 34 -> 41 us, D conv 1->64 wgrad 27 -> 36 us; narrow layers get deeper load batches instead, UNR below)
   w.seg = w.Wa; w.nseg = 1;
-  // (splitting rows into segments was measured: the per-block reduction then outweighs the extra parallelism)
+  // (giving the slots of one warp segments of the SAME row, for L1 locality of the thin loads, was slower still: the per-item
+  //  setup of up to 16 pair pointers is paid per segment)
   // block reduction buffer: (pairs per group <= 16 / Ct ... 16) * Ct * V float4 <= 40 KB
   const int grp = w.Ct == 1 ? 16 : (w.Ct == 2 ? 8 : 4);
   if ((size_t)grp * w.Ct * w.V * 4 * sizeof(float) > 40 * 1024) return false;
@@ -87,7 +93,9 @@ static int thin_wg_blocks(const ThinWg& w) {
   const int64_t items = (int64_t)w.N * w.Ha * w.nseg;
   int64_t nb = (items + w.PS - 1) / w.PS;
   const int64_t cap = std::max(1, NSM * 3 / w.ncls);
-  return (int)std::max<int64_t>(1, std::min(nb, cap));
+  if (nb <= cap) return (int)std::max<int64_t>(1, nb);
+  const int64_t rounds = (nb + cap - 1) / cap;             // every block walks the same number of item rounds
+  return (int)((nb + rounds - 1) / rounds);
 }
 
 bool thin_wgrad_supported(const WgradGeom& g) { ThinWg w; return thin_wg_cfg(g, w); }
@@ -97,14 +105,12 @@ size_t thin_wgrad_scratch_bytes(const WgradGeom& g) {
   return (size_t)thin_wg_blocks(w) * g.Cp * g.Cq * g.ntaps * sizeof(float);
 }
 
-#ifndef THIN_WG_MINB
-#define THIN_WG_MINB 1
-#endif
-#ifndef THIN_WG_UNR
-#define THIN_WG_UNR 4
-#endif
-template <int CT, int MAXP>
-__global__ void __launch_bounds__(256, THIN_WG_MINB) thin_wgrad_kernel(const ThinWg w, const float* __restrict__ fat,
+// 3 resident blocks per SM for the 4-accumulator variant (80 registers, no spills): occupancy is what hides the HBM latency
+// of the fat-tensor stream; the bigger variants would spill under that cap.
+#define THIN_WG_MINB(CT, MAXP, UNR) ((CT) * (MAXP) <= 4 ? ((UNR) <= 4 ? 3 : 2) : 1)
+// UNR = fat pixels loaded per thread before they are used
+template <int CT, int MAXP, int UNR>
+__global__ void __launch_bounds__(256, THIN_WG_MINB(CT, MAXP, UNR)) thin_wgrad_kernel(const ThinWg w, const float* __restrict__ fat,
                                                           const float* __restrict__ thin, float* __restrict__ scratch) {
   __shared__ __align__(16) float4 red4[MAXP * CT * 256 > 2560 ? 2560 : MAXP * CT * 256];   // <= 40 KB: [pair][ct][V lanes]
   const int cls = blockIdx.y;
@@ -123,18 +129,22 @@ __global__ void __launch_bounds__(256, THIN_WG_MINB) thin_wgrad_kernel(const Thi
 #pragma unroll
     for (int c = 0; c < CT; ++c) acc[j][c] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  const int64_t items = (int64_t)w.N * w.Ha * w.nseg;
-  for (int64_t item = (int64_t)blockIdx.x * w.PS + slot; item < items; item += (int64_t)gridDim.x * w.PS) {
-    const int64_t row = item / w.nseg;
-    const int bbeg = (int)(item % w.nseg) * w.seg, bend = min(nb, bbeg + w.seg);
-    const int n = (int)(row / w.Ha), a = (int)(row % w.Ha);
+  const int items = w.N * w.Ha * w.nseg;          // < 2^31 (checked by thin_wg_cfg): 32-bit index arithmetic per item
+  auto run = [&](auto tsc) {
+  constexpr int TS = decltype(tsc)::value;        // thin pixels per class pixel along x (1 or 2), compile time: immediate offsets
+  for (int item = blockIdx.x * w.PS + slot; item < items; item += gridDim.x * w.PS) {
+    const int row = item / w.nseg;
+    const int bbeg = (item - row * w.nseg) * w.seg, bend = min(nb, bbeg + w.seg);
+    const int n = row / w.Ha, a = row - n * w.Ha;
     const int fy = a * w.cs + cy;
     if (fy >= w.Hf || !lane_ok) continue;
     const float* frow = fat + ((int64_t)(n * w.Hf + fy) * w.Wf + cx) * w.Cf + lane4 * 4;
     const int64_t fstep = (int64_t)w.cs * w.Cf;
-    // thin row pointers (null when the thin row is outside the image: zero padding)
+    // thin row pointers (null when the thin row is outside the image: zero padding); [bi0, bi1) = class pixels whose thin
+    // pixel is inside the row for every live pair (no bounds checks there)
     const float* trow[MAXP];
     int tx0[MAXP];
+    int bi0 = bbeg, bi1 = bend;
 #pragma unroll
     for (int j = 0; j < MAXP; ++j) {
       trow[j] = nullptr;
@@ -142,12 +152,35 @@ __global__ void __launch_bounds__(256, THIN_WG_MINB) thin_wgrad_kernel(const Thi
       if (j < np) {
         const int ty = a * w.ts + w.oy[cls][j0 + j];
         tx0[j] = w.ox[cls][j0 + j];
-        if (ty >= 0 && ty < w.Ht) trow[j] = thin + ((int64_t)(n * w.Ht + ty) * w.Wt) * CT;
+        if (ty >= 0 && ty < w.Ht) {
+          trow[j] = thin + ((int64_t)(n * w.Ht + ty) * w.Wt) * CT;
+          bi0 = max(bi0, tx0[j] < 0 ? (-tx0[j] + TS - 1) / TS : 0);
+          bi1 = min(bi1, w.Wt - 1 - tx0[j] >= 0 ? (w.Wt - 1 - tx0[j]) / TS + 1 : 0);
+        }
       }
     }
-    constexpr int UNR = THIN_WG_UNR;
     for (int b0 = bbeg; b0 < bend; b0 += UNR) {
       float4 f[UNR];
+      if (b0 >= bi0 && b0 + UNR <= bi1) {
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) f[u] = __ldg(reinterpret_cast<const float4*>(frow + (int64_t)(b0 + u) * fstep));
+#pragma unroll
+        for (int j = 0; j < MAXP; ++j) {
+          if (j < np && trow[j]) {
+            const float* tp = trow[j] + (b0 * TS + tx0[j]) * CT;
+#pragma unroll
+            for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+              for (int c = 0; c < CT; ++c) {
+                const float tv = __ldg(tp + u * TS * CT + c);
+                acc[j][c].x = fmaf(tv, f[u].x, acc[j][c].x); acc[j][c].y = fmaf(tv, f[u].y, acc[j][c].y);
+                acc[j][c].z = fmaf(tv, f[u].z, acc[j][c].z); acc[j][c].w = fmaf(tv, f[u].w, acc[j][c].w);
+              }
+            }
+          }
+        }
+        continue;
+      }
 #pragma unroll
       for (int u = 0; u < UNR; ++u)
         f[u] = b0 + u < bend ? __ldg(reinterpret_cast<const float4*>(frow + (int64_t)(b0 + u) * fstep)) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -156,7 +189,7 @@ __global__ void __launch_bounds__(256, THIN_WG_MINB) thin_wgrad_kernel(const Thi
         if (j < np && trow[j]) {
 #pragma unroll
           for (int u = 0; u < UNR; ++u) {
-            const int tx = (b0 + u) * w.ts + tx0[j];
+            const int tx = (b0 + u) * TS + tx0[j];
             if (tx >= 0 && tx < w.Wt) {
 #pragma unroll
               for (int c = 0; c < CT; ++c) {
@@ -170,10 +203,27 @@ __global__ void __launch_bounds__(256, THIN_WG_MINB) thin_wgrad_kernel(const Thi
       }
     }
   }
+  };
+  if (w.ts == 1) run(ActC<1>{}); else run(ActC<2>{});
 
   // ---- block reduction over the pixel slots (fixed order), then one partial per block ----
-  for (int k = 0; k < w.PS; ++k) {
-    if (slot == k) {
+  // slots that share a warp first (xor butterfly over the slot bits of the lane id), then unit by unit through shared memory
+  if (w.V < 32) {
+    for (int off = 16; off >= w.V; off >>= 1) {
+#pragma unroll
+      for (int j = 0; j < MAXP; ++j)
+#pragma unroll
+        for (int c = 0; c < CT; ++c) {
+          acc[j][c].x += __shfl_xor_sync(0xffffffffu, acc[j][c].x, off); acc[j][c].y += __shfl_xor_sync(0xffffffffu, acc[j][c].y, off);
+          acc[j][c].z += __shfl_xor_sync(0xffffffffu, acc[j][c].z, off); acc[j][c].w += __shfl_xor_sync(0xffffffffu, acc[j][c].w, off);
+        }
+    }
+  }
+  const int units = w.V < 32 ? 8 : w.PS;
+  const int unit = w.V < 32 ? (int)(threadIdx.x >> 5) : slot;
+  const bool writer = w.V < 32 ? (int)(threadIdx.x & 31) < w.V : true;
+  for (int k = 0; k < units; ++k) {
+    if (unit == k && writer) {
 #pragma unroll
       for (int j = 0; j < MAXP; ++j)
         if (j < np) {
@@ -213,16 +263,16 @@ bool k_wgrad_thin(St st, const WgradGeom& g, const float* P, const float* Q, flo
   int maxp = 0;
   for (int c = 0; c < w.ncls; ++c) maxp = std::max(maxp, w.npairs[c]);
   // accumulators: MAXP * CT float4 per thread, kept <= 16 (64 registers); more pairs -> pair groups on blockIdx.z
-#define THIN_LAUNCH(CT, MP)                                                     \
-  do {                                                                          \
-    dim3 grid(nb, w.ncls, (maxp + (MP) - 1) / (MP));                            \
-    thin_wgrad_kernel<CT, MP><<<grid, 256, 0, st.s>>>(w, fat, thin, scratch);   \
+#define THIN_LAUNCH(CT, MP, UNR)                                                    \
+  do {                                                                              \
+    dim3 grid(nb, w.ncls, (maxp + (MP) - 1) / (MP));                                \
+    thin_wgrad_kernel<CT, MP, UNR><<<grid, 256, 0, st.s>>>(w, fat, thin, scratch);  \
   } while (0)
   switch (w.Ct) {
-    case 1: if (maxp <= 4 || !getenv("DCGANSR_THIN16")) THIN_LAUNCH(1, 4); else THIN_LAUNCH(1, 16); break;
-    case 2: if (maxp <= 4) THIN_LAUNCH(2, 4); else THIN_LAUNCH(2, 8); break;
-    case 3: THIN_LAUNCH(3, 4); break;
-    default: THIN_LAUNCH(4, 4); break;
+    case 1: THIN_LAUNCH(1, 4, 4); break;        // (deeper load batches, UNR 8 / 16, measured on the 16-channel layer: no change)
+    case 2: if (maxp <= 4) THIN_LAUNCH(2, 4, 4); else THIN_LAUNCH(2, 8, 4); break;
+    case 3: THIN_LAUNCH(3, 4, 4); break;
+    default: THIN_LAUNCH(4, 4, 4); break;
   }
 #undef THIN_LAUNCH
   DSR_LAUNCHED(st, "wgrad_thin", 4.0 * ((double)g.N * w.Hf * w.Wf * w.Cf + (double)g.N * w.Ht * w.Wt * w.Ct), WORK_BYTES);
@@ -253,6 +303,20 @@ __device__ __forceinline__ float thin_act(float v, int act, float neg) {
   }
 }
 
+// activation with the id known at compile time (A >= 0) or at run time (A == -1: tanh / sigmoid, rare)
+template <int A>
+__device__ __forceinline__ float4 thin_act4(float4 a, int act, float neg) {
+  if (A == ACT_NONE) return a;
+  if (A == ACT_RELU) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); return a; }
+  if (A == ACT_LRELU) {
+    a.x = a.x > 0.f ? a.x : a.x * neg; a.y = a.y > 0.f ? a.y : a.y * neg;
+    a.z = a.z > 0.f ? a.z : a.z * neg; a.w = a.w > 0.f ? a.w : a.w * neg;
+    return a;
+  }
+  a.x = thin_act(a.x, act, neg); a.y = thin_act(a.y, act, neg); a.z = thin_act(a.z, act, neg); a.w = thin_act(a.w, act, neg);
+  return a;
+}
+
 template <int CI, int NT>
 __global__ void __launch_bounds__(256) thin_in_kernel(const ThinIn p, const float* __restrict__ in, float* __restrict__ out) {
   extern __shared__ __align__(16) float sw[];                  // [t][ci][Co]
@@ -276,6 +340,8 @@ __global__ void __launch_bounds__(256) thin_in_kernel(const ThinIn p, const floa
   // interior columns: every tap inside the image, no bounds checks
   const int gx_lo = c.gx_lo, gx_hi = c.gx_hi;
   const int items = p.N * c.Hg * p.nseg;                       // (row, gx segment)
+  auto run = [&](auto actc) {
+  constexpr int A = decltype(actc)::value;
   for (int item = blockIdx.x * PS + slot; item < items; item += gridDim.x * PS) {
     const int row = item / p.nseg, gx0 = (item - row * p.nseg) * p.seg, gx1 = min(c.Wg, gx0 + p.seg);
     const int n = row / c.Hg, gy = row - n * c.Hg;
@@ -295,38 +361,55 @@ __global__ void __launch_bounds__(256) thin_in_kernel(const ThinIn p, const floa
     }
     const int ostep = p.so * p.Co;
     float* o = out + ((int64_t)(n * p.Ho + gy * p.so + c.oy0) * p.Wo + c.ox0) * p.Co + v * 4 + (int64_t)gx0 * ostep;
-    for (int gx = gx0; gx < gx1; ++gx, o += ostep) {
+    // [gx0, ia) and [ib, gx1): columns where some tap falls outside the image (checked); [ia, ib): interior, every tap inside
+    const int ia = clean ? min(max(gx0, gx_lo), gx1) : gx1;
+    const int ib = clean ? max(min(gx1, gx_hi + 1), ia) : gx1;
+    int gx = gx0;
+    auto edge = [&](int gxe) {
       float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (clean && gx >= gx_lo && gx <= gx_hi) {
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-          const float* ip = ir[t] + (gx * p.si + dxs[t]) * CI;
+      for (int t = 0; t < NT; ++t) {
+        const int ix = gxe * p.si + dxs[t];
+        if (ir[t] && ix >= 0 && ix < p.Wi) {
 #pragma unroll
           for (int ci = 0; ci < CI; ++ci) {
-            const float x = __ldg(ip + ci);
+            const float x = __ldg(ir[t] + ix * CI + ci);
             const float4 w = WREG ? wr[t * CI + ci] : wv[(t * CI + ci) * V];
             acc.x = fmaf(x, w.x, acc.x); acc.y = fmaf(x, w.y, acc.y); acc.z = fmaf(x, w.z, acc.z); acc.w = fmaf(x, w.w, acc.w);
           }
         }
-      } else {
+      }
+      return acc;
+    };
+    for (; gx < ia; ++gx, o += ostep) *reinterpret_cast<float4*>(o) = thin_act4<A>(edge(gx), p.act, p.neg);
+    if (gx < ib) {
+      const float* ip[NT];                                      // walking input pointers, one per tap (clean: all NT taps live)
+#pragma unroll
+      for (int t = 0; t < NT; ++t) ip[t] = ir[t] + (gx * p.si + dxs[t]) * CI;
+      const int istep = p.si * CI;
+      for (; gx < ib; ++gx, o += ostep) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int t = 0; t < NT; ++t) {
-          const int ix = gx * p.si + dxs[t];
-          if (ir[t] && ix >= 0 && ix < p.Wi) {
 #pragma unroll
-            for (int ci = 0; ci < CI; ++ci) {
-              const float x = __ldg(ir[t] + ix * CI + ci);
-              const float4 w = WREG ? wr[t * CI + ci] : wv[(t * CI + ci) * V];
-              acc.x = fmaf(x, w.x, acc.x); acc.y = fmaf(x, w.y, acc.y); acc.z = fmaf(x, w.z, acc.z); acc.w = fmaf(x, w.w, acc.w);
-            }
+          for (int ci = 0; ci < CI; ++ci) {
+            const float x = __ldg(ip[t] + ci);
+            const float4 w = WREG ? wr[t * CI + ci] : wv[(t * CI + ci) * V];
+            acc.x = fmaf(x, w.x, acc.x); acc.y = fmaf(x, w.y, acc.y); acc.z = fmaf(x, w.z, acc.z); acc.w = fmaf(x, w.w, acc.w);
           }
+          ip[t] += istep;
         }
+        *reinterpret_cast<float4*>(o) = thin_act4<A>(acc, p.act, p.neg);
       }
-      acc.x = thin_act(acc.x, p.act, p.neg); acc.y = thin_act(acc.y, p.act, p.neg);
-      acc.z = thin_act(acc.z, p.act, p.neg); acc.w = thin_act(acc.w, p.act, p.neg);
-      *reinterpret_cast<float4*>(o) = acc;
     }
+    for (; gx < gx1; ++gx, o += ostep) *reinterpret_cast<float4*>(o) = thin_act4<A>(edge(gx), p.act, p.neg);
   }
+  };
+  // one uniform branch per thread instead of a jump table per output value
+  if (p.act == ACT_NONE) run(ActC<ACT_NONE>{});
+  else if (p.act == ACT_RELU) run(ActC<ACT_RELU>{});
+  else if (p.act == ACT_LRELU) run(ActC<ACT_LRELU>{});
+  else run(ActC<-1>{});
 }
 
 bool thin_in_supported(const TapGeom* cls, int ncls) {
