@@ -410,33 +410,63 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradGeom g, const floa
 // A block owns one cp and a chunk of its T*Cq row.  The S partials are summed by 4 split groups (s = g, g+4, ...) over 64
 // element lanes, combined through shared memory in fixed order, and the (t,cq) -> (cq,t) transposition to the Torch7
 // layout happens there too, so both the scratch reads and the master-gradient read-modify-write are coalesced.
-#define WR_CHUNK_MAX 2048
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ scratch, int S, int Cp, int Cq, int T, int ncq,
+#define WR_SMEM_FLOATS 10240                              // shared-memory floats: G split groups x (cq chunk x odd-padded taps)
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ scratch, int S, int Cp, int Cq, int T, int ncq, int G,
                                                            float* __restrict__ grad_master) {
-  __shared__ float part[4][WR_CHUNK_MAX];
+  __shared__ float part[WR_SMEM_FLOATS];
   const int row = T * Cq;                               // elements per cp
   const int nchunk = (Cq + ncq - 1) / ncq;
   const int cp = blockIdx.x / nchunk, cq0 = (blockIdx.x % nchunk) * ncq;
   const int nc = min(ncq, Cq - cq0);                    // cq range of this block
   const int n = nc * T;
-  // 4 split groups x 64 element lanes when there are enough partials, else all 256 threads on elements
-  const int G = S >= 4 ? 4 : 1, E = 256 / G;
+  const int TP = T | 1;                                 // odd row stride: the transposed stores spread over the banks
+  const int gstride = ncq * TP;
+  // G split groups x E element lanes (few elements and hundreds of partials -> many groups)
+  const int E = 256 / G;
   const int lane = threadIdx.x % E, grp = threadIdx.x / E;
   const int64_t total = (int64_t)Cp * row;
-  // read order (t major, cq minor): coalesced along cq; stored transposed ([cq][t]) in shared memory
-  for (int e = lane; e < n; e += E) {
-    const int t = e / nc, c = e - t * nc;
-    const float* src = scratch + (int64_t)cp * row + (int64_t)t * Cq + cq0 + c;
-    float a = 0.f;
-    for (int s = grp; s < S; s += G) a += src[(int64_t)s * total];
-    part[grp][c * T + t] = a;
+  // read order (t major, cq minor): coalesced along cq; stored transposed ([cq][t]) in shared memory.  Partials are added
+  // in ascending split order within a group (4 loads in flight), groups in ascending order afterwards: deterministic.
+  float* mine = part + grp * gstride;
+  if (((nc | cq0 | Cq) & 3) == 0) {
+    const int nc4 = nc >> 2, n4 = nc4 * T;
+    const int64_t total4 = total >> 2;
+    for (int e = lane; e < n4; e += E) {
+      const int t = e / nc4, c = (e - t * nc4) << 2;
+      const float4* src = reinterpret_cast<const float4*>(scratch + (int64_t)cp * row + (int64_t)t * Cq + cq0 + c);
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      int s = grp;
+      for (; s + 3 * G < S; s += 4 * G) {
+        const float4 x0 = __ldcg(src + (int64_t)s * total4), x1 = __ldcg(src + (int64_t)(s + G) * total4);
+        const float4 x2 = __ldcg(src + (int64_t)(s + 2 * G) * total4), x3 = __ldcg(src + (int64_t)(s + 3 * G) * total4);
+        a.x += x0.x; a.y += x0.y; a.z += x0.z; a.w += x0.w;
+        a.x += x1.x; a.y += x1.y; a.z += x1.z; a.w += x1.w;
+        a.x += x2.x; a.y += x2.y; a.z += x2.z; a.w += x2.w;
+        a.x += x3.x; a.y += x3.y; a.z += x3.z; a.w += x3.w;
+      }
+      for (; s < S; s += G) {
+        const float4 x = __ldcg(src + (int64_t)s * total4);
+        a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+      }
+      float* d = mine + c * TP + t;
+      d[0] = a.x; d[TP] = a.y; d[2 * TP] = a.z; d[3 * TP] = a.w;
+    }
+  } else {
+    for (int e = lane; e < n; e += E) {
+      const int t = e / nc, c = e - t * nc;
+      const float* src = scratch + (int64_t)cp * row + (int64_t)t * Cq + cq0 + c;
+      float a = 0.f;
+      for (int s = grp; s < S; s += G) a += src[(int64_t)s * total];
+      mine[c * TP + t] = a;
+    }
   }
   __syncthreads();
   float* dst = grad_master + (int64_t)cp * row + (int64_t)cq0 * T;
-  if (S >= 4) {
-    for (int o = threadIdx.x; o < n; o += 256) dst[o] += ((part[0][o] + part[1][o]) + part[2][o]) + part[3][o];
-  } else {
-    for (int o = threadIdx.x; o < n; o += 256) dst[o] += part[0][o];
+  for (int o = threadIdx.x; o < n; o += 256) {
+    const int c = o / T, i = c * TP + (o - c * T);
+    float a = part[i];
+    for (int g = 1; g < G; ++g) a += part[g * gstride + i];
+    dst[o] += a;
   }
 }
 
@@ -457,11 +487,21 @@ void k_wgrad_simt(St st, const WgradGeom& g, const float* P, const float* Q, flo
 void k_wgrad_reduce(St st, const float* scratch, int S, int Cp, int Cq, int T, float* grad_master) {
   const int64_t row = (int64_t)T * Cq, total = row * Cp;
   if (total <= 0) return;
-  // cq values per block: <= 2048 elements of shared memory, and enough blocks for the machine when the gradient is
-  // small (thin layers: few elements, hundreds of partials)
-  int ncq = std::max(1, std::min(Cq, WR_CHUNK_MAX / T));
-  while (ncq > 4 && (int64_t)Cp * ((Cq + ncq - 1) / ncq) < 2 * NSM) ncq = (ncq + 1) / 2;
+  const int TP = T | 1;
+  const bool v4 = (Cq & 3) == 0;
+  // cq values per block: start from everything that fits one split group's share of shared memory at G = 4, then halve
+  // while there are fewer blocks than the machine wants (thin layers: few elements, hundreds of partials)
+  int ncq = std::max(1, std::min(Cq, WR_SMEM_FLOATS / 4 / TP));
+  if (v4 && ncq >= 4) ncq &= ~3;
+  while (ncq > 4 && (int64_t)Cp * ((Cq + ncq - 1) / ncq) < 2 * NSM) ncq = v4 ? (((ncq + 1) / 2 + 3) & ~3) : (ncq + 1) / 2;
   const int64_t nchunk = (Cq + ncq - 1) / ncq;
-  wgrad_reduce_kernel<<<(unsigned)(Cp * nchunk), 256, 0, st.s>>>(scratch, S, Cp, Cq, T, ncq, grad_master);
+  // element lanes per block (float4 lanes when vectorised) -> split groups: as many as the threads, the partial count and
+  // shared memory allow
+  const int lanes = std::max(1, (v4 && (ncq & 3) == 0 ? ncq / 4 : ncq) * T);
+  int E = 16;
+  while (E < 256 && E < lanes) E <<= 1;
+  int G = 256 / E;
+  while (G > 1 && (G > S || (int64_t)G * ncq * TP > WR_SMEM_FLOATS)) G >>= 1;
+  wgrad_reduce_kernel<<<(unsigned)(Cp * nchunk), 256, 0, st.s>>>(scratch, S, Cp, Cq, T, ncq, G, grad_master);
   DSR_LAUNCHED(st, "wgrad_reduce", 4.0 * total * (S + 2), WORK_BYTES);
 }
