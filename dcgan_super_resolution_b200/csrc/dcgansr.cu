@@ -264,12 +264,21 @@ struct ConvPlan {
   int alloc_device(dcgansr_ctx* ctx) {
     const bool fast = ctx->cfg.precision == DCGANSR_FAST_TF32;
     this->fast = fast;
-    for (auto* v : {&fwd, &dgrad})
+    for (auto* v : {&fwd, &dgrad}) {
+      // the halo kernel also takes contraction widths that are not a multiple of 8 (zero-filled K tail, e.g. the 12 channels
+      // of train.lua's ngf = 12): such a class group gets the TF32 pack too, and is then always run by the halo kernel
+      bool halo_grp = false;
+      if (fast && !v->empty() && v->size() <= 4 && !getenv("DCGANSR_NO_HALO")) {
+        TapGeom gs[4];
+        bool wide = true;
+        for (size_t i = 0; i < v->size(); ++i) { gs[i] = (*v)[i].g; gs[i].N = 1; wide = wide && (*v)[i].A > 4 && (*v)[i].B > 4; }
+        halo_grp = wide && halo_tapconv_supported(gs, (int)v->size());
+      }
       for (auto& c : *v) {
         if (fast) {
           TapGeom g = c.g;
           g.N = 1;
-          if (tc_tapconv_supported(g))
+          if (tc_tapconv_supported(g) || halo_grp)
             CK(ctx, cudaMalloc((void**)&c.bp, std::max<size_t>(tc_packed_elems(c.g.ntaps, c.A, c.B), 4) * sizeof(float)));
         }
         size_t n = std::max<size_t>(c.tapidx.size(), 1);
@@ -278,6 +287,7 @@ struct ConvPlan {
           CK(ctx, cudaMemcpy(c.tapidx_dev, c.tapidx.data(), c.tapidx.size() * sizeof(int), cudaMemcpyHostToDevice));
         CK(ctx, cudaMalloc((void**)&c.wp, std::max<size_t>((size_t)c.g.ntaps * c.A * c.B, 4) * sizeof(float)));
       }
+    }
     // class groups the weights-resident halo kernel will NOT take run on the per-tap kernel: give them the pre-tiled
     // weight images as well (decided once, here: it only depends on the geometry, not on the batch)
     if (fast && !getenv("DCGANSR_NO_BT"))

@@ -301,7 +301,14 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
   memset(&c.tab, 0, sizeof(c.tab));
   const TapGeom& g0 = cls[0];
   const int Ci = g0.Ci;
-  if (!(Ci % 32 == 0 || Ci == 16)) return false;
+  // channel counts: multiples of 32 or 16 map exactly; for si == 1 any multiple of 4 (the reference's ngf = 12 gives 48 / 24 / 12)
+  // is taken with the last K chunk zero-filled by TMA (out-of-bounds channels read as 0, so whatever the weight tile holds
+  // there contributes nothing) and only the K = 8 steps that hold real channels issued
+  // For si == 2 (parity view, rows of 2*Ci floats cut into 32-float planes) a tap's channels start at px*Ci floats into the
+  // row: any multiple of 8 works, the K = 8 steps are addressed individually.
+  const bool exactC = Ci % 32 == 0 || Ci == 16;
+  if (!exactC && getenv("DCGANSR_HALO_EXACT_C")) return false;
+  if (!exactC && !(g0.si == 1 ? (Ci % 4 == 0 && Ci >= 8) : (Ci % 8 == 0 && Ci >= 8))) return false;
   if (g0.si != 1 && g0.si != 2) return false;
   if (g0.si == 2 && (ncls != 1 || g0.so != 1 || g0.Hi % 2 || g0.Wi % 2)) return false;
   if (g0.Hg < 8 || g0.Wg < HALO_TW) return false;            // small images: the per-tap kernel tiles several images
@@ -316,9 +323,14 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
   p.tiles_x = (p.Wg + HALO_TW - 1) / HALO_TW;
   p.tiles_y = (p.Hg + HALO_TH - 1) / HALO_TH;
   p.ntiles = p.N * p.tiles_y * p.tiles_x;
-  p.KBw = Ci % 32 == 0 ? 32 : 16;
-  p.kchunks = Ci / p.KBw;
+  p.KBw = Ci >= 32 ? 32 : 16;
+  p.kchunks = (Ci + p.KBw - 1) / p.KBw;
   p.ksteps = p.KBw / 8;
+  // K = 8 steps of chunk q that hold real channels, and their total per (class, tap)
+  auto ks_of = [&](int q) { return (std::min(p.KBw, Ci - q * p.KBw) + 7) / 8; };
+  int ks_tap = 0;
+  for (int q = 0; q < p.kchunks; ++q) ks_tap += ks_of(q);
+  int tap_kb[HALO_MAXTAPS] = {0};        // si == 2: where a tap's channels start inside the wide pixel row (floats)
   // ---- A planes ----
   if (p.si == 1) {
     p.row_bytes = p.KBw * 4;
@@ -343,11 +355,11 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
     // parity view [N][H/2][2][W/2][2*Ci]: rows of 2*Ci floats; planes = (row parity) x (32-float chunk of the wide pixel)
     p.row_bytes = 128;
     p.a_layout = 2;
-    const int J = std::max(1, 2 * Ci / 32);
-    // x range per column parity when the two parities live in different planes (Ci >= 32); shared otherwise
+    const int J = std::max(1, (2 * Ci + 31) / 32);
+    // x range per column parity when the two parities live in different planes (Ci a multiple of 32); shared otherwise
     int ymin[2] = {1 << 20, 1 << 20}, ymax[2] = {-(1 << 20), -(1 << 20)}, xmin[2] = {1 << 20, 1 << 20}, xmax[2] = {-(1 << 20), -(1 << 20)};
     const TapGeom& g = cls[0];
-    const bool split_px = Ci >= 32;
+    const bool split_px = Ci >= 32 && Ci % 32 == 0;
     for (int t = 0; t < g.ntaps; ++t) {
       const int fy = floordiv2_h(g.dy[t]), py = g.dy[t] - 2 * fy, fx = floordiv2_h(g.dx[t]), px = split_px ? g.dx[t] - 2 * fx : 0;
       ymin[py] = std::min(ymin[py], fy); ymax[py] = std::max(ymax[py], fy);
@@ -373,9 +385,9 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
     p.pitch_bytes = p.PW * p.row_bytes;
     for (int t = 0; t < g.ntaps; ++t) {
       const int fy = floordiv2_h(g.dy[t]), py = g.dy[t] - 2 * fy, fx = floordiv2_h(g.dx[t]), px = g.dx[t] - 2 * fx;
-      const int koff = Ci == 16 ? px * 64 : 0;
-      p.tap_plane[0][t] = (unsigned short)(pyidx[py] * J + (split_px ? px * (Ci / 32) : 0));
-      p.tap_aoff[0][t] = ((fy - ymin[py]) * p.PW + (fx - xmin[split_px ? px : 0])) * p.row_bytes + koff;
+      p.tap_plane[0][t] = (unsigned short)(pyidx[py] * J);          // first plane of the row parity; the K step picks the chunk
+      p.tap_aoff[0][t] = ((fy - ymin[py]) * p.PW + (fx - xmin[split_px ? px : 0])) * p.row_bytes;
+      tap_kb[t] = px * Ci;                                           // floats into the wide (2*Ci) pixel
     }
   }
   p.plane_tx = p.PH * p.PW * p.row_bytes;
@@ -508,7 +520,7 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
     p.nslots = p.ngrp;
     for (int cl = 0; cl < ncls; ++cl) p.cls_nsl[cl] = 0;
     for (int g = 0; g < p.ngrp; ++g) {
-      p.gbeg[g] = (int)ops.size() * p.kchunks * p.ksteps;
+      p.gbeg[g] = (int)ops.size() * ks_tap;
       const int cl = ncls > 1 ? g : 0;
       const int tb = ncls > 1 ? 0 : g * p.ntaps[0] / p.ngrp, te = ncls > 1 ? p.ntaps[cl] : (g + 1) * p.ntaps[0] / p.ngrp;
       p.cls_sl[cl][p.cls_nsl[cl]++] = (unsigned char)g;
@@ -519,7 +531,7 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
       }
     }
   }
-  p.nmma = (int)ops.size() * p.kchunks * p.ksteps;
+  p.nmma = (int)ops.size() * ks_tap;
   if (p.nmma > HALO_MAXMMA) return false;
   p.gbeg[p.ngrp] = p.nmma;
   {
@@ -527,8 +539,11 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
     for (auto& o : ops) {
       for (int j = 0; j < o.m; ++j) { p.tap_wtile[o.cl[j]][o.tp[j]] = (unsigned short)(wt + j); p.tap_wstride[o.cl[j]][o.tp[j]] = (unsigned short)o.m; }
       for (int q = 0; q < p.kchunks; ++q)
-        for (int k = 0; k < p.ksteps; ++k, ++i) {
-          const uint32_t aoff = (uint32_t)(o.a_plane + q) * p.plane_bytes + (uint32_t)o.a_off + k * 32;
+        for (int k = 0; k < ks_of(q); ++k, ++i) {
+          // si == 1: plane = K chunk.  si == 2: the tap's K step sits f floats into the wide pixel row -> plane f / 32
+          const int f = tap_kb[o.tp[0]] + q * p.KBw + k * 8;
+          const uint32_t aoff = p.si == 1 ? (uint32_t)(o.a_plane + q) * p.plane_bytes + (uint32_t)o.a_off + k * 32
+                                          : (uint32_t)(o.a_plane + f / 32) * p.plane_bytes + (uint32_t)o.a_off + (f % 32) * 4;
           const uint32_t woff = (uint32_t)(wt + q * o.m) * p.wtile_bytes + k * 32;
           const uint32_t accum = (o.init && q == 0 && k == 0) ? 0u : 1u;
           // D = f32, A = B = tf32, K-major, M = 128, N = m * Npad

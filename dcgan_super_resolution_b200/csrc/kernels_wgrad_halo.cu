@@ -39,7 +39,10 @@ struct WhParams {
   int N, Hg, Wg, Cp, Cq, T, s;
   int tiles_x, tiles_y, ntiles, tiles_per_cta;
   int ny, nx, npl, Qs, mch, q0_stride;     // row / column shifts per plane, planes, 32-channel chunks of Q, chunks of P per M tile
-  int a5d;                                 // P tile through the 5-D [y][chunk][x] map (Cp % 32 == 0) or a single zero-padded chunk
+  int a5d;                                 // P tile through the 5-D [y][chunk][x] map (Cp >= 32) or a single zero-padded chunk
+  int cstride, nch;                        // channels between the starts of consecutive 32-channel chunks of P (32; less when Cp
+                                           // is not a multiple of 32: the chunks then OVERLAP so that none reads past the pixel),
+                                           // and the number of chunks
   int RA, PW, a_bytes, plane_bytes, stage_bytes, nstage, nmma, ncols, tmem_cols;
   short pl_py[WH_MAXPL], pl_px[WH_MAXPL], pl_oy0[WH_MAXPL], pl_ox0[WH_MAXPL];
   short tap_of[WH_MAXPL][4][4][2];         // [plane][row shift i][col shift i2][16-column half] -> tap index (or -1)
@@ -149,11 +152,13 @@ __global__ void __launch_bounds__(WH_THREADS) wgrad_halo_kernel(const __grid_con
     // ===================== epilogue (once): TMEM -> scratch[cta][cp][t*Cq + cq] =====================
     const int q = warp & 3;                                  // TMEM lane quarter = M atom (row shift, chunk)
     const int ip = q / p.mch, ch = q % p.mch;                // stacked row-shift slot i', chunk inside the M tile
-    const int cp = (mt * p.mch + ch) * 32 + lane;
+    const int chunk = mt * p.mch + ch;
+    const int cp = chunk * p.cstride + lane;
     const int ish = p.ny - 1 - ip;                           // plane-local row shift
     mbar_wait(smem_u32(done), 0);
     tc_fence_after();
-    const bool row_ok = ip < p.ny && cp < p.Cp;
+    // overlapping chunks: a channel is written by the first chunk that holds it
+    const bool row_ok = ip < p.ny && cp < p.Cp && chunk < p.nch && (chunk == 0 || lane >= 32 - p.cstride);
     const int Ntot = p.T * p.Cq;
     float* drow = scratch + (long long)blockIdx.x * p.split_stride + (long long)cp * Ntot;
     for (int pl = 0; pl < p.npl; ++pl)
@@ -212,8 +217,17 @@ static bool wh_cfg(const WgradGeom& g, WhCfg& c) {
   if (g.s != 1 && g.s != 2) return false;
   if (g.s == 2 && (g.Hq % 2 || g.Wq % 2)) return false;
   const bool packed = g.Cq == 16 && g.s == 2;
-  if ((g.Cq % 32 && !packed) || g.Cp % 4 || g.Cp < 8 || g.ntaps < 1 || g.ntaps > DSR_MAX_TAPS) return false;
-  if (!(g.Cp % 32 == 0 || g.Cp <= 32)) return false;
+  // Q channels: 32-float chunks, the last one may run past Cq (into the other column parity or into TMA zero fill): those
+  // accumulator columns are never written out.  P channels: chunks of 32 from the 5-D map, overlapping when Cp % 32 != 0.
+  if (g.Cq % 4 || g.Cq < 8 || g.Cp % 4 || g.Cp < 8 || g.ntaps < 1 || g.ntaps > DSR_MAX_TAPS) return false;
+  if (getenv("DCGANSR_HALO_EXACT_C") && ((g.Cq % 32 && !packed) || !(g.Cp % 32 == 0 || g.Cp <= 32))) return false;
+  p.nch = (g.Cp + 31) / 32;
+  p.cstride = 32;
+  if (g.Cp > 32 && g.Cp % 32) {
+    const int st = (g.Cp - 32) / (p.nch - 1);
+    if ((g.Cp - 32) % (p.nch - 1) || st % 4) return false;
+    p.cstride = st;
+  }
   if (g.Hp < 8 || g.Wp < 8) return false;
   p.N = g.N; p.Hg = g.Hp; p.Wg = g.Wp; p.Cp = g.Cp; p.Cq = g.Cq; p.T = g.ntaps; p.s = g.s;
   // planes and their tap rectangles
@@ -245,9 +259,9 @@ static bool wh_cfg(const WgradGeom& g, WhCfg& c) {
     for (int i = 0; i < npl; ++i)
       if (pls[i].py == py && pls[i].px == px) p.tap_of[i][oy - pls[i].oymin][ox - pls[i].oxmin][packed ? pxr : 0] = (short)t;
   }
-  p.Qs = packed ? 1 : g.Cq / 32;
-  p.a5d = g.Cp % 32 == 0 ? 1 : 0;
-  const int Qp = (g.Cp + 31) / 32;
+  p.Qs = packed ? 1 : (g.Cq + 31) / 32;
+  p.a5d = g.Cp >= 32 ? 1 : 0;
+  const int Qp = p.nch;
   p.mch = std::max(1, std::min(Qp, 4 / p.ny));           // M = ny * mch * 32 <= 128
   if (p.ny * p.mch > 4) return false;
   c.mtiles = (Qp + p.mch - 1) / p.mch;
@@ -310,8 +324,8 @@ bool k_wgrad_halo(St st, const WgradGeom& g, const float* P, const float* Q, flo
   CUresult r;
   if (p.a5d) {
     // [n][y][chunk][x][32]: the box lands as [row][chunk][8 pixels] so that M atoms are 1 KB apart
-    cuuint64_t dims[5] = {32, (cuuint64_t)g.Wp, (cuuint64_t)(g.Cp / 32), (cuuint64_t)g.Hp, (cuuint64_t)g.N};
-    cuuint64_t strides[4] = {(cuuint64_t)g.Cp * 4, 128, (cuuint64_t)g.Wp * g.Cp * 4, (cuuint64_t)g.Hp * g.Wp * g.Cp * 4};
+    cuuint64_t dims[5] = {32, (cuuint64_t)g.Wp, (cuuint64_t)p.nch, (cuuint64_t)g.Hp, (cuuint64_t)g.N};
+    cuuint64_t strides[4] = {(cuuint64_t)g.Cp * 4, (cuuint64_t)p.cstride * 4, (cuuint64_t)g.Wp * g.Cp * 4, (cuuint64_t)g.Hp * g.Wp * g.Cp * 4};
     cuuint32_t box[5] = {32, 8, (cuuint32_t)p.mch, (cuuint32_t)p.RA, 1};
     r = enc(&mapP, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)P, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
             CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);

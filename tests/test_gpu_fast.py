@@ -37,6 +37,12 @@ TC_SHAPES = [
     ("conv", 3, 32, 17, 19, 24, 3, 1, 1),      # stride 1, odd sizes: partial tiles in both directions
     ("full", 2, 32, 16, 12, 16, 4, 2, 1),      # C4 G layer 4 (FC 32->16): wgrad with a 16-channel shifted tensor (packed parities)
     ("conv", 2, 16, 32, 24, 32, 4, 2, 1),      # C4 G layer 5 (C 16->32)
+    # the reference's own ngf = 12 (train.lua:19): channel counts 48 / 24 / 12 on the halo-tile kernel -- zero-filled K tails
+    # (stride 1 side) and K steps that straddle the 32-float planes of the parity view (stride 2 side)
+    ("full", 2, 48, 16, 18, 24, 4, 2, 1),      # train.lua G layer 3 (FC 48->24): fwd Ci = 48, dgrad Ci = 24 through the parity view
+    ("conv", 2, 24, 32, 36, 12, 4, 2, 1),      # train.lua G layer 4 (C 24->12): fwd Ci = 24 parity view, dgrad Ci = 12
+    ("conv", 1, 48, 24, 32, 40, 3, 1, 1),      # stride 1, Ci = 48, Co = 40
+    ("full", 1, 96, 16, 32, 48, 4, 2, 1),      # train.lua G layer 2: dgrad Ci = 48 through the parity view (3 planes per row parity)
 ]
 
 
