@@ -46,7 +46,10 @@ bool tc_init(std::string* err) {
   return true;
 }
 
-static inline int kb_of(int C) { return C % 32 == 0 ? 32 : (C % 16 == 0 ? 16 : (C % 8 == 0 ? 8 : 0)); }
+// K block (floats per TMA row): 32 / 16 when the channel count is a multiple; other multiples of 8 from 24 up take 32 with a
+// partial last block per tap, of which only the K = 8 steps that hold real channels are issued (24 -> 3 steps, 40 -> 4 + 1);
+// (48 as 32 + 16 instead of 3 x 16 was measured: slower)
+static inline int kb_of(int C) { return C % 32 == 0 ? 32 : (C % 16 == 0 ? 16 : (C % 8 ? 0 : (C >= 24 ? 32 : 8))); }
 static inline CUtensorMapSwizzle swz_of(int kb) {
   return kb == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : (kb == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
@@ -183,7 +186,7 @@ __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_con
         if (p.bt[cls])    // one contiguous 1-D bulk copy of the whole BN x 32 tile image instead of BN 128-byte TMA rows
           bulk_load(smem_u32(sB + (size_t)s * p.b_stage_bytes), p.bt[cls] + ((size_t)blockIdx.y * nk_all + kb) * (p.BN * 32), (uint32_t)(p.BN * 128), fb);
         else
-          tma_load_2d(smem_u32(sB + (size_t)s * p.b_stage_bytes), &mapsB.b[cls], fb, kb * p.KB, n0);
+          tma_load_2d(smem_u32(sB + (size_t)s * p.b_stage_bytes), &mapsB.b[cls], fb, t * p.Ci + c * p.KB, n0);
         if (++s == p.nstage) { s = 0; ph ^= 1; }
       }
     }
@@ -199,7 +202,8 @@ __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_con
       if (elect_one()) {
         const uint64_t ad = make_kmajor_desc(smem_u32(sA + (size_t)s * p.a_stage_bytes), p.KB);
         const uint64_t bd = make_kmajor_desc(smem_u32(sB + (size_t)s * p.b_stage_bytes), p.KB);
-        const int ksteps = p.KB >> 3;
+        const int kc = (kb_beg + kb) % p.kchunks;                        // K chunk inside the tap: the last one may be partial
+        const int ksteps = min(p.KB, p.Ci - kc * p.KB) >> 3;
         for (int k = 0; k < ksteps; ++k)
           umma_tf32(tmem_base, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);   // +32 B per K step
         umma_commit(smem_u32(&empty[s]));
@@ -334,7 +338,7 @@ bool k_tapconv_tc_multi(St st, const TapGeom* cls, int ncls, const float* const*
   p.N = g.N; p.Hg = g.Hg; p.Wg = g.Wg; p.Ho = g.Ho; p.Wo = g.Wo; p.Co = g.Co;
   p.so = g.so; p.si = g.si; p.Ci = g.Ci; p.ncls = ncls;
   p.KB = kb_of(g.Ci);
-  p.kchunks = g.Ci / p.KB;
+  p.kchunks = (g.Ci + p.KB - 1) / p.KB;
   p.TW = std::min(pow2_ge(g.Wg), 128);
   p.TH = std::min(pow2_ge(g.Hg), 128 / p.TW);
   p.TB = 128 / (p.TW * p.TH);
