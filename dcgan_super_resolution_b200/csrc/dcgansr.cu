@@ -261,6 +261,17 @@ struct ConvPlan {
     return "";
   }
 
+  // how the weights-resident halo kernel takes a class group: 2 = all sub-pixel classes in one launch, 1 = one launch per class
+  // (the group's weights do not fit shared memory together, each class's do: the input is read once per class, still far less
+  // than once per tap), 0 = not at all
+  static int halo_mode(const TapGeom* gs, int n) {
+    if (n < 1 || n > 4 || getenv("DCGANSR_NO_HALO")) return 0;
+    if (halo_tapconv_supported(gs, n)) return 2;
+    if (n == 1 || getenv("DCGANSR_NO_HALO_PER_CLASS")) return 0;
+    for (int i = 0; i < n; ++i)
+      if (gs[i].Hg > 0 && gs[i].Wg > 0 && !halo_tapconv_supported(gs + i, 1)) return 0;
+    return 1;
+  }
   int alloc_device(dcgansr_ctx* ctx) {
     const bool fast = ctx->cfg.precision == DCGANSR_FAST_TF32;
     this->fast = fast;
@@ -272,7 +283,7 @@ struct ConvPlan {
         TapGeom gs[4];
         bool wide = true;
         for (size_t i = 0; i < v->size(); ++i) { gs[i] = (*v)[i].g; gs[i].N = 1; wide = wide && (*v)[i].A > 4 && (*v)[i].B > 4; }
-        halo_grp = wide && halo_tapconv_supported(gs, (int)v->size());
+        halo_grp = wide && halo_mode(gs, (int)v->size()) != 0;
       }
       for (auto& c : *v) {
         if (fast) {
@@ -296,7 +307,7 @@ struct ConvPlan {
         TapGeom gs[4];
         bool all_tc = true;
         for (size_t i = 0; i < v->size(); ++i) { gs[i] = (*v)[i].g; gs[i].N = 1; all_tc = all_tc && (*v)[i].bp && (*v)[i].A > 4; }
-        if (!all_tc || (*v)[0].A % 32 || !tc_tapconv_multi_ok(gs, (int)v->size()) || halo_tapconv_supported(gs, (int)v->size())) continue;
+        if (!all_tc || (*v)[0].A % 32 || !tc_tapconv_multi_ok(gs, (int)v->size()) || halo_mode(gs, (int)v->size()) != 0) continue;
         for (auto& c : *v)
           CK(ctx, cudaMalloc((void**)&c.bt, std::max<size_t>(tc_bt_elems(c.g.ntaps, c.A, c.B), 4) * sizeof(float)));
       }
@@ -380,11 +391,24 @@ struct ConvPlan {
       const float* bps[4];
       bool all_tc = true;
       for (size_t i = 0; i < v.size(); ++i) { gs[i] = v[i].g; gs[i].N = N; bps[i] = v[i].bp; all_tc = all_tc && v[i].bp && v[i].A > 4; }
-      if (all_tc && !v[0].bt && halo_tapconv_supported(gs, (int)v.size())) {     // (groups with pre-tiled images belong to the per-tap kernel)
+      const int hm = (all_tc && !v[0].bt) ? halo_mode(gs, (int)v.size()) : 0;    // (groups with pre-tiled images belong to the per-tap kernel)
+      if (hm == 2) {
         std::string e;
         if (k_tapconv_halo(ctx->st(), gs, (int)v.size(), bps, in, out, act, neg, &e)) return;
         ctx->err = "tcgen05 halo path: " + e;
         ctx->tc_failed = true;
+        return;
+      }
+      if (hm == 1) {
+        for (size_t i = 0; i < v.size(); ++i) {
+          if (gs[i].Hg <= 0 || gs[i].Wg <= 0) continue;
+          std::string e;
+          if (!k_tapconv_halo(ctx->st(), gs + i, 1, bps + i, in, out, act, neg, &e)) {
+            ctx->err = "tcgen05 halo path: " + e;
+            ctx->tc_failed = true;
+            return;
+          }
+        }
         return;
       }
       const float* bts[4];
