@@ -158,6 +158,8 @@ bool thin_in_supported(const TapGeom* classes, int ncls);
 bool k_tapconv_thin_in(St st, const TapGeom* classes, int ncls, const float* const* wp, const float* in, float* out, int act, float neg);
 bool thin_out_supported(const TapGeom& g);
 bool k_tapconv_thin_out(St st, const TapGeom& g, const float* in, const float* wp, float* out, int act, float neg);
+bool thin_out_px_supported(const TapGeom& g);
+bool k_tapconv_thin_out_px(St st, const TapGeom& g, const float* in, const float* wp, float* out, int act, float neg);
 
 // ---- kernels_tc.cu : tcgen05 / TMA / TMEM implicit-GEMM convolutions (FAST_TF32) --------------
 bool tc_init(std::string* err);                       // resolves cuTensorMapEncodeTiled

@@ -384,6 +384,13 @@ struct ConvPlan {
           if (gs[i].Hg > 0 && gs[i].Wg > 0) k_tapconv_thin_out(ctx->st(), gs[i], in, wps[i], out, act, neg);
         return;
       }
+      // many pixels, 1..4 output channels, and no tensor-core pack (strict mode, or a contraction width the TC kernels do not
+      // take): one thread per output pixel instead of the generic FFMA tile kernel
+      if (thin_out_px_supported(gs[0]) && !v[0].bp) {
+        for (size_t i = 0; i < v.size(); ++i)
+          if (gs[i].Hg > 0 && gs[i].Wg > 0) k_tapconv_thin_out_px(ctx->st(), gs[i], in, wps[i], out, act, neg);
+        return;
+      }
     }
     // spatially large thin layers: one weights-resident halo launch for all sub-pixel classes
     if (!v.empty() && v.size() <= 4 && !getenv("DCGANSR_NO_HALO")) {

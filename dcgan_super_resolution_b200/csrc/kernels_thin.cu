@@ -317,6 +317,9 @@ __device__ __forceinline__ float4 thin_act4(float4 a, int act, float neg) {
   return a;
 }
 
+#ifndef THIN_IN_UNR
+#define THIN_IN_UNR 4
+#endif
 template <int CI, int NT>
 __global__ void __launch_bounds__(256) thin_in_kernel(const ThinIn p, const float* __restrict__ in, float* __restrict__ out) {
   extern __shared__ __align__(16) float sw[];                  // [t][ci][Co]
@@ -387,6 +390,9 @@ __global__ void __launch_bounds__(256) thin_in_kernel(const ThinIn p, const floa
 #pragma unroll
       for (int t = 0; t < NT; ++t) ip[t] = ir[t] + (gx * p.si + dxs[t]) * CI;
       const int istep = p.si * CI;
+      constexpr int kUnr = NT <= 4 ? THIN_IN_UNR : 1;      // independent accumulator chains in flight per thread (few taps only:
+                                                           // 9 / 16 taps double the registers and lose occupancy)
+#pragma unroll kUnr
       for (; gx < ib; ++gx, o += ostep) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -545,6 +551,72 @@ __global__ void __launch_bounds__(256) thin_out_kernel(const ThinOut p, const fl
     }
     __syncthreads();
   }
+}
+
+// Many pixels, short contraction (G's last conv 12 -> 3 of train.lua:111 when the tensor-core kernels cannot take it: 12 is not a
+// multiple of 8): one thread per output pixel, the whole K = ntaps * Ci contraction in registers, weights in shared memory as
+// [tap][4-channel chunk][co] float4 so that a chunk costs one 16-byte input load + CO broadcast shared loads + 4*CO FMAs.
+template <int CO>
+__global__ void __launch_bounds__(256) thin_out_px_kernel(const ThinOut p, const float* __restrict__ in, const float* __restrict__ wp,
+                                                           float* __restrict__ out) {
+  extern __shared__ __align__(16) float4 sw4[];                 // [t][c4][co] = w[t][4*c4 .. 4*c4+3][co]
+  const int V = p.Ci >> 2;
+  for (int i = threadIdx.x; i < p.ntaps * V * CO; i += 256) {
+    const int co = i % CO, tc = i / CO;                         // tc = t*V + c4 -> first input channel row (t*Ci + 4*c4)
+    const float* w = wp + (int64_t)tc * 4 * CO + co;
+    sw4[i] = make_float4(w[0], w[CO], w[2 * CO], w[3 * CO]);
+  }
+  __syncthreads();
+  const int64_t npix = (int64_t)p.N * p.Hg * p.Wg;
+  for (int64_t pix = (int64_t)blockIdx.x * 256 + threadIdx.x; pix < npix; pix += (int64_t)gridDim.x * 256) {
+    int64_t q = pix;
+    const int gx = (int)(q % p.Wg); q /= p.Wg;
+    const int gy = (int)(q % p.Hg);
+    const int n = (int)(q / p.Hg);
+    float acc[CO];
+#pragma unroll
+    for (int c = 0; c < CO; ++c) acc[c] = 0.f;
+    for (int t = 0; t < p.ntaps; ++t) {
+      const int iy = gy * p.si + p.dy[t], ix = gx * p.si + p.dx[t];
+      if (iy < 0 || iy >= p.Hi || ix < 0 || ix >= p.Wi) continue;
+      const float4* ip = reinterpret_cast<const float4*>(in + ((int64_t)(n * p.Hi + iy) * p.Wi + ix) * p.Ci);
+      const float4* w = sw4 + t * V * CO;
+      for (int c4 = 0; c4 < V; ++c4) {
+        const float4 x = __ldg(ip + c4);
+#pragma unroll
+        for (int c = 0; c < CO; ++c) {
+          const float4 wv = w[c4 * CO + c];
+          acc[c] = fmaf(x.x, wv.x, fmaf(x.y, wv.y, fmaf(x.z, wv.z, fmaf(x.w, wv.w, acc[c]))));
+        }
+      }
+    }
+    float* o = out + ((int64_t)(n * p.Ho + gy * p.so + p.oy0) * p.Wo + gx * p.so + p.ox0) * p.Co;
+#pragma unroll
+    for (int c = 0; c < CO; ++c) o[c] = thin_act(acc[c], p.act, p.neg);
+  }
+}
+bool thin_out_px_supported(const TapGeom& g) {
+  return g.Co >= 1 && g.Co <= 4 && g.Ci % 4 == 0 && g.Ci >= 4 && g.Ci <= 64 && g.ntaps >= 1 && g.ntaps <= DSR_MAX_TAPS &&
+         (int64_t)g.N * g.Hg * g.Wg > NSM * 32;
+}
+bool k_tapconv_thin_out_px(St st, const TapGeom& g, const float* in, const float* wp, float* out, int act, float neg) {
+  if (!thin_out_px_supported(g)) return false;
+  ThinOut p;
+  memset(&p, 0, sizeof(p));
+  p.N = g.N; p.Hi = g.Hi; p.Wi = g.Wi; p.Ci = g.Ci; p.Ho = g.Ho; p.Wo = g.Wo; p.Co = g.Co; p.Hg = g.Hg; p.Wg = g.Wg;
+  p.si = g.si; p.so = g.so; p.oy0 = g.oy0; p.ox0 = g.ox0; p.ntaps = g.ntaps; p.act = act; p.neg = neg;
+  for (int t = 0; t < g.ntaps; ++t) { p.dy[t] = (short)g.dy[t]; p.dx[t] = (short)g.dx[t]; }
+  const int64_t npix = (int64_t)g.N * g.Hg * g.Wg;
+  const size_t smem = (size_t)g.ntaps * (g.Ci / 4) * g.Co * sizeof(float4);
+  const unsigned nb = (unsigned)std::min<int64_t>((npix + 255) / 256, NSM * 16);
+  switch (g.Co) {
+    case 1: thin_out_px_kernel<1><<<nb, 256, smem, st.s>>>(p, in, wp, out); break;
+    case 2: thin_out_px_kernel<2><<<nb, 256, smem, st.s>>>(p, in, wp, out); break;
+    case 3: thin_out_px_kernel<3><<<nb, 256, smem, st.s>>>(p, in, wp, out); break;
+    default: thin_out_px_kernel<4><<<nb, 256, smem, st.s>>>(p, in, wp, out); break;
+  }
+  DSR_LAUNCHED(st, "tapconv_thin_out_px", 4.0 * ((double)g.N * g.Hi * g.Wi * g.Ci + (double)npix * g.Co), WORK_BYTES);
+  return true;
 }
 
 // only where the contraction is long and the pixels are few (D's final 512 -> 1 conv: 64 outputs of K = 8192); with many

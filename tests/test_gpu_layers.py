@@ -23,6 +23,8 @@ CONV_SHAPES = [
     (1, 8, 7, 9, 20, 3, 2, 1),         # odd sizes, stride 2 with k 3
     (2, 4, 5, 5, 6, 5, 1, 2),          # 5x5 kernel
     (2, 256, 2, 2, 1, 2, 1, 0),        # patch-D final 2x2
+    (3, 12, 96, 80, 3, 4, 2, 1),       # G last layer at size: > 148*32 output pixels -> the pixel-per-thread thin-output kernel
+    (2, 16, 128, 96, 1, 4, 2, 1),      # same with Co = 1 (train-gray.lua:116)
 ]
 
 
