@@ -92,7 +92,8 @@ static bool thin_wg_cfg(const WgradGeom& g, ThinWg& w) {
 static int thin_wg_blocks(const ThinWg& w) {
   const int64_t items = (int64_t)w.N * w.Ha * w.nseg;
   int64_t nb = (items + w.PS - 1) / w.PS;
-  const int64_t cap = std::max(1, NSM * 3 / w.ncls);
+  const int resident = w.Ct == 1 ? 3 : (w.Ct <= 3 ? 2 : 1);        // blocks per SM the launch bounds allow (THIN_WG_MINB)
+  const int64_t cap = std::max(1, NSM * resident / w.ncls);
   if (nb <= cap) return (int)std::max<int64_t>(1, nb);
   const int64_t rounds = (nb + cap - 1) / cap;             // every block walks the same number of item rounds
   return (int)((nb + rounds - 1) / rounds);
@@ -107,7 +108,7 @@ size_t thin_wgrad_scratch_bytes(const WgradGeom& g) {
 
 // 3 resident blocks per SM for the 4-accumulator variant (80 registers, no spills): occupancy is what hides the HBM latency
 // of the fat-tensor stream; the bigger variants would spill under that cap.
-#define THIN_WG_MINB(CT, MAXP, UNR) ((CT) * (MAXP) <= 4 ? ((UNR) <= 4 ? 3 : 2) : 1)
+#define THIN_WG_MINB(CT, MAXP, UNR) ((CT) * (MAXP) <= 4 ? ((UNR) <= 4 ? 3 : 2) : ((CT) * (MAXP) <= 12 ? 2 : 1))
 // UNR = fat pixels loaded per thread before they are used
 template <int CT, int MAXP, int UNR>
 __global__ void __launch_bounds__(256, THIN_WG_MINB(CT, MAXP, UNR)) thin_wgrad_kernel(const ThinWg w, const float* __restrict__ fat,
