@@ -181,6 +181,7 @@ struct ConvPlan {
   int cin = 0, cout = 0, k = 0, s = 1, p = 0, adj = 0;
   int Hin = 0, Win = 0, Hout = 0, Wout = 0, T = 0;
   std::vector<TapClass> fwd, dgrad;
+  int hmode_fwd = -1, hmode_dgrad = -1;      // halo_mode() of the two class groups, decided once in alloc_device (host cost per launch)
   WgradGeom wg;
   bool device = false;
 
@@ -268,8 +269,13 @@ struct ConvPlan {
     if (n < 1 || n > 4 || getenv("DCGANSR_NO_HALO")) return 0;
     if (halo_tapconv_supported(gs, n)) return 2;
     if (n == 1 || getenv("DCGANSR_NO_HALO_PER_CLASS")) return 0;
-    for (int i = 0; i < n; ++i)
-      if (gs[i].Hg > 0 && gs[i].Wg > 0 && !halo_tapconv_supported(gs + i, 1)) return 0;
+    // only for spatially large classes (>= 16 tiles of 16 x 8 per image): every CTA reloads its class's weights, which a small
+    // discriminator-sized grid does not amortise (D conv 64->128 dgrad, 16 x 16 per class: 41 us against 27 us per-tap)
+    for (int i = 0; i < n; ++i) {
+      if (gs[i].Hg <= 0 || gs[i].Wg <= 0) continue;
+      if ((int64_t)gs[i].Hg * gs[i].Wg < 16 * 128 && !getenv("DCGANSR_HALO_ALL")) return 0;
+      if (!halo_tapconv_supported(gs + i, 1)) return 0;
+    }
     return 1;
   }
   int alloc_device(dcgansr_ctx* ctx) {
@@ -283,7 +289,9 @@ struct ConvPlan {
         TapGeom gs[4];
         bool wide = true;
         for (size_t i = 0; i < v->size(); ++i) { gs[i] = (*v)[i].g; gs[i].N = 1; wide = wide && (*v)[i].A > 4 && (*v)[i].B > 4; }
-        halo_grp = wide && halo_mode(gs, (int)v->size()) != 0;
+        const int hm = halo_mode(gs, (int)v->size());
+        (v == &fwd ? hmode_fwd : hmode_dgrad) = hm;
+        halo_grp = wide && hm != 0;
       }
       for (auto& c : *v) {
         if (fast) {
@@ -307,7 +315,7 @@ struct ConvPlan {
         TapGeom gs[4];
         bool all_tc = true;
         for (size_t i = 0; i < v->size(); ++i) { gs[i] = (*v)[i].g; gs[i].N = 1; all_tc = all_tc && (*v)[i].bp && (*v)[i].A > 4; }
-        if (!all_tc || (*v)[0].A % 32 || !tc_tapconv_multi_ok(gs, (int)v->size()) || halo_mode(gs, (int)v->size()) != 0) continue;
+        if (!all_tc || (*v)[0].A % 32 || !tc_tapconv_multi_ok(gs, (int)v->size()) || (v == &fwd ? hmode_fwd : hmode_dgrad) > 0) continue;
         for (auto& c : *v)
           CK(ctx, cudaMalloc((void**)&c.bt, std::max<size_t>(tc_bt_elems(c.g.ntaps, c.A, c.B), 4) * sizeof(float)));
       }
@@ -372,7 +380,7 @@ struct ConvPlan {
           }
         }
   }
-  static void run_classes(dcgansr_ctx* ctx, std::vector<TapClass>& v, const float* in, float* out, int N, int act, float neg) {
+  static void run_classes(dcgansr_ctx* ctx, std::vector<TapClass>& v, int hmode, const float* in, float* out, int N, int act, float neg) {
     // 1..4-channel side: streaming fp32 kernels (both precisions)
     if (!v.empty() && v.size() <= 4 && !getenv("DCGANSR_NO_THIN")) {
       TapGeom gs[4];
@@ -398,7 +406,7 @@ struct ConvPlan {
       const float* bps[4];
       bool all_tc = true;
       for (size_t i = 0; i < v.size(); ++i) { gs[i] = v[i].g; gs[i].N = N; bps[i] = v[i].bp; all_tc = all_tc && v[i].bp && v[i].A > 4; }
-      const int hm = (all_tc && !v[0].bt) ? halo_mode(gs, (int)v.size()) : 0;    // (groups with pre-tiled images belong to the per-tap kernel)
+      const int hm = (all_tc && !v[0].bt) ? (hmode >= 0 ? hmode : halo_mode(gs, (int)v.size())) : 0;    // (groups with pre-tiled images belong to the per-tap kernel)
       if (hm == 2) {
         std::string e;
         if (k_tapconv_halo(ctx->st(), gs, (int)v.size(), bps, in, out, act, neg, &e)) return;
@@ -442,8 +450,8 @@ struct ConvPlan {
       k_tapconv_simt(ctx->st(), g, in, c.wp, out, act, neg);
     }
   }
-  void forward(dcgansr_ctx* ctx, const float* in, float* out, int N, int act, float neg) { run_classes(ctx, fwd, in, out, N, act, neg); }
-  void dgrad_run(dcgansr_ctx* ctx, const float* dy, float* dx, int N) { run_classes(ctx, dgrad, dy, dx, N, ACT_NONE, 0.f); }
+  void forward(dcgansr_ctx* ctx, const float* in, float* out, int N, int act, float neg) { run_classes(ctx, fwd, hmode_fwd, in, out, N, act, neg); }
+  void dgrad_run(dcgansr_ctx* ctx, const float* dy, float* dx, int N) { run_classes(ctx, dgrad, hmode_dgrad, dy, dx, N, ACT_NONE, 0.f); }
   bool fast = false;       // FAST_TF32: tensor-core wgrad when the geometry allows
   size_t wscratch_bytes(int N) const {
     WgradGeom g = wg;

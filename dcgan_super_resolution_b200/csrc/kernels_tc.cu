@@ -196,14 +196,16 @@ __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_con
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
     int s = 0;
     uint32_t ph = 0;
+    int kc = kb_beg % p.kchunks;                                              // K chunk inside the tap (no division in the issue loop)
+    const int ksteps_full = p.KB >> 3, ksteps_last = (p.Ci - (p.kchunks - 1) * p.KB) >> 3;
     for (int kb = 0; kb < nk; ++kb) {
       mbar_wait(smem_u32(&full[s]), ph);
       tc_fence_after();
+      const int ksteps = kc == p.kchunks - 1 ? ksteps_last : ksteps_full;        // the last K chunk of a tap may be partial
+      if (++kc == p.kchunks) kc = 0;
       if (elect_one()) {
         const uint64_t ad = make_kmajor_desc(smem_u32(sA + (size_t)s * p.a_stage_bytes), p.KB);
         const uint64_t bd = make_kmajor_desc(smem_u32(sB + (size_t)s * p.b_stage_bytes), p.KB);
-        const int kc = (kb_beg + kb) % p.kchunks;                        // K chunk inside the tap: the last one may be partial
-        const int ksteps = min(p.KB, p.Ci - kc * p.KB) >> 3;
         for (int k = 0; k < ksteps; ++k)
           umma_tf32(tmem_base, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);   // +32 B per K step
         umma_commit(smem_u32(&empty[s]));
