@@ -43,6 +43,14 @@ void k_pack_taps(St st, const float* master, float* wp, int ntaps, const int* ta
 // all weight packs of a net in ONE launch (after every Adam step): jobs[j] covers flat elements [begin_j, begin_{j+1})
 // ------------------------------------------------------------------------------------------
 #define PACK_MAXJOBS 128
+// x / d and x % d with a shift when d is a power of two (the DCGAN widths 64 ... 512, 16 taps): the runtime divisions were most
+// of this kernel's instructions
+__device__ __forceinline__ uint32_t fast_divmod(uint32_t x, uint32_t d, uint32_t& rem) {
+  if ((d & (d - 1)) == 0) { rem = x & (d - 1); return x >> (__ffs((int)d) - 1); }
+  const uint32_t q = x / d;
+  rem = x - q * d;
+  return q;
+}
 __global__ void pack_all_kernel(const PackJob* __restrict__ jobs, int njobs, int64_t total) {
   __shared__ int64_t sbeg[PACK_MAXJOBS + 1];
   for (int i = threadIdx.x; i <= njobs && i <= PACK_MAXJOBS; i += blockDim.x) sbeg[i] = jobs[i].begin;     // jobs[njobs] = sentinel
@@ -57,24 +65,28 @@ __global__ void pack_all_kernel(const PackJob* __restrict__ jobs, int njobs, int
     const PackJob& j = jobs[lo];
     const uint32_t l = (uint32_t)(i - sbeg[lo]);        // a job has < 2^31 elements: 32-bit index arithmetic
     const uint32_t A = (uint32_t)j.A, B = (uint32_t)j.B, T = (uint32_t)j.ntaps;
+    const uint32_t sa = (uint32_t)j.sa, sb = (uint32_t)j.sb;      // a master tensor has < 2^31 elements
     if (j.tc == 2) {                        // pre-tiled, pre-swizzled smem images: [n tile][k block][bn rows][32 floats]
       const uint32_t BNr = (uint32_t)j.bn, nk = T * A / 32;
-      const uint32_t c = l & 31, r = (l >> 5) % BNr, q = (l >> 5) / BNr, kb = q % nk, nt = q / nk;
+      uint32_t r, kb, a;
+      const uint32_t c = l & 31, q = fast_divmod(l >> 5, BNr, r), nt = fast_divmod(q, nk, kb);
       const uint32_t kcol = ((((c >> 2) ^ (r & 7)) << 2) | (c & 3));       // SWIZZLE_128B: 16-byte chunk index ^ (row & 7)
-      const uint32_t k = kb * 32 + kcol, t = k / A, a = k - t * A, n = nt * BNr + r;
-      float v = n < B ? j.src[(int64_t)a * j.sa + (int64_t)n * j.sb + j.tapidx[t]] : 0.f;
+      const uint32_t k = kb * 32 + kcol, t = fast_divmod(k, A, a), n = nt * BNr + r;
+      float v = n < B ? j.src[a * sa + n * sb + (uint32_t)j.tapidx[t]] : 0.f;
       uint32_t u;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
       j.dst[l] = __uint_as_float(u);
     } else if (j.tc) {                      // K-major tensor-core pack bp[b][t*A + a], TF32-rounded
-      const uint32_t a = l % A, r = l / A, t = r % T, b = r / T;
-      float v = j.src[(int64_t)a * j.sa + (int64_t)b * j.sb + j.tapidx[t]];
+      uint32_t a, t;
+      const uint32_t r = fast_divmod(l, A, a), b = fast_divmod(r, T, t);
+      float v = j.src[a * sa + b * sb + (uint32_t)j.tapidx[t]];
       uint32_t u;
       asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
       j.dst[l] = __uint_as_float(u);
     } else {                                // SIMT / streaming pack wp[t][a][b]
-      const uint32_t b = l % B, r = l / B, a = r % A, t = r / A;
-      j.dst[l] = j.src[(int64_t)a * j.sa + (int64_t)b * j.sb + j.tapidx[t]];
+      uint32_t b, a;
+      const uint32_t r = fast_divmod(l, B, b), t = fast_divmod(r, A, a);
+      j.dst[l] = j.src[a * sa + b * sb + (uint32_t)j.tapidx[t]];
     }
   }
 }
