@@ -188,7 +188,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="per-GPU batch override")
     ap.add_argument("--sync-bn", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    ap.add_argument("--cpu-sample-batch", type=int, default=64, help="batch of the CPU arms (bounded sample of the workload)")
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--profile-out", default="", help="write the full per-kernel profile table (JSON) here")
     args = ap.parse_args()
@@ -365,7 +365,7 @@ def main():
     cpu = None
     if not args.no_cpu_baseline:
         try:
-            v, n, dt, cores = oracle_step_rate(args.workload, min(args.cpu_sample_batch, B), 10.0, 4)
+            v, n, dt, cores = oracle_step_rate(args.workload, min(args.cpu_sample_batch, B), 10.0, 40)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"oracle float32 step (PyTorch-CPU restatement of the Torch7 path), {min(args.cpu_sample_batch, B)}-sample "
                              f"batches of {args.workload}, {n} steps in {dt:.1f} s after 1 warm-up"}
