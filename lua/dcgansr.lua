@@ -146,4 +146,44 @@ function M.train_step(ctx, netG, netD, cfg, real)     -- returns errD_real, errD
    return losses[0], losses[1], losses[2]
 end
 
+-- ---------------------------------------------------------------- patches, eval metrics, stitching (SURVEY 8(f))
+-- real_none of the patch scripts without the per-pixel loops (train-gray-patch.lua:267-275): images K x H x W FloatTensor
+function M.stage_patches(ctx, netD, images, patchSize, line, nper, stride, slot)
+   check(lib.dcgansr_stage_patches(ctx, netD.h, images:data(), images:size(1), images:size(2), images:size(3), patchSize, line, nper,
+                                   stride, slot or 0), ctx)
+   return images:size(1) * nper
+end
+function M.extract_patches(ctx, images, patchSize, line, nper, stride)
+   local out = torch.FloatTensor(images:size(1) * nper, patchSize, patchSize)
+   check(lib.dcgansr_extract_patches(ctx, images:data(), out:data(), images:size(1), images:size(2), images:size(3), patchSize, line,
+                                     nper, stride), ctx)
+   return out
+end
+function M.assemble_patches(ctx, patches, images, patchSize, line, nper, stride)     -- images: K x H x W, overwritten where covered
+   check(lib.dcgansr_assemble_patches(ctx, patches:data(), images:data(), images:size(1), images:size(2), images:size(3), patchSize,
+                                      line, nper, stride), ctx)
+   return images
+end
+-- calPSNR / calSSIM (train-gray-3.lua:143-221) on n x H x W pairs -> FloatTensor(n)
+local function metric(fn, ctx, a, b)
+   local out = torch.FloatTensor(a:size(1))
+   check(fn(ctx, a:data(), b:data(), out:data(), a:size(1), a:size(2), a:size(3)), ctx)
+   return out
+end
+function M.calPSNR(ctx, a, b) return metric(lib.dcgansr_psnr, ctx, a, b) end
+function M.calSSIM(ctx, a, b) return metric(lib.dcgansr_ssim, ctx, a, b) end
+-- image.scale(src, W, H) bilinear baseline (train-gray-3.lua:399) on n x h x w -> n x H x W
+function M.scale_bilinear(ctx, src, H, W)
+   local out = torch.FloatTensor(src:size(1), H, W)
+   check(lib.dcgansr_scale_bilinear(ctx, src:data(), out:data(), src:size(1), src:size(2), src:size(3), H, W), ctx)
+   return out
+end
+-- minimum-error boundary cut stitching (train-gray-patch-batch-overlap.lua:457-694): patches (k*L*L) x p x p -> k x fine x fine
+function M.stitch_overlap(ctx, patches, fineSize, patchSize, overlap, k, fix_top_cost)
+   local out = torch.FloatTensor(k or 1, fineSize, fineSize):zero()
+   check(lib.dcgansr_stitch_overlap(ctx, patches:data(), out:data(), k or 1, fineSize, fineSize, patchSize, overlap,
+                                    fix_top_cost and 1 or 0), ctx)
+   return out
+end
+
 return M
