@@ -126,3 +126,43 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".h", ".cpp")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_lua_shim_only_calls_declared_entry_points():
+    """Every lib.dcgansr_* the LuaJIT shim calls is declared inside the header's ffi.cdef block (the shim cannot be executed
+    here: no LuaJIT), with the argument count the declaration has."""
+    src = open(HEADER).read()
+    b = src.index("\n", src.index("FFI-CDEF-BEGIN")) + 1
+    e = src.index("/* FFI-CDEF-END")
+    cdef = re.sub(r"/\*.*?\*/", "", src[b:e], flags=re.S)
+    decl = {m.group(1): m.group(2) for m in re.finditer(r"\b(dcgansr_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", cdef, flags=re.S)}
+    lua = open(os.path.join(ROOT, "lua", "dcgansr.lua")).read()
+    lua = re.sub(r"--[^\n]*", "", lua)
+    used = set(re.findall(r"lib\.(dcgansr_[a-z0-9_]+)", lua))
+    assert len(used) >= 20
+    for name in sorted(used):
+        assert name in decl, f"lua/dcgansr.lua calls {name}, which the ffi.cdef block does not declare"
+
+    def nargs_decl(params):
+        params = params.strip()
+        return 0 if params in ("", "void") else params.count(",") + 1
+
+    def call_args(text, pos):          # argument count of the call whose '(' is at pos
+        depth, n, i, seen = 0, 0, pos, False
+        while i < len(text):
+            ch = text[i]
+            if ch in "({":
+                depth += 1
+            elif ch in ")}":
+                depth -= 1
+                if depth == 0:
+                    return n + 1 if seen else 0
+            elif ch == "," and depth == 1:
+                n += 1
+            elif depth >= 1 and not ch.isspace():
+                seen = True
+            i += 1
+        raise AssertionError("unbalanced call")
+
+    for m in re.finditer(r"lib\.(dcgansr_[a-z0-9_]+)\s*\(", lua):
+        assert call_args(lua, m.end() - 1) == nargs_decl(decl[m.group(1)]), f"argument count of {m.group(1)} in lua/dcgansr.lua"
