@@ -63,6 +63,9 @@ struct HaloParams {
   unsigned char cls_sl[HALO_MAXCLS][4];
   int act;
   float neg;
+  int tstore, st_bytes, st_cls;          // TMA-store epilogue: rows of Co floats staged in shared memory (SWIZZLE_128B pattern), one box
+                                         // per class and tile; bytes of one staging buffer (ncls class blocks) and of a class block
+                                         // (128 pixels x Co*4 B, rounded to 1 KB); two buffers after the A stages
   int dbg;                               // DCGANSR_HALO_DBG (timing experiments only): 1 skip MMAs, 2 skip stores, 4 skip the halo TMA loads
 };
 
@@ -85,7 +88,8 @@ __device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr, uint32_t sbo, ui
 // them.  Per item all TMEM loads (one per accumulator slot of the class) are issued before a single wait.
 template <int ACT>
 __device__ __forceinline__ void halo_epilogue(const HaloParams& p, float* __restrict__ out, uint32_t tmem_base, uint64_t* acc_full,
-                                              uint64_t* acc_empty, int warp, int half, int lane, int n0) {
+                                              uint64_t* acc_empty, int warp, int half, int lane, int n0, const CUtensorMap* mapO,
+                                              uint32_t sO) {
   const int q = warp & 3;                       // TMEM lane quarter this warp may access
   const int r = q * 32 + lane;                  // tile row = pixel
   const int w = r % HALO_TW, h = r / HALO_TW;
@@ -103,6 +107,13 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams& p, float* __rest
     const bool valid = gy < p.Hg && gx < p.Wg && !(p.dbg & 2);
     float* pix = out + ((int64_t)(n * p.Ho + gy * p.so) * p.Wo + gx * p.so) * p.Co + n0;
     const uint32_t cbase = lane_base + (uint32_t)(buf * p.acc_cols);
+    // TMA-store mode: staging buffer it & 1 was the source of the store group issued two tiles ago
+    const bool leader = warp == p.ngrp + 1 && lane == 0;
+    const uint32_t stg = sO + (uint32_t)((it & 1) * p.st_bytes);
+    if (p.tstore) {
+      if (leader) tma_store_wait_read<1>();
+      named_bar_sync(2, 256);
+    }
     mbar_wait(smem_u32(&acc_full[buf]), aph);
     tc_fence_after();
     for (int item = half; item < nitems; item += 2) {
@@ -132,23 +143,50 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams& p, float* __rest
           v[j] = __float_as_uint(sum);
         }
       }
-      if (valid) store_row<ACT, 16>(orow, v, n0 + c0, p.Co, p.neg);
+      if (p.tstore) {
+        // row r of class c: Co floats at pitch Co*4 inside the (1 KB aligned) class block; the SWIZZLE_128B store map expects
+        // byte offset o at o ^ (((o >> 7) & 7) << 4) (16-byte chunk index XOR 128-byte line index, mod 8)
+        const uint32_t blk = stg + (uint32_t)(c * p.st_cls);
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+          if (c0 + j < p.Co) {
+            const uint32_t o = (uint32_t)(r * p.Co + c0 + j) * 4u;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (o ^ (((o >> 7) & 7u) << 4))),
+                         "f"(act_c<ACT>(__uint_as_float(v[j]), p.neg)), "f"(act_c<ACT>(__uint_as_float(v[j + 1]), p.neg)),
+                         "f"(act_c<ACT>(__uint_as_float(v[j + 2]), p.neg)), "f"(act_c<ACT>(__uint_as_float(v[j + 3]), p.neg))
+                         : "memory");
+          }
+        }
+      } else if (valid) store_row<ACT, 16>(orow, v, n0 + c0, p.Co, p.neg);
     }
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+    if (p.tstore) {
+      fence_proxy_async_smem();
+      named_bar_sync(3, 256);
+      if (leader && !(p.dbg & 2)) {
+        const int gy0 = ty * HALO_TH, gx0 = tx * HALO_TW;
+        for (int c = 0; c < p.ncls; ++c)      // output seen as [N][Ho/2][2][Wo/2][2*Co]: class (coy, cox) = row parity, channel offset cox*Co
+          tma_store_5d(mapO, stg + (uint32_t)(c * p.st_cls), p.cox[c] * p.Co, gx0, p.coy[c], gy0, n);
+        tma_store_commit();
+      }
+    }
   }
+  if (p.tstore && warp == p.ngrp + 1 && lane == 0) tma_store_wait_all();
 }
 
 __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                     const __grid_constant__ HaloMaps mapsB,
                                                                     const __grid_constant__ HaloTab tab,
+                                                                    const __grid_constant__ CUtensorMap mapO,
                                                                     const HaloParams p, float* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = smem;
   uint8_t* sA = smem + p.w_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sA + (size_t)p.nstage * p.stage_bytes);
+  uint8_t* sOut = sA + (size_t)p.nstage * p.stage_bytes;                 // TMA-store staging (2 buffers) when p.tstore
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + (size_t)(p.tstore ? 2 * p.st_bytes : 0));
   uint64_t* w_full = bars;
   uint64_t* a_full = bars + 1;
   uint64_t* a_empty = bars + 3;
@@ -269,11 +307,11 @@ __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel
     const int half = (warp - p.ngrp - 1) >> 2;
     // ===================== epilogue: TMEM -> registers -> activation -> NHWC global =====================
     switch (p.act) {
-      case ACT_RELU: halo_epilogue<ACT_RELU>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0); break;
-      case ACT_LRELU: halo_epilogue<ACT_LRELU>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0); break;
-      case ACT_TANH: halo_epilogue<ACT_TANH>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0); break;
-      case ACT_SIGMOID: halo_epilogue<ACT_SIGMOID>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0); break;
-      default: halo_epilogue<ACT_NONE>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0); break;
+      case ACT_RELU: halo_epilogue<ACT_RELU>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut)); break;
+      case ACT_LRELU: halo_epilogue<ACT_LRELU>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut)); break;
+      case ACT_TANH: halo_epilogue<ACT_TANH>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut)); break;
+      case ACT_SIGMOID: halo_epilogue<ACT_SIGMOID>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut)); break;
+      default: halo_epilogue<ACT_NONE>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut)); break;
     }
   }
   tc_fence_before();
@@ -561,6 +599,21 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
   p.tmem_cols = std::max(32, pow2_ge_h(p.nacc * p.acc_cols));
   if (p.tmem_cols > 512) return false;
   c.smem = 1024 + (size_t)p.w_bytes + (size_t)p.nstage * p.stage_bytes + 16 * sizeof(uint64_t);
+  // TMA-store epilogue where an output row fits one 128-byte swizzle row (Co <= 32, one cout slice), the four sub-pixel classes
+  // of a stride-2 output are present (the output viewed as [N][Ho/2][2][Wo/2][2*Co] makes a class one 5-D box per tile) and
+  // two staging buffers still fit beside the resident weights and the halo stages.  The direct epilogue (32-byte vector stores
+  // from 8 warps) tops out near 4 TB/s; the staged one leaves the write-out to the TMA engine (C 32->16 dgrad 148 -> 104 us).
+  p.tstore = 0;
+  p.st_cls = (128 * p.Co * 4 + 1023) / 1024 * 1024;
+  p.st_bytes = ncls * p.st_cls;
+  // (rows narrower than 128 bytes -- Co = 24 / 16 -- were tried with a Co-float box: wrong results, TMA does not pack such rows the
+  //  way the staging writer assumed; only full 128-byte rows are taken)
+  if (p.so == 2 && ncls == 4 && p.Co == 32 && p.Npad == 32 && c.nsplit == 1 && p.Ho % 2 == 0 && p.Wo % 2 == 0 &&
+      c.smem + 2 * (size_t)p.st_bytes <= HALO_SMEM_MAX && !getenv("DCGANSR_HALO_NO_TSTORE")) {
+    bool ok = true;
+    for (int i = 0; i < ncls; ++i) ok = ok && p.coy[i] >= 0 && p.coy[i] < 2 && p.cox[i] >= 0 && p.cox[i] < 2;
+    if (ok) { p.tstore = 1; c.smem += 2 * (size_t)p.st_bytes; }
+  }
   // one persistent CTA per SM (13 warps x ~100 registers; the 8 epilogue warps provide the memory-level parallelism)
   c.grid_x = std::max(1, std::min(p.ntiles, (NSM + c.nsplit - 1) / c.nsplit));
   return true;
@@ -615,6 +668,17 @@ bool k_tapconv_halo(St st, const TapGeom* classes, int ncls, const float* const*
             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled(B, halo) failed: " + std::to_string((int)r); return false; }
   }
+  CUtensorMap mapO;
+  memset(&mapO, 0, sizeof(mapO));
+  if (p.tstore) {
+    cuuint64_t dims[5] = {(cuuint64_t)2 * g.Co, (cuuint64_t)g.Wo / 2, 2, (cuuint64_t)g.Ho / 2, (cuuint64_t)g.N};
+    cuuint64_t strides[4] = {(cuuint64_t)2 * g.Co * 4, (cuuint64_t)g.Wo * g.Co * 4, (cuuint64_t)2 * g.Wo * g.Co * 4,
+                             (cuuint64_t)g.Ho * g.Wo * g.Co * 4};
+    cuuint32_t box[5] = {(cuuint32_t)g.Co, HALO_TW, 1, HALO_TH, 1};
+    r = enc(&mapO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)out, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled(out, halo) failed: " + std::to_string((int)r); return false; }
+  }
   static bool configured = false;
   if (!configured) {
     if (cudaFuncSetAttribute(tapconv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
@@ -624,7 +688,7 @@ bool k_tapconv_halo(St st, const TapGeom* classes, int ncls, const float* const*
     configured = true;
   }
   dim3 grid((unsigned)c.grid_x, (unsigned)c.nsplit);
-  tapconv_halo_kernel<<<grid, 32 * (9 + p.ngrp), c.smem, st.s>>>(mapA, maps, c.tab, p, out);
+  tapconv_halo_kernel<<<grid, 32 * (9 + p.ngrp), c.smem, st.s>>>(mapA, maps, c.tab, mapO, p, out);
   // HBM-bound by construction (input and output once, weights resident): the roofline work of a launch is its
   // algorithmic bytes = input + output + weights (fp32)
   double wbytes = 0;

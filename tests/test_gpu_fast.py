@@ -43,6 +43,9 @@ TC_SHAPES = [
     ("conv", 2, 24, 32, 36, 12, 4, 2, 1),      # train.lua G layer 4 (C 24->12): fwd Ci = 24 parity view, dgrad Ci = 12
     ("conv", 1, 48, 24, 32, 40, 3, 1, 1),      # stride 1, Ci = 48, Co = 40
     ("full", 1, 96, 16, 32, 48, 4, 2, 1),      # train.lua G layer 2: dgrad Ci = 48 through the parity view (3 planes per row parity)
+    ("conv", 1, 32, 40, 36, 16, 4, 2, 1),      # dgrad writes 32 channels through the TMA-store epilogue: ragged tiles both ways (clipped boxes)
+    ("conv", 2, 24, 48, 40, 12, 4, 2, 1),      # dgrad Co = 24: 96-byte rows in the swizzled staging buffer
+    ("full", 1, 32, 24, 20, 16, 4, 2, 1),      # fwd Co = 16: 64-byte rows
     ("conv", 3, 12, 96, 80, 3, 4, 2, 1),       # train.lua G last layer at size: exact-fp32 pixel-per-thread kernel (12 is not a TC width)
 ]
 
