@@ -79,9 +79,24 @@ struct dcgansr_ctx {
   uint64_t graph_seq = 0;
   Prof prof;
   TcWorkspace tcws;
+  std::vector<dcgansr_net*> nets;          // live nets created on this ctx (dcgansr_ctx_destroy detaches them)
   St st() { return St{stream, &launches, &prof, &tcws}; }
   int world() const { return cfg.world_size > 1 && comm ? cfg.world_size : 1; }
 };
+
+// A captured step graph bakes in device pointers (net buffers, the staged batch, lr_buf, label_vec): every entry that could
+// reference a buffer about to be freed is destroyed first.  net == nullptr: all of them.
+static void graphs_invalidate(dcgansr_ctx* ctx, const void* net) {
+  if (!ctx || ctx->graphs.empty()) return;
+  cudaStreamSynchronize(ctx->stream);
+  size_t k = 0;
+  for (size_t i = 0; i < ctx->graphs.size(); ++i) {
+    GraphEntry& g = ctx->graphs[i];
+    if (!net || g.G == net || g.D == net) { if (g.exec) cudaGraphExecDestroy(g.exec); }
+    else ctx->graphs[k++] = g;
+  }
+  ctx->graphs.resize(k);
+}
 
 static int fail(dcgansr_ctx* ctx, int code, const std::string& msg) {
   t_err = msg;
@@ -127,7 +142,7 @@ struct Arena {
 
 static int ensure(dcgansr_ctx* ctx, float** buf, size_t* cap, size_t bytes) {
   if (*cap >= bytes) return 0;
-  if (*buf) { cudaStreamSynchronize(ctx->stream); cudaFree(*buf); *buf = nullptr; *cap = 0; }
+  if (*buf) { graphs_invalidate(ctx, nullptr); cudaStreamSynchronize(ctx->stream); cudaFree(*buf); *buf = nullptr; *cap = 0; }
   CK(ctx, cudaMalloc((void**)buf, bytes));
   *cap = bytes;
   return 0;
@@ -535,6 +550,28 @@ struct dcgansr_net {
   float* other(const float* cur) { return cur == gbuf[0] ? gbuf[1] : gbuf[0]; }
 };
 
+// Frees everything the net holds on the device and detaches it from its context (the handle stays valid as a plan-only net).
+static void net_release_device(dcgansr_net* net) {
+  if (!net || !net->ctx) return;
+  dcgansr_ctx* c = net->ctx;
+  cudaSetDevice(c->cfg.device);
+  cudaStreamSynchronize(c->stream);
+  graphs_invalidate(c, net);          // a re-created net often gets the same heap / device addresses: no stale replay
+  c->nets.erase(std::remove(c->nets.begin(), c->nets.end(), net), c->nets.end());
+  for (auto& m : net->mods) {
+    if (m.conv) m.conv->free_device();
+    if (m.owns_out && m.out) cudaFree(m.out);
+    m.out = nullptr; m.owns_out = false; m.save_mean = nullptr; m.save_invstd = nullptr;
+  }
+  void** ptrs[] = {(void**)&net->params, (void**)&net->grads, (void**)&net->adam_m, (void**)&net->adam_v, (void**)&net->adam_t,
+                   (void**)&net->adam_step, (void**)&net->bn_rmean, (void**)&net->bn_rvar, (void**)&net->bn_save, (void**)&net->in_buf,
+                   (void**)&net->gbuf[0], (void**)&net->gbuf[1], (void**)&net->bn_partials, (void**)&net->bn_sums,
+                   (void**)&net->bn_sums_total, (void**)&net->wscratch, (void**)&net->pack_jobs};
+  for (void** p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+  net->last_out = nullptr; net->last_batch = 0;
+  net->ctx = nullptr;
+}
+
 static int act_of_kind(int kind) {
   switch (kind) {
     case DCGANSR_RELU: return ACT_RELU;
@@ -802,6 +839,14 @@ void dcgansr_ctx_destroy(dcgansr_ctx* ctx) {
   cudaSetDevice(ctx->cfg.device);
   cudaDeviceSynchronize();
   for (auto& g : ctx->graphs) cudaGraphExecDestroy(g.exec);
+  ctx->graphs.clear();
+  // nets that outlive their context (LuaJIT / Python finalizers run in no particular order): release their device memory now
+  // and leave plan-only handles behind, so a later dcgansr_net_destroy never touches this ctx
+  {
+    std::vector<dcgansr_net*> live;
+    live.swap(ctx->nets);
+    for (dcgansr_net* n : live) net_release_device(n);
+  }
   if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
   for (float* p : ctx->slots) if (p) cudaFree(p);
   if (ctx->tcws.part) cudaFree(ctx->tcws.part);
@@ -948,15 +993,9 @@ int dcgansr_comm_init(dcgansr_ctx* ctx, const void* unique_id_128) {
 // ---- net description --------------------------------------------------------------------------
 void dcgansr_net_destroy(dcgansr_net* net) {
   if (!net) return;
-  if (net->ctx) { cudaSetDevice(net->ctx->cfg.device); cudaStreamSynchronize(net->ctx->stream); }
-  for (auto& m : net->mods) {
-    if (m.conv) { m.conv->free_device(); delete m.conv; }
-    if (m.owns_out && m.out) cudaFree(m.out);
-  }
-  void* ptrs[] = {net->params, net->grads, net->adam_m, net->adam_v, net->adam_t, net->adam_step, net->bn_rmean,
-                  net->bn_rvar, net->bn_save, net->in_buf, net->gbuf[0], net->gbuf[1], net->bn_partials, net->bn_sums,
-                  net->bn_sums_total, net->wscratch, net->pack_jobs};
-  for (void* p : ptrs) if (p) cudaFree(p);
+  net_release_device(net);
+  for (auto& m : net->mods)
+    if (m.conv) { delete m.conv; m.conv = nullptr; }
   delete net;
 }
 
@@ -1120,6 +1159,7 @@ int dcgansr_net_create(dcgansr_ctx* ctx, const dcgansr_layer* layers, int n_laye
   // BN running_var starts at 1 (Torch7 init)
   if (net->nbn > 0) k_fill(ctx->st(), net->bn_rvar, net->nbn, 1.f);
   CK(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->nets.push_back(net);
   *out = net;
   return 0;
 }
@@ -1343,6 +1383,8 @@ static int check_step_args(dcgansr_ctx* ctx, dcgansr_net* G, dcgansr_net* D, con
   if (G->out_c != D->in_c || G->out_h != D->in_h || G->out_w != D->in_w)
     return fail(ctx, DCGANSR_ERR_INVALID, "G output shape must equal D input shape");
   if (cfg->loss != DCGANSR_LOSS_BCE && cfg->loss != DCGANSR_LOSS_MSE) return fail(ctx, DCGANSR_ERR_INVALID, "bad loss kind");
+  if (ctx->cfg.world_size > 1 && !ctx->comm)
+    return fail(ctx, DCGANSR_ERR_NCCL, "world_size > 1 but dcgansr_comm_init was never called: the ranks would train unsynchronised replicas");
   return 0;
 }
 

@@ -39,6 +39,8 @@ function M.Context(opt)
                                       sync_bn = opt.sync_bn and 1 or 0, use_graph = opt.use_graph and 1 or 0})
    local out = ffi.new('dcgansr_ctx*[1]')
    check(lib.dcgansr_ctx_create(cfg, out), nil)
+   -- finalizer order between a ctx and its nets is not defined in LuaJIT: dcgansr_ctx_destroy releases the device memory of
+   -- every net still alive and leaves plan-only handles behind, so either order is safe
    return ffi.gc(out[0], lib.dcgansr_ctx_destroy)
 end
 
@@ -143,6 +145,14 @@ end
 local losses = ffi.new('float[3]')
 function M.train_step(ctx, netG, netD, cfg, real)     -- returns errD_real, errD_fake, errG
    check(lib.dcgansr_train_step(ctx, netG.h, netD.h, cfg, real:data(), real:size(1), losses), ctx)
+   return losses[0], losses[1], losses[2]
+end
+-- the same step on a batch already resident on the device (dcgansr.stage_batch / dcgansr.stage_patches filled `slot`)
+function M.stage_batch(ctx, netD, real, slot)
+   check(lib.dcgansr_stage_batch(ctx, netD.h, real:data(), real:size(1), slot or 0), ctx)
+end
+function M.train_step_staged(ctx, netG, netD, cfg, slot, batch)
+   check(lib.dcgansr_train_step_staged(ctx, netG.h, netD.h, cfg, slot or 0, batch, losses), ctx)
    return losses[0], losses[1], losses[2]
 end
 

@@ -166,3 +166,37 @@ def test_lua_shim_only_calls_declared_entry_points():
 
     for m in re.finditer(r"lib\.(dcgansr_[a-z0-9_]+)\s*\(", lua):
         assert call_args(lua, m.end() - 1) == nargs_decl(decl[m.group(1)]), f"argument count of {m.group(1)} in lua/dcgansr.lua"
+
+
+LUA_HOSTS = ["train.lua", "train-gray.lua", "train-gray-patch.lua", "train-gray-patch-batch-overlap.lua"]
+
+
+@pytest.mark.parametrize("host", LUA_HOSTS)
+def test_lua_hosts_use_only_the_shim_surface(host):
+    """The Lua hosts of the BASELINE-named scripts (they cannot be executed here: no LuaJIT) only use names the shim exports,
+    and build the same layer lists as the Python spec builders the parity tests run (so the graphs the GPU tests cover ARE
+    the graphs these hosts create)."""
+    shim = re.sub(r"--[^\n]*", "", open(os.path.join(ROOT, "lua", "dcgansr.lua")).read())
+    exported = set(re.findall(r"function M\.([A-Za-z_][A-Za-z0-9_]*)", shim)) | {"nn", "optim", "lib"}
+    nn_exported = set(re.findall(r"function M\.nn\.([A-Za-z_][A-Za-z0-9_]*)", shim))
+    src = open(os.path.join(ROOT, "lua", host)).read()
+    src = re.sub(r"--\[\[.*?\]\]", "", src, flags=re.S)
+    src = re.sub(r"--[^\n]*", "", src)
+    for name in set(re.findall(r"\bdsr\.([A-Za-z_][A-Za-z0-9_]*)", src)):
+        assert name in exported, f"lua/{host} uses dsr.{name}, which lua/dcgansr.lua does not export"
+    for name in set(re.findall(r"\bnn\.([A-Za-z_][A-Za-z0-9_]*)", src)):
+        assert name in nn_exported, f"lua/{host} uses nn.{name}, which lua/dcgansr.lua does not export"
+    # layer lists: count the constructor calls per net and compare with the spec builders
+    want = {"train.lua": (models.train_lua_G(3, 12), models.dcgan64_D(3, 64)),
+            "train-gray.lua": (models.train_gray_G(16), models.dcgan64_D(1, 64)),
+            "train-gray-patch.lua": (models.train_gray_3_G(16), models.patch_D(64)),
+            "train-gray-patch-batch-overlap.lua": (models.train_gray_3_G(16), models.patch_D(64))}[host]
+    lua_kind = {"SpatialConvolution": "conv", "SpatialFullConvolution": "fullconv", "SpatialBatchNormalization": "bn", "ReLU": "relu",
+                "LeakyReLU": "lrelu", "Tanh": "tanh", "Sigmoid": "sigmoid", "SpatialUpSamplingNearest": "upnearest", "View": "view"}
+    for var, specs in zip(("netG", "netD"), want):
+        kinds = []
+        for ln in src.splitlines():
+            if re.match(rf"\s*{var}:add\(", ln):
+                kinds += [lua_kind[k] for k in re.findall(r"(?:nn\.)?\b(SpatialFullConvolution|SpatialConvolution|SpatialBatchNormalization|"
+                                                          r"SpatialUpSamplingNearest|LeakyReLU|ReLU|Tanh|Sigmoid|View)\(", ln)]
+        assert kinds == [s["kind"] for s in specs], (host, var, kinds)

@@ -100,25 +100,27 @@ def _sync_from_oracle(net, onet, st):
     net.set_adam_state(st.m.numpy().astype(np.float32), st.v.numpy().astype(np.float32), st.t)
 
 
+# Data seeds of the step tests, chosen on the CPU by scripts/find_step_seeds.py: with ~1e5..1e6 ReLU / LeakyReLU inputs per step
+# some pre-activation can sit within float32 rounding of the kink, and then ANY two float32 evaluations (the float32 and the
+# float64 oracle included) differ at the 1e-3 level in that step.  On these seeds the float32 ORACLE stays within 1e-5 of the
+# float64 oracle on every one of the four iterations, so the strict bound can be demanded of every iteration.
+STEP_SEEDS = {"bce_patch": 1033, "bce_patch_batch": 1006, "mse_gray": 1030, "mse_rgb": 1007}
+
+
 @pytest.mark.parametrize("paired", [False, True])
 @pytest.mark.parametrize("name", sorted(STEP_CASES))
 def test_train_step_parity(ctx, name, paired):
-    """Every step starts from the oracle's exact state (parameters + Adam moments), so each iteration is an
-    independent single-step parity check at t = 1..4 (bias correction, accumulated moments).
-
-    Conditioning: with ~1e6 ReLU inputs per step some pre-activation always sits within float32 rounding of the
-    kink; if such an element carries a large gradient, ANY two float32 implementations (the float32 and float64
-    oracles included) differ at the 1e-3 level in that step.  The strict bound must therefore hold
-    in at least 3 of the 4 iterations; the remaining one must still be within a 5e-2 sanity bound.  Execution is
-    deterministic, so this is not a flaky allowance."""
+    """Every step starts from the oracle's exact state (parameters + Adam moments), so each iteration is an independent
+    single-step parity check at t = 1..4 (bias correction, accumulated moments).  The strict bound holds on EVERY iteration:
+    losses and parameters within 1e-5, gradients / Adam moments within 5e-5 (max-norm over the flat vector, whose small tensors
+    see a relative error a few times their own)."""
     case = STEP_CASES[name]
     oG, oD, G, D = _build(ctx, case, paired=paired)
     B, nc, hr = case["batch"], case["nc"], case["hr"]
     ocfg = ostep_cfg(case["step"])
     cfg = dsr.make_step_cfg(**case["step"])
     stG, stD = ostep.new_adam_state(oG), ostep.new_adam_state(oD)
-    r = rng(1234)
-    strict_ok = 0
+    r = rng(STEP_SEEDS[name])
     report = []
     for it in range(4):
         real = smooth_images(r, (B, nc, hr, hr), *case["rng"])
@@ -138,13 +140,35 @@ def test_train_step_parity(ctx, name, paired):
             rm, rv = D.get_bn_running()
             orm = torch.cat([m.running_mean for m in oD.bn_modules()]).numpy()
             orv = torch.cat([m.running_var for m in oD.bn_modules()]).numpy()
-            assert rel_err(rm, orm) <= 1e-4 and rel_err(rv, orv) <= 1e-4, (name, it, "BN running statistics")
+            assert rel_err(rm, orm) <= STRICT_TOL and rel_err(rv, orv) <= STRICT_TOL, (name, it, "BN running statistics")
         report.append((it, eD, eG, pD, pG, eM))
-        assert max(eD, eG) <= 5e-2 and max(pD, pG) <= 1e-3, (name, report)
-        strict_ok += (max(eD, eG, eM) <= 5 * STRICT_TOL and max(pD, pG) <= STRICT_TOL)
+        assert max(eD, eG, eM) <= 5 * STRICT_TOL and max(pD, pG) <= STRICT_TOL, (name, report)
         _sync_from_oracle(G, oG, stG)
         _sync_from_oracle(D, oD, stD)
-    assert strict_ok >= 3, (name, report)
+    G.close(); D.close()
+
+
+@pytest.mark.parametrize("name", sorted(STEP_CASES))
+def test_train_steps_free_running(ctx, name):
+    """Four consecutive steps WITHOUT re-synchronising from the oracle (drift accumulates through the parameters, the Adam
+    moments and D's BN running statistics): losses within 1e-5 at every step, parameters within 5e-5 after the fourth (the
+    float32 oracle itself is 1e-6..7e-6 away from the float64 one there, scripts/find_step_seeds.py)."""
+    case = STEP_CASES[name]
+    oG, oD, G, D = _build(ctx, case, paired=True)
+    B, nc, hr = case["batch"], case["nc"], case["hr"]
+    ocfg = ostep_cfg(case["step"])
+    cfg = dsr.make_step_cfg(**case["step"])
+    stG, stD = ostep.new_adam_state(oG), ostep.new_adam_state(oD)
+    r = rng(STEP_SEEDS[name])
+    for it in range(4):
+        real = smooth_images(r, (B, nc, hr, hr), *case["rng"])
+        oerr = ostep.train_step(oG, oD, stG, stD, torch.from_numpy(real), ocfg)
+        err = dsr.train_step(ctx, G, D, cfg, real)
+        for a, b in zip(err, oerr):
+            assert abs(a - b) <= 1e-5 * max(abs(b), 1e-3), (name, it, err, oerr)
+    pD = rel_err(D.get_params(), oD.get_flat_params().numpy())
+    pG = rel_err(G.get_params(), oG.get_flat_params().numpy())
+    assert max(pD, pG) <= 5 * STRICT_TOL, (name, pD, pG)
     G.close(); D.close()
 
 

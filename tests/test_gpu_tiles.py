@@ -1,0 +1,57 @@
+"""Per-layer parity at BASELINE spatial sizes: every persistent CTA of the halo-tile kernels walks several tiles (>= 4 x 148
+tiles per launch), so the stage / accumulator ring wrap and the TMA-store staging-buffer reuse are checked per layer, not only
+through the step tests.  Strict fp32 <= 1e-5 and FAST_TF32 <= 2e-3 (max-norm) against the float64 oracle."""
+import numpy as np
+import pytest
+
+from dcgan_super_resolution_b200 import _lib as L
+from oracle import ops
+from util import FAST_TOL, STRICT_TOL, ptr, rel_err, rng, t64
+
+pytestmark = pytest.mark.gpu
+
+# (kind, n, cin, h, w, cout, k, s, p) -- tiles are 16 x 8 pixels of the iterated grid (per sub-pixel class group)
+BIG_SHAPES = [
+    ("full", 8, 64, 128, 128, 32, 4, 2, 1),     # C2 G layer 3 (FC 64->32, 128^2 -> 256^2): 1024 tiles; dgrad = two cout slices
+    ("conv", 8, 32, 256, 256, 16, 4, 2, 1),     # C2 G layer 4 (C 32->16, 256^2 -> 128^2): dgrad through the TMA-store epilogue
+    ("full", 4, 48, 256, 256, 24, 4, 2, 1),     # train.lua G layer 3 at C3b size (FC 48->24, 256^2 -> 512^2): 96-byte output rows
+    ("conv", 4, 24, 512, 512, 12, 4, 2, 1),     # train.lua G layer 4 at C3b size (C 24->12): fwd 48-byte rows, dgrad 96-byte rows
+    ("full", 6, 96, 128, 128, 48, 4, 2, 1),     # train.lua G layer 2 at C3b size (FC 96->48): one launch per sub-pixel class
+]
+
+
+@pytest.mark.parametrize("mode", ["strict", "tf32"])
+@pytest.mark.parametrize("shape", BIG_SHAPES)
+def test_big_layer_fwd_dgrad_wgrad(ctx, ctx_fast, shape, mode):
+    c = ctx if mode == "strict" else ctx_fast
+    tol = STRICT_TOL if mode == "strict" else FAST_TOL
+    kind, n, cin, h, w, cout, k, s, p = shape
+    full = kind == "full"
+    r = rng(hash(shape[1:]) % 2**31)
+    x = r.standard_normal((n, cin, h, w)).astype(np.float32)
+    wt = (0.1 * r.standard_normal((cin, cout, k, k) if full else (cout, cin, k, k))).astype(np.float32)
+    ho, wo = ((h - 1) * s - 2 * p + k, (w - 1) * s - 2 * p + k) if full else ((h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1)
+    dy = r.standard_normal((n, cout, ho, wo)).astype(np.float32)
+    lib, hc = c.lib, c.h
+    pre = "dcgansr_fullconv2d_" if full else "dcgansr_conv2d_"
+    args = (n, cin, h, w, cout, k, s, p)
+    X, W, DY = t64(x), t64(wt), t64(dy)
+    y = np.empty((n, cout, ho, wo), np.float32)
+    L.check(getattr(lib, pre + "fwd")(hc, ptr(x), ptr(wt), ptr(y), *args), hc)
+    ref = (ops.fullconv2d_fwd(X, W, s, p) if full else ops.conv2d_fwd(X, W, s, p)).numpy()
+    assert rel_err(y, ref) <= tol, ("fwd", rel_err(y, ref))
+    # every image and every tile row must be right, not only the largest element: per-image check as well
+    for i in range(n):
+        assert rel_err(y[i], ref[i]) <= 2 * tol, ("fwd image", i)
+    del y, ref
+    dx = np.empty_like(x)
+    L.check(getattr(lib, pre + "dgrad")(hc, ptr(dy), ptr(wt), ptr(dx), *args), hc)
+    ref = (ops.fullconv2d_dgrad(DY, W, s, p) if full else ops.conv2d_dgrad(DY, W, x.shape, s, p)).numpy()
+    assert rel_err(dx, ref) <= tol, ("dgrad", rel_err(dx, ref))
+    for i in range(n):
+        assert rel_err(dx[i], ref[i]) <= 2 * tol, ("dgrad image", i)
+    del dx, ref
+    dw = np.empty_like(wt)
+    L.check(getattr(lib, pre + "wgrad")(hc, ptr(x), ptr(dy), ptr(dw), *args), hc)
+    ref = (ops.fullconv2d_wgrad(X, DY, wt.shape, s, p) if full else ops.conv2d_wgrad(X, DY, wt.shape, s, p)).numpy()
+    assert rel_err(dw, ref) <= tol, ("wgrad", rel_err(dw, ref))
