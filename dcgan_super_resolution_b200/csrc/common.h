@@ -91,22 +91,23 @@ void k_bn_apply_act(St st, const float* x, float* y, int64_t P, int C, const flo
                     const float* mean, const float* invstd, int act, float negval);
 void k_act(St st, const float* x, float* y, int64_t count, int act, float negval);
 void k_act_bwd(St st, const float* y, const float* dy, float* dx, int64_t count, int act, float negval);
-// BN backward: g = dy*act'(y) written to g_out (y may be null when act == ACT_NONE);
-// sums[2C] = (sum g, sum g*xhat)
-void k_bn_bwd_reduce(St st, const float* dy, const float* y, const float* x, float* g_out, int64_t P, int C,
-                     const float* mean, const float* invstd, int act, float negval,
-                     double* partials, double* sums);
+// BN backward: g = dy*act'(.) is re-derived per element in both passes (nothing is written but the sums / dx).  y == nullptr
+// (allowed for ACT_NONE / RELU / LRELU): the mask is recomputed from x with the CURRENT gamma / beta -- only valid while the
+// parameters are those of the cached forward; otherwise pass the cached activation output y.  sums[2C] = (sum g, sum g*xhat)
+void k_bn_bwd_reduce(St st, const float* dy, const float* y, const float* x, int64_t P, int C, const float* gamma, const float* beta,
+                     const float* mean, const float* invstd, int act, float negval, double* partials, double* sums);
 // dbeta += sums_local[0..C), dgamma += sums_local[C..2C)   (either pointer may be null)
 void k_bn_bwd_param(St st, const double* sums_local, int C, float* dgamma, float* dbeta);
-void k_bn_bwd_apply(St st, const float* g, const float* x, float* dx, int64_t P, int C, const float* gamma,
-                    const float* mean, const float* invstd, const double* sums_total, double n_total);
+void k_bn_bwd_apply(St st, const float* dy, const float* y, const float* x, float* dx, int64_t P, int C, const float* gamma,
+                    const float* beta, const float* mean, const float* invstd, int act, float negval, const double* sums_total,
+                    double n_total, float* fmeans /* scratch, 2C floats */);
 // grouped + fused BatchNorm of the training step (no cross-rank statistics): see kernels_bw.cu
 void k_bn_fwd_grouped(St st, const float* x, float* y, int64_t P, int C, int groups, const float* gamma, const float* beta,
                       float* save_mean, float* save_invstd, int64_t sstride, float* running_mean, float* running_var, float eps,
                       float momentum, int act, float negval, double* partials);
 void k_bn_bwd_grouped(St st, const float* dy, const float* y, const float* x, float* dx, int64_t P, int C, int groups,
-                      const float* gamma, const float* save_mean, const float* save_invstd, int64_t sstride, int act, float negval,
-                      double* partials, double* sums, float* dgamma, float* dbeta);
+                      const float* gamma, const float* beta, const float* save_mean, const float* save_invstd, int64_t sstride, int act,
+                      float negval, double* partials, double* sums, float* dgamma, float* dbeta, float* fmeans /* groups x 2C floats */);
 void k_upnearest_fwd(St st, const float* x, float* y, int N, int H, int W, int C, int scale);
 void k_upnearest_bwd(St st, const float* dy, float* dx, int N, int H, int W, int C, int scale);
 void k_extract_patches(St st, const float* img, float* patches, int K, int H, int W, int p, int line, int nper, int stride);

@@ -535,11 +535,15 @@ struct dcgansr_net {
   float* gbuf[2] = {nullptr, nullptr};
   int64_t gelems = 0;
   double *bn_partials = nullptr, *bn_sums = nullptr, *bn_sums_total = nullptr;
+  float* bn_fmeans = nullptr;                         // (float)(sum / n) of the BN backward reductions, 2 groups x 2C
   float* wscratch = nullptr;
   size_t wscratch_bytes = 0;
   int first_param_mod = -1;
   int last_batch = 0;
   const float* last_out = nullptr;
+  // parameter version at the last update / at the cached forward: while they agree, the BatchNorm backward may re-derive the
+  // activation mask from x and the current gamma / beta instead of reading the cached output (kernels_bw.cu:bn_gval)
+  uint64_t params_ver = 1, fwd_ver = 0;
   int out_c = 0, out_h = 0, out_w = 0;
   std::vector<std::pair<int64_t, int64_t>> buckets;   // gradient buckets (offset, count), forward order
   PackJob* pack_jobs = nullptr;                       // fused weight repack (one launch per net)
@@ -566,7 +570,7 @@ static void net_release_device(dcgansr_net* net) {
   void** ptrs[] = {(void**)&net->params, (void**)&net->grads, (void**)&net->adam_m, (void**)&net->adam_v, (void**)&net->adam_t,
                    (void**)&net->adam_step, (void**)&net->bn_rmean, (void**)&net->bn_rvar, (void**)&net->bn_save, (void**)&net->in_buf,
                    (void**)&net->gbuf[0], (void**)&net->gbuf[1], (void**)&net->bn_partials, (void**)&net->bn_sums,
-                   (void**)&net->bn_sums_total, (void**)&net->wscratch, (void**)&net->pack_jobs};
+                   (void**)&net->bn_sums_total, (void**)&net->bn_fmeans, (void**)&net->wscratch, (void**)&net->pack_jobs};
   for (void** p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
   net->last_out = nullptr; net->last_batch = 0;
   net->ctx = nullptr;
@@ -654,6 +658,7 @@ static int net_forward_dev(dcgansr_net* net, const float* in, int B, int groups 
   }
   net->last_out = cur;
   net->last_batch = NB;
+  net->fwd_ver = net->params_ver;
   CKLAST(ctx);
   return 0;
 }
@@ -727,11 +732,17 @@ static int net_backward_dev(dcgansr_net* net, const float* in, const float* dy, 
         int64_t P = (int64_t)B * m.hin * m.win;
         int C = m.cin;
         float* gall = net->own(cur);
+        const float* gamma = net->params + m.p_off;
+        const float* beta = gamma + C;
+        // the activation mask: re-derived from x while the parameters are those of the cached forward (one tensor less to
+        // read), else from the cached output (fGx walks D with post-Adam weights and pre-Adam activations, train.lua:264-270)
+        const bool remask = net->fwd_ver == net->params_ver && (m.fused_act == ACT_RELU || m.fused_act == ACT_LRELU) && !getenv("DCGANSR_BN_READ_Y");
+        const float* yact = (m.fused_act != ACT_NONE && !remask) ? mout : nullptr;
         if (!sync) {
-          k_bn_bwd_grouped(st, cur, m.fused_act != ACT_NONE ? mout : nullptr, inp, gall, P, C, groups, net->params + m.p_off,
+          k_bn_bwd_grouped(st, cur, yact, inp, gall, P, C, groups, gamma, beta,
                            m.save_mean + (int64_t)goff * 2 * net->nbn, m.save_invstd + (int64_t)goff * 2 * net->nbn, 2 * net->nbn,
                            m.fused_act, m.fused_neg, net->bn_partials, net->bn_sums, acc ? net->grads + m.p_off : nullptr,
-                           acc ? net->grads + m.p_off + C : nullptr);
+                           acc ? net->grads + m.p_off + C : nullptr, net->bn_fmeans);
           cur = gall;
           break;
         }
@@ -739,9 +750,8 @@ static int net_backward_dev(dcgansr_net* net, const float* in, const float* dy, 
           const int64_t off = (int64_t)gi * P * C;
           const float* smean = m.save_mean + (int64_t)(goff + gi) * 2 * net->nbn;
           const float* sinv = m.save_invstd + (int64_t)(goff + gi) * 2 * net->nbn;
-          float* g = gall + off;
-          k_bn_bwd_reduce(st, cur + off, m.fused_act != ACT_NONE ? mout + off : nullptr, inp + off, g, P, C, smean, sinv,
-                          m.fused_act, m.fused_neg, net->bn_partials, net->bn_sums);
+          k_bn_bwd_reduce(st, cur + off, yact ? yact + off : nullptr, inp + off, P, C, gamma, beta, smean, sinv, m.fused_act, m.fused_neg,
+                          net->bn_partials, net->bn_sums);
           if (acc) k_bn_bwd_param(st, net->bn_sums, C, net->grads + m.p_off, net->grads + m.p_off + C);
           const double* tot = net->bn_sums;
           double n_total = (double)P;
@@ -751,7 +761,8 @@ static int net_backward_dev(dcgansr_net* net, const float* in, const float* dy, 
             tot = net->bn_sums_total;
             n_total *= ctx->world();
           }
-          k_bn_bwd_apply(st, g, inp + off, g, P, C, net->params + m.p_off, smean, sinv, tot, n_total);
+          k_bn_bwd_apply(st, cur + off, yact ? yact + off : nullptr, inp + off, gall + off, P, C, gamma, beta, smean, sinv, m.fused_act,
+                         m.fused_neg, tot, n_total, net->bn_fmeans);
         }
         cur = gall;
         break;
@@ -776,6 +787,7 @@ static int net_adam_dev(dcgansr_net* net, double lr, double b1, double b2, doubl
   St st = ctx->st();
   k_adam_prep(st, net->adam_t, net->adam_step, lr, b1, b2);
   k_adam(st, net->params, net->grads, net->adam_m, net->adam_v, net->nparams, net->adam_step, b1, b2, eps);
+  ++net->params_ver;
   net_pack_all(net);
   CKLAST(ctx);
   return 0;
@@ -1132,6 +1144,7 @@ int dcgansr_net_create(dcgansr_ctx* ctx, const dcgansr_layer* layers, int n_laye
     A(&tmpf, std::max<int64_t>(rows, 2) * 2 * 2); net->bn_partials = (double*)tmpf; tmpf = nullptr;     // x 2 sample groups
     A(&tmpf, (int64_t)maxC * 4 * 2 + 4); net->bn_sums = (double*)tmpf; tmpf = nullptr;
     A(&tmpf, (int64_t)maxC * 4 + 4); net->bn_sums_total = (double*)tmpf;
+    A(&net->bn_fmeans, (int64_t)maxC * 4 + 4);
   }
   net->wscratch_bytes = wsc;
   A(&net->wscratch, (int64_t)(wsc / sizeof(float)) + 4);
@@ -1192,6 +1205,7 @@ int dcgansr_net_set_params(dcgansr_net* net, const float* host_flat) {
   NEED_DEV(net);
   if (!host_flat) return fail(ctx, DCGANSR_ERR_INVALID, "null params");
   CK(ctx, cudaMemcpyAsync(net->params, host_flat, net->nparams * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  ++net->params_ver;
   net_pack_all(net);
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   CKLAST(ctx);
@@ -1730,9 +1744,11 @@ int dcgansr_bn_bwd(dcgansr_ctx* ctx, const float* x, const float* dy, const floa
   CK(ctx, cudaMemsetAsync(dDG, 0, c * sizeof(float), ctx->stream));
   CK(ctx, cudaMemsetAsync(dDB, 0, c * sizeof(float), ctx->stream));
   St st = ctx->st();
-  k_bn_bwd_reduce(st, dDY, nullptr, dX, dGm, P, c, dM, dI, ACT_NONE, 0.f, part, sums);
+  k_bn_bwd_reduce(st, dDY, nullptr, dX, P, c, dG, nullptr, dM, dI, ACT_NONE, 0.f, part, sums);
   k_bn_bwd_param(st, sums, c, dDG, dDB);
-  k_bn_bwd_apply(st, dGm, dX, dGm, P, c, dG, dM, dI, sums, (double)P);
+  float* dFm = ar.f(2 * c);
+  if (!dFm) return fail(ctx, DCGANSR_ERR_NOMEM, "device allocation failed");
+  k_bn_bwd_apply(st, dDY, nullptr, dX, dGm, P, c, dG, nullptr, dM, dI, ACT_NONE, 0.f, sums, (double)P, dFm);
   if (dx) if (int rc = download_nchw(ctx, dGm, n, c, h, wd, dx)) return rc;
   if (int rc = d2h(ctx, dgamma, dDG, c)) return rc;
   return d2h(ctx, dbeta, dDB, c);

@@ -195,6 +195,7 @@ __device__ __forceinline__ void bn_block_reduce_store(double (&a)[2 * VEC], int 
   __syncthreads();
 }
 
+#define BN_CHUNK 16
 template <int VEC>
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ x, int64_t P, int C, int TX, int TY,
                                                        int64_t ppb, double* __restrict__ partials) {
@@ -210,16 +211,39 @@ __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__
 #pragma unroll
     for (int j = 0; j < 2 * VEC; ++j) a[j] = 0.0;
     if (cv < CV) {
-      for (int64_t p = p0 + ty; p < p1; p += TY) {
-        if (VEC == 4) {
-          float4 v = *reinterpret_cast<const float4*>(x + p * C + cv * 4);
-          double d0 = v.x, d1 = v.y, d2 = v.z, d3 = v.w;
-          a[0] += d0; a[1] += d1; a[2] += d2; a[3] += d3;
-          a[VEC + 0] += d0 * d0; a[VEC + 1] += d1 * d1; a[VEC + 2] += d2 * d2; a[VEC + 3] += d3 * d3;
+      // two-level accumulation: BN_CHUNK pixels in fp32 (the f32 -> f64 conversions and DADDs of a per-element double sum
+      // bound the kernel at ~4.9 TB/s), chunk sums in double -- the error of a 16-term fp32 sum is a few 1e-8 relative
+      for (int64_t pc = p0 + ty; pc < p1; pc += (int64_t)TY * BN_CHUNK) {
+        float f[2 * VEC];
+#pragma unroll
+        for (int j = 0; j < 2 * VEC; ++j) f[j] = 0.f;
+        const int cnt = (int)((p1 - pc + TY - 1) / TY < BN_CHUNK ? (p1 - pc + TY - 1) / TY : BN_CHUNK);
+        auto one = [&](const float4& v) {
+          f[0] += v.x; f[1] += v.y; f[2] += v.z; f[3] += v.w;
+          f[VEC + 0] = fmaf(v.x, v.x, f[VEC + 0]); f[VEC + 1] = fmaf(v.y, v.y, f[VEC + 1]);
+          f[VEC + 2] = fmaf(v.z, v.z, f[VEC + 2]); f[VEC + 3] = fmaf(v.w, v.w, f[VEC + 3]);
+        };
+        if (VEC == 4 && cnt == BN_CHUNK) {
+          // full chunk: loads batched four deep, no bounds checks
+          const float* xp = x + pc * C + cv * 4;
+          const int64_t step = (int64_t)TY * C;
+#pragma unroll
+          for (int u0 = 0; u0 < BN_CHUNK; u0 += 4) {
+            float4 v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const float4*>(xp + (int64_t)(u0 + u) * step);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) one(v[u]);
+          }
         } else {
-          double d0 = x[p * C + cv];
-          a[0] += d0; a[VEC] += d0 * d0;
+          for (int u = 0; u < cnt; ++u) {
+            const int64_t p = pc + (int64_t)u * TY;
+            if (VEC == 4) one(*reinterpret_cast<const float4*>(x + p * C + cv * 4));
+            else { const float d0 = x[p * C + cv]; f[0] += d0; f[VEC] = fmaf(d0, d0, f[VEC]); }
+          }
         }
+#pragma unroll
+        for (int j = 0; j < 2 * VEC; ++j) a[j] += (double)f[j];
       }
     }
     bn_block_reduce_store<VEC>(a, tx, ty, TX, TY, cv, CV, C, prow);
@@ -278,6 +302,12 @@ void k_bn_finalize(St st, const double* sums, int C, double n_total, float eps, 
   DSR_LAUNCHED(st, "bn_finalize", 32.0 * C, WORK_BYTES);
 }
 
+// BatchNorm pre-activation gamma * xhat + beta with every rounding spelled out: the forward (bn_apply_kernel) and the backward
+// (which re-derives the ReLU / LeakyReLU mask from x instead of reading the output tensor) must agree bit for bit, whatever the
+// compiler contracts elsewhere.
+__device__ __forceinline__ float bn_pre(float x, float m, float s, float g, float b) {
+  return __fmaf_rn(__fmul_rn(__fsub_rn(x, m), s), g, b);
+}
 // y = act(gamma * (x - mean) * invstd + beta)
 template <int VEC>
 __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t total_v, int CV,
@@ -295,14 +325,14 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
       float4 b = __ldg(reinterpret_cast<const float4*>(beta) + cv);
       float4 m = __ldg(reinterpret_cast<const float4*>(mean) + cv);
       float4 s = __ldg(reinterpret_cast<const float4*>(invstd) + cv);
-      v.x = act_apply((v.x - m.x) * s.x * g.x + b.x, act, neg);
-      v.y = act_apply((v.y - m.y) * s.y * g.y + b.y, act, neg);
-      v.z = act_apply((v.z - m.z) * s.z * g.z + b.z, act, neg);
-      v.w = act_apply((v.w - m.w) * s.w * g.w + b.w, act, neg);
+      v.x = act_apply(bn_pre(v.x, m.x, s.x, g.x, b.x), act, neg);
+      v.y = act_apply(bn_pre(v.y, m.y, s.y, g.y, b.y), act, neg);
+      v.z = act_apply(bn_pre(v.z, m.z, s.z, g.z, b.z), act, neg);
+      v.w = act_apply(bn_pre(v.w, m.w, s.w, g.w, b.w), act, neg);
       reinterpret_cast<float4*>(y)[i] = v;
     } else {
       float v = x[i];
-      y[i] = act_apply((v - __ldg(mean + cv)) * __ldg(invstd + cv) * __ldg(gamma + cv) + __ldg(beta + cv), act, neg);
+      y[i] = act_apply(bn_pre(v, __ldg(mean + cv), __ldg(invstd + cv), __ldg(gamma + cv), __ldg(beta + cv)), act, neg);
     }
   }
 }
@@ -319,18 +349,29 @@ void k_bn_apply_act(St st, const float* x, float* y, int64_t P, int C, const flo
   DSR_LAUNCHED(st, "bn_apply_act", 8.0 * P * C, WORK_BYTES);
 }
 
-// backward reductions: g = dy * act'(y) ; sum g, sum g * xhat
+// g = dy * act'(.) of one element.  y != nullptr: the activation OUTPUT is read (Torch7 in-place modules test the output; needed
+// when the parameters changed since the cached forward -- fGx's updateGradInput through D, train.lua:268 -- and for Tanh /
+// Sigmoid).  y == nullptr (ReLU / LeakyReLU only): output > 0 <=> pre-activation > 0, recomputed from x: one tensor less to read.
+__device__ __forceinline__ float bn_gval(float dy, const float* y, int64_t o, float x, float m, float s, float ga, float be, int act, float neg) {
+  if (act == ACT_NONE) return dy;
+  if (y) return act_grad(y[o], dy, act, neg);
+  const bool pos = bn_pre(x, m, s, ga, be) > 0.f;
+  return pos ? dy : (act == ACT_LRELU ? dy * neg : 0.f);
+}
+
+// backward reductions: g = dy * act'(y) ; sum g, sum g * xhat.  Reads dy, x (and y when given); writes only the partial sums.
 template <int VEC>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* dy, const float* __restrict__ y,
-                                                            const float* __restrict__ x, float* g_out /* may alias dy */, int64_t P,
-                                                            int C, int TX, int TY, int64_t ppb, const float* __restrict__ mean,
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ y,
+                                                            const float* __restrict__ x, int64_t P,
+                                                            int C, int TX, int TY, int64_t ppb, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, const float* __restrict__ mean,
                                                             const float* __restrict__ invstd, int act, float neg,
                                                             double* __restrict__ partials, int64_t sstride) {
   int tx = threadIdx.x % TX, ty = threadIdx.x / TX;
   int CV = C / VEC;
   {
     const int64_t go = (int64_t)blockIdx.y * P * C;               // sample group
-    dy += go; x += go; g_out += go;
+    dy += go; x += go;
     if (y) y += go;
     mean += (int64_t)blockIdx.y * sstride; invstd += (int64_t)blockIdx.y * sstride;
   }
@@ -344,35 +385,74 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* dy, con
     for (int j = 0; j < 2 * VEC; ++j) a[j] = 0.0;
     if (cv < CV) {
       if (VEC == 4) {
-        float4 m = __ldg(reinterpret_cast<const float4*>(mean) + cv);
-        float4 s = __ldg(reinterpret_cast<const float4*>(invstd) + cv);
-        for (int64_t p = p0 + ty; p < p1; p += TY) {
-          int64_t o = p * C + cv * 4;
-          float4 d = *reinterpret_cast<const float4*>(dy + o);
-          float4 xv = *reinterpret_cast<const float4*>(x + o);
+        const float4 m = __ldg(reinterpret_cast<const float4*>(mean) + cv);
+        const float4 s = __ldg(reinterpret_cast<const float4*>(invstd) + cv);
+        float4 ga = make_float4(1.f, 1.f, 1.f, 1.f), be = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (act != ACT_NONE && !y) { ga = __ldg(reinterpret_cast<const float4*>(gamma) + cv); be = __ldg(reinterpret_cast<const float4*>(beta) + cv); }
+        auto gof = [&](const float4& d, const float4& xv, int64_t o) {
           float4 g = d;
           if (act != ACT_NONE) {
-            float4 yv = *reinterpret_cast<const float4*>(y + o);
-            g.x = act_grad(yv.x, d.x, act, neg); g.y = act_grad(yv.y, d.y, act, neg);
-            g.z = act_grad(yv.z, d.z, act, neg); g.w = act_grad(yv.w, d.w, act, neg);
+            if (y) {
+              const float4 yv = *reinterpret_cast<const float4*>(y + o);
+              g.x = act_grad(yv.x, d.x, act, neg); g.y = act_grad(yv.y, d.y, act, neg);
+              g.z = act_grad(yv.z, d.z, act, neg); g.w = act_grad(yv.w, d.w, act, neg);
+            } else {
+              g.x = bn_gval(d.x, nullptr, 0, xv.x, m.x, s.x, ga.x, be.x, act, neg);
+              g.y = bn_gval(d.y, nullptr, 0, xv.y, m.y, s.y, ga.y, be.y, act, neg);
+              g.z = bn_gval(d.z, nullptr, 0, xv.z, m.z, s.z, ga.z, be.z, act, neg);
+              g.w = bn_gval(d.w, nullptr, 0, xv.w, m.w, s.w, ga.w, be.w, act, neg);
+            }
           }
-          *reinterpret_cast<float4*>(g_out + o) = g;
-          double g0 = g.x, g1 = g.y, g2 = g.z, g3 = g.w;
-          a[0] += g0; a[1] += g1; a[2] += g2; a[3] += g3;
-          a[VEC + 0] += g0 * (double)((xv.x - m.x) * s.x);
-          a[VEC + 1] += g1 * (double)((xv.y - m.y) * s.y);
-          a[VEC + 2] += g2 * (double)((xv.z - m.z) * s.z);
-          a[VEC + 3] += g3 * (double)((xv.w - m.w) * s.w);
+          return g;
+        };
+        for (int64_t pc = p0 + ty; pc < p1; pc += (int64_t)TY * BN_CHUNK) {
+          float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};       // fp32 over a chunk of pixels, double across chunks (see bn_stats_kernel)
+          auto one = [&](const float4& d, const float4& xv, int64_t o) {
+            const float4 g = gof(d, xv, o);
+            f[0] += g.x; f[1] += g.y; f[2] += g.z; f[3] += g.w;
+            f[4] = fmaf(g.x, (xv.x - m.x) * s.x, f[4]); f[5] = fmaf(g.y, (xv.y - m.y) * s.y, f[5]);
+            f[6] = fmaf(g.z, (xv.z - m.z) * s.z, f[6]); f[7] = fmaf(g.w, (xv.w - m.w) * s.w, f[7]);
+          };
+          const int cnt = (int)((p1 - pc + TY - 1) / TY < BN_CHUNK ? (p1 - pc + TY - 1) / TY : BN_CHUNK);
+          const int64_t o0 = pc * C + cv * 4, step = (int64_t)TY * C;
+          if (cnt == BN_CHUNK) {
+#pragma unroll
+            for (int u0 = 0; u0 < BN_CHUNK; u0 += 4) {
+              float4 d[4], xv[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                d[u] = *reinterpret_cast<const float4*>(dy + o0 + (int64_t)(u0 + u) * step);
+                xv[u] = *reinterpret_cast<const float4*>(x + o0 + (int64_t)(u0 + u) * step);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) one(d[u], xv[u], o0 + (int64_t)(u0 + u) * step);
+            }
+          } else {
+            for (int u = 0; u < cnt; ++u) {
+              const int64_t o = o0 + (int64_t)u * step;
+              one(*reinterpret_cast<const float4*>(dy + o), *reinterpret_cast<const float4*>(x + o), o);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) a[j] += (double)f[j];
         }
       } else {
-        float m = __ldg(mean + cv), s = __ldg(invstd + cv);
-        for (int64_t p = p0 + ty; p < p1; p += TY) {
-          int64_t o = p * C + cv;
-          float d = dy[o];
-          float g = act != ACT_NONE ? act_grad(y[o], d, act, neg) : d;
-          g_out[o] = g;
-          a[0] += (double)g;
-          a[VEC] += (double)g * (double)((x[o] - m) * s);
+        const float m = __ldg(mean + cv), s = __ldg(invstd + cv);
+        const float ga = (act != ACT_NONE && !y) ? __ldg(gamma + cv) : 1.f, be = (act != ACT_NONE && !y) ? __ldg(beta + cv) : 0.f;
+        for (int64_t pc = p0 + ty; pc < p1; pc += (int64_t)TY * BN_CHUNK) {
+          float f0 = 0.f, f1 = 0.f;
+#pragma unroll 4
+          for (int u = 0; u < BN_CHUNK; ++u) {
+            const int64_t p = pc + (int64_t)u * TY;
+            if (p >= p1) break;
+            const int64_t o = p * C + cv;
+            const float xv = x[o];
+            const float g = bn_gval(dy[o], y, o, xv, m, s, ga, be, act, neg);
+            f0 += g;
+            f1 = fmaf(g, (xv - m) * s, f1);
+          }
+          a[0] += (double)f0;
+          a[VEC] += (double)f1;
         }
       }
     }
@@ -380,14 +460,17 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* dy, con
   }
 }
 
-void k_bn_bwd_reduce(St st, const float* dy, const float* y, const float* x, float* g_out, int64_t P, int C,
+static inline double bn_bwd_reduce_bytes(int64_t P, int C, int act, const float* y) { return ((act != ACT_NONE && y) ? 12.0 : 8.0) * P * C; }
+static inline double bn_bwd_apply_bytes(int64_t P, int C, int act, const float* y) { return ((act != ACT_NONE && y) ? 16.0 : 12.0) * P * C; }
+
+void k_bn_bwd_reduce(St st, const float* dy, const float* y, const float* x, int64_t P, int C, const float* gamma, const float* beta,
                      const float* mean, const float* invstd, int act, float negval, double* partials, double* sums) {
   BnCfg c = bn_cfg(P, C);
   if (c.vec == 4)
-    bn_bwd_reduce_kernel<4><<<c.nb, 256, 0, st.s>>>(dy, y, x, g_out, P, C, c.TX, c.TY, c.ppb, mean, invstd, act, negval, partials, 0);
+    bn_bwd_reduce_kernel<4><<<c.nb, 256, 0, st.s>>>(dy, y, x, P, C, c.TX, c.TY, c.ppb, gamma, beta, mean, invstd, act, negval, partials, 0);
   else
-    bn_bwd_reduce_kernel<1><<<c.nb, 256, 0, st.s>>>(dy, y, x, g_out, P, C, c.TX, c.TY, c.ppb, mean, invstd, act, negval, partials, 0);
-  DSR_LAUNCHED(st, "bn_bwd_reduce", (act != ACT_NONE ? 16.0 : 12.0) * P * C, WORK_BYTES);
+    bn_bwd_reduce_kernel<1><<<c.nb, 256, 0, st.s>>>(dy, y, x, P, C, c.TX, c.TY, c.ppb, gamma, beta, mean, invstd, act, negval, partials, 0);
+  DSR_LAUNCHED(st, "bn_bwd_reduce", bn_bwd_reduce_bytes(P, C, act, y), WORK_BYTES);
   colsum_kernel<<<(2 * C + 31) / 32, dim3(32, 8), 0, st.s>>>(partials, c.nb, 2 * C, sums);
   DSR_LAUNCHED(st, "bn_colsum", 16.0 * c.nb * C, WORK_BYTES);
 }
@@ -403,53 +486,76 @@ void k_bn_bwd_param(St st, const double* sums_local, int C, float* dgamma, float
   DSR_LAUNCHED(st, "bn_bwd_param", 32.0 * C, WORK_BYTES);
 }
 
-// dx = (g - sum_g/n - xhat * sum_gxhat/n) * gamma * invstd      (in place on g allowed)
+// dx = (g - sum_g/n - xhat * sum_gxhat/n) * gamma * invstd with g = dy * act'(.) re-derived per element (see bn_gval); dx may
+// alias dy (in place: every element is read before it is written by the same thread).
 template <int VEC>
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* g, const float* __restrict__ x,
-                                                           float* dx /* may alias g (in place) */, int64_t total_v, int CV, int C,
-                                                           const float* __restrict__ gamma, const float* __restrict__ mean,
-                                                           const float* __restrict__ invstd, const double* __restrict__ sums,
-                                                           double n_total, int64_t sstride) {
-  g += (int64_t)blockIdx.y * total_v * VEC; x += (int64_t)blockIdx.y * total_v * VEC; dx += (int64_t)blockIdx.y * total_v * VEC;
-  mean += (int64_t)blockIdx.y * sstride; invstd += (int64_t)blockIdx.y * sstride; sums += (int64_t)blockIdx.y * 2 * C;
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* dy, const float* __restrict__ y, const float* __restrict__ x,
+                                                           float* dx /* may alias dy */, int64_t total_v, int CV, int C,
+                                                           const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                           const float* __restrict__ mean, const float* __restrict__ invstd, int act,
+                                                           float neg, const float* __restrict__ fmeans, int64_t sstride) {
+  // fmeans[2C] per group: (float)(sum g / n), (float)(sum g*xhat / n), written once by the tail kernel (the double divisions
+  // used to sit in this loop: 8 per float4, which bound the kernel at ~4 TB/s)
+  dy += (int64_t)blockIdx.y * total_v * VEC; x += (int64_t)blockIdx.y * total_v * VEC; dx += (int64_t)blockIdx.y * total_v * VEC;
+  if (y) y += (int64_t)blockIdx.y * total_v * VEC;
+  mean += (int64_t)blockIdx.y * sstride; invstd += (int64_t)blockIdx.y * sstride; fmeans += (int64_t)blockIdx.y * 2 * C;
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_v; i += stride) {
     int cv = (int)(i % CV);
     if (VEC == 4) {
-      float4 gv = reinterpret_cast<const float4*>(g)[i];
+      float4 gv = reinterpret_cast<const float4*>(dy)[i];
       float4 xv = reinterpret_cast<const float4*>(x)[i];
       float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + cv);
       float4 m = __ldg(reinterpret_cast<const float4*>(mean) + cv);
       float4 s = __ldg(reinterpret_cast<const float4*>(invstd) + cv);
-      int c = cv * 4;
-      float mg0 = (float)(sums[c + 0] / n_total), mg1 = (float)(sums[c + 1] / n_total);
-      float mg2 = (float)(sums[c + 2] / n_total), mg3 = (float)(sums[c + 3] / n_total);
-      float mx0 = (float)(sums[C + c + 0] / n_total), mx1 = (float)(sums[C + c + 1] / n_total);
-      float mx2 = (float)(sums[C + c + 2] / n_total), mx3 = (float)(sums[C + c + 3] / n_total);
+      if (act != ACT_NONE) {
+        if (y) {
+          float4 yv = reinterpret_cast<const float4*>(y)[i];
+          gv.x = act_grad(yv.x, gv.x, act, neg); gv.y = act_grad(yv.y, gv.y, act, neg);
+          gv.z = act_grad(yv.z, gv.z, act, neg); gv.w = act_grad(yv.w, gv.w, act, neg);
+        } else {
+          float4 be = __ldg(reinterpret_cast<const float4*>(beta) + cv);
+          gv.x = bn_gval(gv.x, nullptr, 0, xv.x, m.x, s.x, ga.x, be.x, act, neg);
+          gv.y = bn_gval(gv.y, nullptr, 0, xv.y, m.y, s.y, ga.y, be.y, act, neg);
+          gv.z = bn_gval(gv.z, nullptr, 0, xv.z, m.z, s.z, ga.z, be.z, act, neg);
+          gv.w = bn_gval(gv.w, nullptr, 0, xv.w, m.w, s.w, ga.w, be.w, act, neg);
+        }
+      }
+      const float4 mg = __ldg(reinterpret_cast<const float4*>(fmeans) + cv);
+      const float4 mx = __ldg(reinterpret_cast<const float4*>(fmeans + C) + cv);
       float4 o;
-      o.x = (gv.x - mg0 - (xv.x - m.x) * s.x * mx0) * (ga.x * s.x);
-      o.y = (gv.y - mg1 - (xv.y - m.y) * s.y * mx1) * (ga.y * s.y);
-      o.z = (gv.z - mg2 - (xv.z - m.z) * s.z * mx2) * (ga.z * s.z);
-      o.w = (gv.w - mg3 - (xv.w - m.w) * s.w * mx3) * (ga.w * s.w);
+      o.x = (gv.x - mg.x - (xv.x - m.x) * s.x * mx.x) * (ga.x * s.x);
+      o.y = (gv.y - mg.y - (xv.y - m.y) * s.y * mx.y) * (ga.y * s.y);
+      o.z = (gv.z - mg.z - (xv.z - m.z) * s.z * mx.z) * (ga.z * s.z);
+      o.w = (gv.w - mg.w - (xv.w - m.w) * s.w * mx.w) * (ga.w * s.w);
       reinterpret_cast<float4*>(dx)[i] = o;
     } else {
-      float mg = (float)(sums[cv] / n_total), mx = (float)(sums[C + cv] / n_total);
-      float s = __ldg(invstd + cv);
-      dx[i] = (g[i] - mg - (x[i] - __ldg(mean + cv)) * s * mx) * (__ldg(gamma + cv) * s);
+      const float mg = __ldg(fmeans + cv), mx = __ldg(fmeans + C + cv);
+      float s = __ldg(invstd + cv), m = __ldg(mean + cv), ga = __ldg(gamma + cv);
+      const float xv = x[i];
+      const float g = bn_gval(dy[i], y, i, xv, m, s, ga, (act != ACT_NONE && !y) ? __ldg(beta + cv) : 0.f, act, neg);
+      dx[i] = (g - mg - (xv - m) * s * mx) * (ga * s);
     }
   }
 }
 
-void k_bn_bwd_apply(St st, const float* g, const float* x, float* dx, int64_t P, int C, const float* gamma,
-                    const float* mean, const float* invstd, const double* sums_total, double n_total) {
+__global__ void bn_fmeans_kernel(const double* __restrict__ sums, int n2c, double n_total, float* __restrict__ fmeans) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n2c) fmeans[i] = (float)(sums[i] / n_total);
+}
+void k_bn_bwd_apply(St st, const float* dy, const float* y, const float* x, float* dx, int64_t P, int C, const float* gamma,
+                    const float* beta, const float* mean, const float* invstd, int act, float negval, const double* sums_total,
+                    double n_total, float* fmeans) {
+  bn_fmeans_kernel<<<(2 * C + 127) / 128, 128, 0, st.s>>>(sums_total, 2 * C, n_total, fmeans);
+  DSR_LAUNCHED(st, "bn_fmeans", 24.0 * C, WORK_BYTES);
   if (C % 4 == 0) {
     int64_t tv = P * (C / 4);
-    bn_bwd_apply_kernel<4><<<ew_grid(tv * 4), 256, 0, st.s>>>(g, x, dx, tv, C / 4, C, gamma, mean, invstd, sums_total, n_total, 0);
+    bn_bwd_apply_kernel<4><<<ew_grid(tv * 4), 256, 0, st.s>>>(dy, y, x, dx, tv, C / 4, C, gamma, beta, mean, invstd, act, negval, fmeans, 0);
   } else {
     int64_t tv = P * C;
-    bn_bwd_apply_kernel<1><<<ew_grid(tv * 4), 256, 0, st.s>>>(g, x, dx, tv, C, C, gamma, mean, invstd, sums_total, n_total, 0);
+    bn_bwd_apply_kernel<1><<<ew_grid(tv * 4), 256, 0, st.s>>>(dy, y, x, dx, tv, C, C, gamma, beta, mean, invstd, act, negval, fmeans, 0);
   }
-  DSR_LAUNCHED(st, "bn_bwd_apply", 12.0 * P * C, WORK_BYTES);
+  DSR_LAUNCHED(st, "bn_bwd_apply", bn_bwd_apply_bytes(P, C, act, y), WORK_BYTES);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -514,7 +620,7 @@ void k_bn_fwd_grouped(St st, const float* x, float* y, int64_t P, int C, int gro
 
 // sums[g][2C] = column sums of group g's partial rows; dbeta += sum_g sums[g][c], dgamma += sum_g sums[g][C + c]
 __global__ void bn_bwd_tail_kernel(const double* __restrict__ partials, int nb, int C, int groups, double* __restrict__ sums,
-                                   float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                   float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ fmeans, double n_total) {
   __shared__ double red[2][BN_TAIL_Y][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   for (int g = 0; g < groups; ++g) {
@@ -531,6 +637,8 @@ __global__ void bn_bwd_tail_kernel(const double* __restrict__ partials, int nb, 
       for (int r = 0; r < BN_TAIL_Y; ++r) { s1 += red[0][r][threadIdx.x]; s2 += red[1][r][threadIdx.x]; }
       sums[(int64_t)g * 2 * C + c] = s1;
       sums[(int64_t)g * 2 * C + C + c] = s2;
+      fmeans[(int64_t)g * 2 * C + c] = (float)(s1 / n_total);            // what the apply pass subtracts
+      fmeans[(int64_t)g * 2 * C + C + c] = (float)(s2 / n_total);
       // the reference accumulates group after group in fp32 (two backward calls): same order here
       if (dbeta) dbeta[c] += (float)s1;
       if (dgamma) dgamma[c] += (float)s2;
@@ -540,25 +648,25 @@ __global__ void bn_bwd_tail_kernel(const double* __restrict__ partials, int nb, 
 }
 
 void k_bn_bwd_grouped(St st, const float* dy, const float* y, const float* x, float* dx, int64_t P, int C, int groups,
-                      const float* gamma, const float* save_mean, const float* save_invstd, int64_t sstride, int act, float negval,
-                      double* partials, double* sums, float* dgamma, float* dbeta) {
+                      const float* gamma, const float* beta, const float* save_mean, const float* save_invstd, int64_t sstride, int act,
+                      float negval, double* partials, double* sums, float* dgamma, float* dbeta, float* fmeans) {
   BnCfg c = bn_cfg(P, C);
   dim3 grid(c.nb, groups);
   if (c.vec == 4)
-    bn_bwd_reduce_kernel<4><<<grid, 256, 0, st.s>>>(dy, y, x, dx, P, C, c.TX, c.TY, c.ppb, save_mean, save_invstd, act, negval, partials, sstride);
+    bn_bwd_reduce_kernel<4><<<grid, 256, 0, st.s>>>(dy, y, x, P, C, c.TX, c.TY, c.ppb, gamma, beta, save_mean, save_invstd, act, negval, partials, sstride);
   else
-    bn_bwd_reduce_kernel<1><<<grid, 256, 0, st.s>>>(dy, y, x, dx, P, C, c.TX, c.TY, c.ppb, save_mean, save_invstd, act, negval, partials, sstride);
-  DSR_LAUNCHED(st, "bn_bwd_reduce", (act != ACT_NONE ? 16.0 : 12.0) * P * C * groups, WORK_BYTES);
-  bn_bwd_tail_kernel<<<(C + 31) / 32, dim3(32, BN_TAIL_Y), 0, st.s>>>(partials, c.nb, C, groups, sums, dgamma, dbeta);
+    bn_bwd_reduce_kernel<1><<<grid, 256, 0, st.s>>>(dy, y, x, P, C, c.TX, c.TY, c.ppb, gamma, beta, save_mean, save_invstd, act, negval, partials, sstride);
+  DSR_LAUNCHED(st, "bn_bwd_reduce", bn_bwd_reduce_bytes(P, C, act, y) * groups, WORK_BYTES);
+  bn_bwd_tail_kernel<<<(C + 31) / 32, dim3(32, BN_TAIL_Y), 0, st.s>>>(partials, c.nb, C, groups, sums, dgamma, dbeta, fmeans, (double)P);
   DSR_LAUNCHED(st, "bn_bwd_tail", 16.0 * c.nb * C * groups, WORK_BYTES);
   if (C % 4 == 0) {
     int64_t tv = P * (C / 4);
-    bn_bwd_apply_kernel<4><<<dim3(ew_grid(tv * 4), groups), 256, 0, st.s>>>(dx, x, dx, tv, C / 4, C, gamma, save_mean, save_invstd, sums, (double)P, sstride);
+    bn_bwd_apply_kernel<4><<<dim3(ew_grid(tv * 4), groups), 256, 0, st.s>>>(dy, y, x, dx, tv, C / 4, C, gamma, beta, save_mean, save_invstd, act, negval, fmeans, sstride);
   } else {
     int64_t tv = P * C;
-    bn_bwd_apply_kernel<1><<<dim3(ew_grid(tv * 4), groups), 256, 0, st.s>>>(dx, x, dx, tv, C, C, gamma, save_mean, save_invstd, sums, (double)P, sstride);
+    bn_bwd_apply_kernel<1><<<dim3(ew_grid(tv * 4), groups), 256, 0, st.s>>>(dy, y, x, dx, tv, C, C, gamma, beta, save_mean, save_invstd, act, negval, fmeans, sstride);
   }
-  DSR_LAUNCHED(st, "bn_bwd_apply", 12.0 * P * C * groups, WORK_BYTES);
+  DSR_LAUNCHED(st, "bn_bwd_apply", bn_bwd_apply_bytes(P, C, act, y) * groups, WORK_BYTES);
 }
 
 // ------------------------------------------------------------------------------------------

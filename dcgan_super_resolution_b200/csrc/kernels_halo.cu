@@ -7,8 +7,11 @@
 // re-fetches the input pixels once per tap (4..16x) and the weights once per 128-pixel tile.  Here
 //
 //   * a persistent CTA loads its slice of the packed weights ONCE (TMA, K-major, swizzled) and keeps it in smem;
-//   * per 16 x 8 tile of the output grid it loads the input pixels ONCE: a halo tile (one TMA box per 32-channel
-//     plane, zero fill = padding), double buffered;
+//   * per 16 x 8 tile of the output grid it loads the input pixels ONCE: a halo tile, one TMA box per 32-channel
+//     plane (zero fill = padding).  The planes of consecutive tiles go through a RING of plane buffers: the MMAs of a
+//     tile are issued plane by plane, so a buffer is free again as soon as the MMAs that read it have completed -- the
+//     ring can be shorter than two whole tiles (resident weights of 100..150 KB leave room for 3..6 planes) and the
+//     freed shared memory takes the TMA-store staging buffers;
 //   * every tap is then just another START ADDRESS of the same smem tile: the UMMA descriptor's swizzle is a
 //     function of the absolute shared-memory address, so a window shifted by whole pixel rows (and stepping
 //     `pitch` bytes between 8-pixel groups, SBO = halo row pitch) is a valid K-major operand
@@ -36,6 +39,7 @@
 #define HALO_MAXPLANES 8
 #define HALO_MAXGRP 4
 #define HALO_MAXSLOT 8
+#define HALO_MAXRING 16
 
 struct HaloMaps { CUtensorMap b[HALO_MAXCLS]; };
 #define HALO_MAXMMA 256
@@ -56,16 +60,23 @@ struct HaloParams {
   short coy[HALO_MAXCLS], cox[HALO_MAXCLS];
   unsigned short tap_plane[HALO_MAXCLS][HALO_MAXTAPS], tap_wtile[HALO_MAXCLS][HALO_MAXTAPS], tap_wstride[HALO_MAXCLS][HALO_MAXTAPS];
   int tap_aoff[HALO_MAXCLS][HALO_MAXTAPS];
-  int nstage, stage_bytes, acc_cols, nacc, tmem_cols, nmma;
+  int nring, acc_cols, nacc, tmem_cols, nmma;   // nring: plane buffers in the ring
   int ngrp, gbeg[HALO_MAXGRP + 1];      // MMA issuer warps and their table ranges
+  unsigned short pend[HALO_MAXGRP][HALO_MAXPLANES];   // group g, plane pl: its table entries end at pend[g][pl] (entries sorted by plane)
   int nslots;                            // accumulator slots (Npad TMEM columns each)
   int cls_nsl[HALO_MAXCLS];              // class c = sum of slots cls_sl[c][0 .. cls_nsl[c])
   unsigned char cls_sl[HALO_MAXCLS][4];
   int act;
   float neg;
-  int tstore, st_bytes, st_cls;          // TMA-store epilogue: rows of Co floats staged in shared memory (SWIZZLE_128B pattern), one box
-                                         // per class and tile; bytes of one staging buffer (ncls class blocks) and of a class block
-                                         // (128 pixels x Co*4 B, rounded to 1 KB); two buffers after the A stages
+  int tstore, st_bytes, st_cls;          // TMA-store epilogue: rows of st_row floats staged in shared memory, one box per class and
+                                         // tile; bytes of one staging buffer (ncls class blocks) and of a class block (128 pixels x
+                                         // st_row*4 B, rounded to 1 KB); st_nbuf buffers after the plane ring
+  int st_nbuf, st_row, st_xor;           // st_xor: 16-byte chunk index ^= (128-byte line index & st_xor) -- the pattern of the store
+                                         // map's swizzle mode (7 = 128B rows, 3 = 64B rows, 1 = 32B rows, 0 = none: dense rows)
+  int st_nbox;                           // TMA boxes per tile: one per class, or one per output-row parity when the two column
+                                         // classes of a row parity are staged side by side (rows of 2*Co floats: wider global segments)
+  short st_cblk[HALO_MAXCLS], st_coff[HALO_MAXCLS];      // class -> staging block, float offset inside the staged row
+  short st_bc0[HALO_MAXCLS], st_bpy[HALO_MAXCLS];        // box -> channel coordinate, row-parity coordinate
   int dbg;                               // DCGANSR_HALO_DBG (timing experiments only): 1 skip MMAs, 2 skip stores, 4 skip the halo TMA loads
 };
 
@@ -107,11 +118,12 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams& p, float* __rest
     const bool valid = gy < p.Hg && gx < p.Wg && !(p.dbg & 2);
     float* pix = out + ((int64_t)(n * p.Ho + gy * p.so) * p.Wo + gx * p.so) * p.Co + n0;
     const uint32_t cbase = lane_base + (uint32_t)(buf * p.acc_cols);
-    // TMA-store mode: staging buffer it & 1 was the source of the store group issued two tiles ago
+    // TMA-store mode: with two staging buffers, buffer it & 1 was the source of the store group issued two tiles ago; with
+    // one, of the previous tile's group
     const bool leader = warp == p.ngrp + 1 && lane == 0;
-    const uint32_t stg = sO + (uint32_t)((it & 1) * p.st_bytes);
+    const uint32_t stg = sO + (uint32_t)((p.st_nbuf == 2 ? (it & 1) : 0) * p.st_bytes);
     if (p.tstore) {
-      if (leader) tma_store_wait_read<1>();
+      if (leader) { if (p.st_nbuf == 2) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
       named_bar_sync(2, 256);
     }
     mbar_wait(smem_u32(&acc_full[buf]), aph);
@@ -144,14 +156,17 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams& p, float* __rest
         }
       }
       if (p.tstore) {
-        // row r of class c: Co floats at pitch Co*4 inside the (1 KB aligned) class block; the SWIZZLE_128B store map expects
-        // byte offset o at o ^ (((o >> 7) & 7) << 4) (16-byte chunk index XOR 128-byte line index, mod 8)
-        const uint32_t blk = stg + (uint32_t)(c * p.st_cls);
+        // row r of class c: st_row floats (this CTA's cout slice), dense, inside the (1 KB aligned) class block.  A swizzled
+        // store map (rows of exactly 128 / 64 / 32 bytes) expects byte offset o at o ^ (((o >> 7) & st_xor) << 4): the 16-byte
+        // chunk index XORed with the 128-byte line index -- which also makes the 32 lanes' stores conflict-free; other row
+        // widths use a non-swizzled map (st_xor = 0, dense rows)
+        const uint32_t blk = stg + (uint32_t)(p.st_cblk[c] * p.st_cls);
+        const int coff = p.st_coff[c];
 #pragma unroll
         for (int j = 0; j < 16; j += 4) {
-          if (c0 + j < p.Co) {
-            const uint32_t o = (uint32_t)(r * p.Co + c0 + j) * 4u;
-            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (o ^ (((o >> 7) & 7u) << 4))),
+          if (c0 + j < p.Npad && n0 + c0 + j < p.Co) {
+            const uint32_t o = (uint32_t)(r * p.st_row + coff + c0 + j) * 4u;
+            asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(blk + (o ^ (((o >> 7) & (uint32_t)p.st_xor) << 4))),
                          "f"(act_c<ACT>(__uint_as_float(v[j]), p.neg)), "f"(act_c<ACT>(__uint_as_float(v[j + 1]), p.neg)),
                          "f"(act_c<ACT>(__uint_as_float(v[j + 2]), p.neg)), "f"(act_c<ACT>(__uint_as_float(v[j + 3]), p.neg))
                          : "memory");
@@ -167,8 +182,10 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams& p, float* __rest
       named_bar_sync(3, 256);
       if (leader && !(p.dbg & 2)) {
         const int gy0 = ty * HALO_TH, gx0 = tx * HALO_TW;
-        for (int c = 0; c < p.ncls; ++c)      // output seen as [N][Ho/2][2][Wo/2][2*Co]: class (coy, cox) = row parity, channel offset cox*Co
-          tma_store_5d(mapO, stg + (uint32_t)(c * p.st_cls), p.cox[c] * p.Co, gx0, p.coy[c], gy0, n);
+        // so == 2: output seen as [N][Ho/2][2][Wo/2][2*Co], class (coy, cox) = row parity coy, channel offset cox*Co;
+        // so == 1: the same 5-D view [N][Ho][1][Wo][Co] with a unit parity dimension
+        for (int b = 0; b < p.st_nbox; ++b)
+          tma_store_5d(mapO, stg + (uint32_t)(b * p.st_cls), p.st_bc0[b] + n0, gx0, p.st_bpy[b], gy0, n);
         tma_store_commit();
       }
     }
@@ -185,21 +202,21 @@ __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sW = smem;
   uint8_t* sA = smem + p.w_bytes;
-  uint8_t* sOut = sA + (size_t)p.nstage * p.stage_bytes;                 // TMA-store staging (2 buffers) when p.tstore
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + (size_t)(p.tstore ? 2 * p.st_bytes : 0));
+  uint8_t* sOut = sA + (size_t)p.nring * p.plane_bytes;                  // TMA-store staging (st_nbuf buffers) when p.tstore
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOut + (size_t)(p.tstore ? p.st_nbuf * p.st_bytes : 0));
   uint64_t* w_full = bars;
-  uint64_t* a_full = bars + 1;
-  uint64_t* a_empty = bars + 3;
-  uint64_t* acc_full = bars + 5;
-  uint64_t* acc_empty = bars + 9;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* acc_full = bars + 1;
+  uint64_t* acc_empty = bars + 5;
+  uint64_t* a_full = bars + 9;                                           // [HALO_MAXRING]
+  uint64_t* a_empty = a_full + HALO_MAXRING;                             // [HALO_MAXRING]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + HALO_MAXRING);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * p.Npad;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     mbar_init(smem_u32(w_full), 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < p.nring; ++s) {
       mbar_init(smem_u32(&a_full[s]), 1);
       mbar_init(smem_u32(&a_empty[s]), (uint32_t)p.ngrp);
     }
@@ -230,11 +247,11 @@ __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel
           for (int q = 0; q < p.kchunks; ++q)
             tma_load_2d(smem_u32(sW) + (uint32_t)(p.tap_wtile[c][t] + q * p.tap_wstride[c][t]) * p.wtile_bytes, &mapsB.b[c], wf,
                         t * p.Ci + q * p.KBw, n0);
-      int it = 0;
-      const int pf_dist = p.nstage + 1;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-        const int s = it % p.nstage;
-        const uint32_t ph = (uint32_t)(it / p.nstage) & 1u;
+      // plane ring: plane pl of the CTA's it-th tile lives in buffer (it * nplanes + pl) % nring
+      int rs = 0;
+      uint32_t rph = 0;
+      const int pf_dist = p.nring / p.nplanes + 1;
+      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
         int tt = tile;
         const int tx = tt % p.tiles_x; tt /= p.tiles_x;
         const int ty = tt % p.tiles_y; tt /= p.tiles_y;
@@ -255,17 +272,19 @@ __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel
             }
           }
         }
-        mbar_wait(smem_u32(&a_empty[s]), ph ^ 1u);
-        const uint32_t fb = smem_u32(&a_full[s]);
-        if (p.dbg & 4) { mbar_arrive(fb); continue; }
-        mbar_expect_tx(fb, (uint32_t)(p.nplanes * p.plane_tx));
-        const uint32_t dst0 = smem_u32(sA + (size_t)s * p.stage_bytes);
         for (int pl = 0; pl < p.nplanes; ++pl) {
-          const uint32_t dst = dst0 + (uint32_t)pl * p.plane_bytes;
-          if (p.si == 1)
-            tma_load_4d(dst, &mapA, fb, p.pl_c[pl], gx0 + p.pl_x[pl], gy0 + p.pl_y[pl], n);
-          else
-            tma_load_5d(dst, &mapA, fb, p.pl_c[pl], gx0 + p.pl_x[pl], p.pl_py[pl], gy0 + p.pl_y[pl], n);
+          mbar_wait(smem_u32(&a_empty[rs]), rph ^ 1u);
+          const uint32_t fb = smem_u32(&a_full[rs]);
+          if (p.dbg & 4) mbar_arrive(fb);
+          else {
+            mbar_expect_tx(fb, (uint32_t)p.plane_tx);
+            const uint32_t dst = smem_u32(sA + (size_t)rs * p.plane_bytes);
+            if (p.si == 1)
+              tma_load_4d(dst, &mapA, fb, p.pl_c[pl], gx0 + p.pl_x[pl], gy0 + p.pl_y[pl], n);
+            else
+              tma_load_5d(dst, &mapA, fb, p.pl_c[pl], gx0 + p.pl_x[pl], p.pl_py[pl], gy0 + p.pl_y[pl], n);
+          }
+          if (++rs == p.nring) { rs = 0; rph ^= 1u; }
         }
       }
     }
@@ -278,30 +297,37 @@ __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel
     const int grp = warp - 1;
     const uint64_t wl = p.KBw == 32 ? 2ull : (p.KBw == 16 ? 4ull : 6ull);
     const uint32_t w_sbo = 8u * (uint32_t)p.KBw * 4u;
-    const int ibeg = p.gbeg[grp], iend = p.gbeg[grp + 1];
+    const int ibeg = p.gbeg[grp];
     mbar_wait(smem_u32(w_full), 0);
-    int it = 0;
+    const uint64_t bdesc = make_desc_k(smem_u32(sW), w_sbo, wl);
+    int it = 0, rs = 0;
+    uint32_t rph = 0;
     for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
-      const int s = it % p.nstage;
-      const uint32_t ph = (uint32_t)(it / p.nstage) & 1u;
       const int buf = it % p.nacc;
       const uint32_t aph = (uint32_t)(it / p.nacc) & 1u;
       mbar_wait(smem_u32(&acc_empty[buf]), aph ^ 1u);
-      mbar_wait(smem_u32(&a_full[s]), ph);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint64_t adesc = make_desc_k(smem_u32(sA + (size_t)s * p.stage_bytes), (uint32_t)p.pitch_bytes, (uint64_t)p.a_layout);
-        const uint64_t bdesc = make_desc_k(smem_u32(sW), w_sbo, wl);
-        const uint32_t dbase = tmem_base + (uint32_t)(buf * p.acc_cols);
+      const uint32_t dbase = tmem_base + (uint32_t)(buf * p.acc_cols);
+      int i = ibeg;
+      // plane by plane (the table is sorted by plane): every issuer waits for every plane and releases it after its own MMAs
+      // on it (possibly none) -- a plane buffer is refilled once all issuers have let go of it
+      for (int pl = 0; pl < p.nplanes; ++pl) {
+        mbar_wait(smem_u32(&a_full[rs]), rph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint64_t adesc = make_desc_k(smem_u32(sA + (size_t)rs * p.plane_bytes), (uint32_t)p.pitch_bytes, (uint64_t)p.a_layout);
+          const int iend = (p.dbg & 1) ? min(i + 1, (int)p.pend[grp][pl]) : (int)p.pend[grp][pl];
 #pragma unroll 4
-        for (int i = ibeg; i < ((p.dbg & 1) ? ibeg + 1 : iend); ++i) {
-          const uint4 e = tab.e[i];
-          umma_tf32(dbase + (e.z & 0xFFFFu), adesc + (uint64_t)e.x, bdesc + (uint64_t)e.y, e.w, (uint32_t)((int)e.z < 0 ? 0 : 1));
+          for (int k = i; k < iend; ++k) {
+            const uint4 e = tab.e[k];
+            umma_tf32(dbase + (e.z & 0xFFFFu), adesc + (uint64_t)e.x, bdesc + (uint64_t)e.y, e.w, (uint32_t)((int)e.z < 0 ? 0 : 1));
+          }
+          umma_commit(smem_u32(&a_empty[rs]));
+          if (pl == p.nplanes - 1) umma_commit(smem_u32(&acc_full[buf]));
         }
-        umma_commit(smem_u32(&a_empty[s]));
-        umma_commit(smem_u32(&acc_full[buf]));
+        __syncwarp();
+        i = p.pend[grp][pl];
+        if (++rs == p.nring) { rs = 0; rph ^= 1u; }
       }
-      __syncwarp();
     }
   } else if (warp <= p.ngrp + 8) {
     const int half = (warp - p.ngrp - 1) >> 2;
@@ -361,7 +387,9 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
   p.tiles_x = (p.Wg + HALO_TW - 1) / HALO_TW;
   p.tiles_y = (p.Hg + HALO_TH - 1) / HALO_TH;
   p.ntiles = p.N * p.tiles_y * p.tiles_x;
-  p.KBw = Ci >= 32 ? 32 : 16;
+  // weight rows (and, for si == 1, the A planes): 32-float chunks, or 16-float ones when that tiles Ci exactly (48 = 3 x 16
+  // instead of 32 + a half-empty 32: a quarter less shared memory for the resident weights)
+  p.KBw = (Ci >= 32 && !(Ci % 32 == 16 && !getenv("DCGANSR_HALO_KB32"))) ? 32 : 16;
   p.kchunks = (Ci + p.KBw - 1) / p.KBw;
   p.ksteps = p.KBw / 8;
   // K = 8 steps of chunk q that hold real channels, and their total per (class, tap)
@@ -430,7 +458,6 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
   }
   p.plane_tx = p.PH * p.PW * p.row_bytes;
   p.plane_bytes = (p.plane_tx + 1023) / 1024 * 1024;
-  p.stage_bytes = p.nplanes * p.plane_bytes;
   // ---- cout slice so that the resident weights + >= 1 stage fit ----
   int ttot = 0;
   for (int i = 0; i < ncls; ++i) {
@@ -450,7 +477,7 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
     else { ring[0] = ci[0][0]; ring[1] = ci[0][1]; ring[2] = ci[1][1]; ring[3] = ci[1][0]; ring[4] = ci[0][0]; }
   }
   const int co16 = (p.Co + 15) / 16 * 16;
-  const size_t fixed = 1024 + 16 * sizeof(uint64_t);
+  const size_t fixed = 1024 + (16 + 2 * HALO_MAXRING) * sizeof(uint64_t);
   auto set_npad = [&](int npad) {
     p.Npad = npad;
     p.wtile_bytes = npad * p.KBw * 4;            // a multiple of 1024 (npad % 16 == 0, KBw >= 16)
@@ -458,18 +485,27 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
     p.w_tx = p.w_bytes;
     p.acc_cols = (try_merge ? 5 : (ncls > 1 ? ncls : std::min(HALO_MAXGRP, cls[0].ntaps))) * npad;
   };
-  // largest cout slice whose weights leave room for a double-buffered halo tile; failing that, a single stage
+  // Largest cout slice whose resident weights leave room for a useful plane ring: two whole tiles when they fit, never fewer
+  // than min_ring planes (the issuer works on one plane while the next ones are in flight; L2 prefetch covers the DRAM latency).
+  const int full_ring = std::min(HALO_MAXRING, 2 * p.nplanes);
+  const int min_ring = p.nplanes == 1 ? 2 : std::min(full_ring, 3);
+  auto ring_for = [&](size_t extra) {
+    const size_t used = fixed + (size_t)p.w_bytes + extra;
+    if (used >= HALO_SMEM_MAX) return 0;
+    return (int)std::min<size_t>(full_ring, (HALO_SMEM_MAX - used) / p.plane_bytes);
+  };
   bool found = false;
-  for (int want = 2; want >= 1 && !found; --want)
-    for (int npad = std::min(co16, 256); npad >= 16; npad -= 16) {
-      if (co16 % npad && npad != std::min(co16, 256)) continue;       // equal slices only
-      if (try_merge && 4 * npad > 256) continue;                      // a merged MMA spans up to 4 slots (N <= 256)
-      set_npad(npad);
-      if (p.acc_cols <= 512 && p.w_bytes + (size_t)want * p.stage_bytes + fixed <= HALO_SMEM_MAX) { p.nstage = want; found = true; break; }
-    }
+  for (int npad = std::min(co16, 256); npad >= 16 && !found; npad -= 16) {
+    if (co16 % npad && npad != std::min(co16, 256)) continue;       // equal slices only
+    if (try_merge && 4 * npad > 256) continue;                      // a merged MMA spans up to 4 slots (N <= 256)
+    set_npad(npad);
+    if (p.acc_cols > 512) continue;
+    p.nring = ring_for(0);
+    if (p.nring >= min_ring) found = true;
+  }
   if (!found) return false;
-  if (const char* e = getenv("DCGANSR_HALO_NSTAGE")) p.nstage = std::max(1, std::min(p.nstage, atoi(e)));      // timing experiments
-  if (p.w_bytes > (1 << 20) || p.stage_bytes > (1 << 20)) return false;      // 16-bit (>> 4) offsets in the table
+  if (const char* e = getenv("DCGANSR_HALO_NRING")) p.nring = std::max(min_ring, std::min(p.nring, atoi(e)));      // timing experiments
+  if (p.w_bytes > (1 << 20) || p.plane_bytes > (1 << 20)) return false;      // 16-bit (>> 4) offsets in the table
 
   struct Op { int a_plane, a_off, m, slot0, cl[4], tp[4]; bool init; };
   std::vector<Op> ops;
@@ -573,23 +609,50 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
   if (p.nmma > HALO_MAXMMA) return false;
   p.gbeg[p.ngrp] = p.nmma;
   {
+    // one entry per MMA, then a stable sort by (issuer group, plane): the issuers consume the plane ring in plane order
+    struct Ent { int grp, plane; uint4 e; };
+    std::vector<Ent> ents;
     int i = 0, wt = 0;       // wt: running weight-tile index
     for (auto& o : ops) {
+      int grp = 0;
+      while (grp + 1 < p.ngrp && i >= p.gbeg[grp + 1]) ++grp;
       for (int j = 0; j < o.m; ++j) { p.tap_wtile[o.cl[j]][o.tp[j]] = (unsigned short)(wt + j); p.tap_wstride[o.cl[j]][o.tp[j]] = (unsigned short)o.m; }
       for (int q = 0; q < p.kchunks; ++q)
         for (int k = 0; k < ks_of(q); ++k, ++i) {
           // si == 1: plane = K chunk.  si == 2: the tap's K step sits f floats into the wide pixel row -> plane f / 32
           const int f = tap_kb[o.tp[0]] + q * p.KBw + k * 8;
-          const uint32_t aoff = p.si == 1 ? (uint32_t)(o.a_plane + q) * p.plane_bytes + (uint32_t)o.a_off + k * 32
-                                          : (uint32_t)(o.a_plane + f / 32) * p.plane_bytes + (uint32_t)o.a_off + (f % 32) * 4;
+          const int plane = p.si == 1 ? o.a_plane + q : o.a_plane + f / 32;
+          const uint32_t aoff = p.si == 1 ? (uint32_t)o.a_off + k * 32 : (uint32_t)o.a_off + (f % 32) * 4;
           const uint32_t woff = (uint32_t)(wt + q * o.m) * p.wtile_bytes + k * 32;
           const uint32_t accum = (o.init && q == 0 && k == 0) ? 0u : 1u;
           // D = f32, A = B = tf32, K-major, M = 128, N = m * Npad
           const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((o.m * p.Npad) >> 3) << 17) | ((128u >> 4) << 24);
-          c.tab.e[i] = make_uint4(aoff >> 4, woff >> 4, (uint32_t)(o.slot0 * p.Npad) | (accum ? 0u : 0x80000000u), idesc);
+          if (plane < 0 || plane >= p.nplanes) return false;
+          ents.push_back(Ent{grp, plane, make_uint4(aoff >> 4, woff >> 4, (uint32_t)(o.slot0 * p.Npad) | (accum ? 0u : 0x80000000u), idesc)});
         }
       wt += o.m * p.kchunks;
     }
+    std::stable_sort(ents.begin(), ents.end(), [](const Ent& a, const Ent& b) { return a.grp != b.grp ? a.grp < b.grp : a.plane < b.plane; });
+    if (!merged) {
+      // every issuer group owns one accumulator slot: its first MMA in ISSUE order initialises it
+      int prev = -1;
+      for (auto& en : ents) {
+        if (en.grp != prev) { en.e.z |= 0x80000000u; prev = en.grp; }
+        else en.e.z &= 0x7FFFFFFFu;
+      }
+    } else {
+      // merged classes: planes are the K chunks and the generation order (all-class op, slot 4's initialiser, rest) is kept
+      // inside every plane, so the initialising MMAs (chunk 0, K step 0) still come first
+      for (size_t k = 1; k < ents.size(); ++k) if (ents[k].plane < ents[k - 1].plane) return false;
+    }
+    for (size_t k = 0; k < ents.size(); ++k) c.tab.e[k] = ents[k].e;
+    size_t k = 0;
+    for (int g = 0; g < p.ngrp; ++g)
+      for (int pl = 0; pl < p.nplanes; ++pl) {
+        while (k < ents.size() && ents[k].grp == g && ents[k].plane == pl) ++k;
+        p.pend[g][pl] = (unsigned short)k;
+      }
+    if (k != ents.size()) return false;
   }
   p.acc_cols = p.nslots * p.Npad;
   if (p.acc_cols > 512) return false;
@@ -598,22 +661,50 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
   if (const char* e = getenv("DCGANSR_HALO_NACC")) p.nacc = std::max(1, std::min(p.nacc, atoi(e)));
   p.tmem_cols = std::max(32, pow2_ge_h(p.nacc * p.acc_cols));
   if (p.tmem_cols > 512) return false;
-  c.smem = 1024 + (size_t)p.w_bytes + (size_t)p.nstage * p.stage_bytes + 16 * sizeof(uint64_t);
-  // TMA-store epilogue where an output row fits one 128-byte swizzle row (Co <= 32, one cout slice), the four sub-pixel classes
-  // of a stride-2 output are present (the output viewed as [N][Ho/2][2][Wo/2][2*Co] makes a class one 5-D box per tile) and
-  // two staging buffers still fit beside the resident weights and the halo stages.  The direct epilogue (32-byte vector stores
-  // from 8 warps) tops out near 4 TB/s; the staged one leaves the write-out to the TMA engine (C 32->16 dgrad 148 -> 104 us).
+  // TMA-store epilogue.  The direct epilogue (32-byte vector stores from 8 warps) tops out near 4 TB/s; staging the tile in
+  // shared memory and leaving the write-out to the TMA engine took C 32->16 dgrad from 148 to 104 us.  Output rows of this
+  // CTA's cout slice (st_row = min(Npad, Co) floats) are staged densely; rows of exactly 128 / 64 / 32 bytes use the matching
+  // swizzled store map (conflict-free staging writes), any other width a non-swizzled map.  The output is seen as
+  // [N][Ho/so][so][Wo/so][so*Co]: a class of a tile is one 5-D box.  Taken when the staging buffers (two, else one) fit
+  // beside the resident weights and a plane ring of at least min_ring.
   p.tstore = 0;
-  p.st_cls = (128 * p.Co * 4 + 1023) / 1024 * 1024;
-  p.st_bytes = ncls * p.st_cls;
-  // (rows narrower than 128 bytes -- Co = 24 / 16 -- were tried with a Co-float box: wrong results, TMA does not pack such rows the
-  //  way the staging writer assumed; only full 128-byte rows are taken)
-  if (p.so == 2 && ncls == 4 && p.Co == 32 && p.Npad == 32 && c.nsplit == 1 && p.Ho % 2 == 0 && p.Wo % 2 == 0 &&
-      c.smem + 2 * (size_t)p.st_bytes <= HALO_SMEM_MAX && !getenv("DCGANSR_HALO_NO_TSTORE")) {
+  p.st_row = std::min(p.Npad, p.Co);
+  p.st_nbox = ncls;
+  for (int i = 0; i < ncls; ++i) { p.st_cblk[i] = (short)i; p.st_coff[i] = 0; p.st_bc0[i] = (short)(p.cox[i] * p.Co); p.st_bpy[i] = p.coy[i]; }
+  // stride-2 outputs whose rows are not a multiple of 128 bytes: the two column classes (cox = 0, 1) of an output-row parity
+  // are neighbours in memory ([..][Wo/2][2*Co]), so they are staged side by side and leave as ONE box of 2*Co-float rows --
+  // 96-byte segments with 96-byte gaps become contiguous 192-byte ones (C 24->12 dgrad: 965 us with per-class boxes, 828 direct)
+  if (p.so == 2 && ncls == 4 && c.nsplit == 1 && p.Co % 32 != 0 && 2 * p.Co <= 256 && !getenv("DCGANSR_HALO_NO_PAIR")) {
     bool ok = true;
     for (int i = 0; i < ncls; ++i) ok = ok && p.coy[i] >= 0 && p.coy[i] < 2 && p.cox[i] >= 0 && p.cox[i] < 2;
-    if (ok) { p.tstore = 1; c.smem += 2 * (size_t)p.st_bytes; }
+    if (ok) {
+      p.st_row = 2 * p.Co;
+      p.st_nbox = 2;
+      for (int i = 0; i < ncls; ++i) { p.st_cblk[i] = p.coy[i]; p.st_coff[i] = (short)(p.cox[i] * p.Co); }
+      for (int b = 0; b < 2; ++b) { p.st_bc0[b] = 0; p.st_bpy[b] = (short)b; }
+    }
   }
+  p.st_cls = (128 * p.st_row * 4 + 1023) / 1024 * 1024;
+  p.st_bytes = p.st_nbox * p.st_cls;
+  p.st_xor = p.st_row == 32 ? 7 : (p.st_row == 16 ? 3 : (p.st_row == 8 ? 1 : 0));
+  p.st_nbuf = 0;
+  {
+    bool ok = (p.so == 1 || p.so == 2) && p.Ho % p.so == 0 && p.Wo % p.so == 0 && p.Co % 4 == 0 && p.Co % p.Npad % 4 == 0 &&
+              (p.Co % p.Npad == 0 || c.nsplit == 1) && !getenv("DCGANSR_HALO_NO_TSTORE");
+    // measured (C3b, B200): a non-swizzled store map pays for a single-class launch (FC 96->48 forward per class: 1200 -> 852 us)
+    // but loses against the direct epilogue when four classes share the tile (C 24->12 dgrad 828 -> 965 us, FC 48->24 forward
+    // 1106 -> 1375 us with its single staging buffer)
+    if (p.st_xor == 0 && ncls > 1 && !getenv("DCGANSR_HALO_TSTORE_ALL")) ok = false;
+    for (int i = 0; i < ncls; ++i) ok = ok && p.coy[i] >= 0 && p.coy[i] < p.so && p.cox[i] >= 0 && p.cox[i] < p.so;
+    if (ok) {
+      for (int nb = 2; nb >= 1 && !p.tstore; --nb) {
+        const int r = ring_for((size_t)nb * p.st_bytes);
+        // two buffers only if the ring keeps its full depth or at least min_ring + 1; one buffer whenever min_ring still fits
+        if (r >= min_ring && (nb == 1 || r >= std::min(full_ring, min_ring + 1))) { p.tstore = 1; p.st_nbuf = nb; p.nring = std::min(p.nring, r); }
+      }
+    }
+  }
+  c.smem = fixed + (size_t)p.w_bytes + (size_t)p.nring * p.plane_bytes + (size_t)p.st_nbuf * p.st_bytes;
   // one persistent CTA per SM (13 warps x ~100 registers; the 8 epilogue warps provide the memory-level parallelism)
   c.grid_x = std::max(1, std::min(p.ntiles, (NSM + c.nsplit - 1) / c.nsplit));
   return true;
@@ -625,7 +716,10 @@ bool halo_tapconv_supported(const TapGeom* classes, int ncls) {
   HaloCfg c;
   if (!halo_cfg(classes, ncls, c)) return false;
   if (getenv("DCGANSR_HALO_ALL")) return true;
-  return c.nsplit <= 2 && c.p.nstage == 2;
+  // few cout slices (the input is read once per slice), and either the full two-tile ring or a spatially large layer (a short
+  // ring leans on the L2 prefetch, which needs many tiles per CTA to pay off)
+  const int full_ring = std::min(HALO_MAXRING, 2 * c.p.nplanes);
+  return c.nsplit <= 2 && (c.p.nring >= full_ring || (int64_t)c.p.Hg * c.p.Wg >= 4096);
 }
 
 bool k_tapconv_halo(St st, const TapGeom* classes, int ncls, const float* const* bp, const float* in, float* out, int act,
@@ -671,12 +765,14 @@ bool k_tapconv_halo(St st, const TapGeom* classes, int ncls, const float* const*
   CUtensorMap mapO;
   memset(&mapO, 0, sizeof(mapO));
   if (p.tstore) {
-    cuuint64_t dims[5] = {(cuuint64_t)2 * g.Co, (cuuint64_t)g.Wo / 2, 2, (cuuint64_t)g.Ho / 2, (cuuint64_t)g.N};
-    cuuint64_t strides[4] = {(cuuint64_t)2 * g.Co * 4, (cuuint64_t)g.Wo * g.Co * 4, (cuuint64_t)2 * g.Wo * g.Co * 4,
-                             (cuuint64_t)g.Ho * g.Wo * g.Co * 4};
-    cuuint32_t box[5] = {(cuuint32_t)g.Co, HALO_TW, 1, HALO_TH, 1};
-    r = enc(&mapO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)out, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
-            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const cuuint64_t so = (cuuint64_t)p.so;
+    cuuint64_t dims[5] = {so * g.Co, (cuuint64_t)g.Wo / so, so, (cuuint64_t)g.Ho / so, (cuuint64_t)g.N};
+    cuuint64_t strides[4] = {so * g.Co * 4, (cuuint64_t)g.Wo * g.Co * 4, so * g.Wo * g.Co * 4, (cuuint64_t)g.Ho * g.Wo * g.Co * 4};
+    cuuint32_t box[5] = {(cuuint32_t)p.st_row, HALO_TW, 1, HALO_TH, 1};
+    const CUtensorMapSwizzle oswz = p.st_xor == 7 ? CU_TENSOR_MAP_SWIZZLE_128B : p.st_xor == 3 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                    : p.st_xor == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    r = enc(&mapO, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)out, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, oswz,
+            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled(out, halo) failed: " + std::to_string((int)r); return false; }
   }
   static bool configured = false;
