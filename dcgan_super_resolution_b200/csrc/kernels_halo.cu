@@ -691,10 +691,11 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
   {
     bool ok = (p.so == 1 || p.so == 2) && p.Ho % p.so == 0 && p.Wo % p.so == 0 && p.Co % 4 == 0 && p.Co % p.Npad % 4 == 0 &&
               (p.Co % p.Npad == 0 || c.nsplit == 1) && !getenv("DCGANSR_HALO_NO_TSTORE");
-    // measured (C3b, B200): a non-swizzled store map pays for a single-class launch (FC 96->48 forward per class: 1200 -> 852 us)
-    // but loses against the direct epilogue when four classes share the tile (C 24->12 dgrad 828 -> 965 us, FC 48->24 forward
-    // 1106 -> 1375 us with its single staging buffer)
-    if (p.st_xor == 0 && ncls > 1 && !getenv("DCGANSR_HALO_TSTORE_ALL")) ok = false;
+    // measured on B200 (same box, per-layer A/B): the staged epilogue wins where the four classes leave as 128-byte swizzled rows
+    // (C 32->16 dgrad 150 -> 140 us) and for the per-class launches of a stride-2 output (FC 96->48 forward 1200 -> 852 us at
+    // C3b); it loses with non-swizzled rows shared by four classes (C 24->12 dgrad 828 -> 965 us), with 64-byte rows (FC 32->16
+    // forward 687 -> 701 us) and on single-class stride-1 outputs (FC 64->32 dgrad 153 -> 214 us): those keep the direct epilogue
+    if (!(p.st_xor == 7 && ncls == 4 && p.st_nbox == 4) && !(ncls == 1 && p.so == 2) && !getenv("DCGANSR_HALO_TSTORE_ALL")) ok = false;
     for (int i = 0; i < ncls; ++i) ok = ok && p.coy[i] >= 0 && p.coy[i] < p.so && p.cox[i] >= 0 && p.cox[i] < p.so;
     if (ok) {
       for (int nb = 2; nb >= 1 && !p.tstore; --nb) {

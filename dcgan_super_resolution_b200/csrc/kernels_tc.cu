@@ -67,7 +67,11 @@ bool tc_tapconv_supported(const TapGeom& g) {
 // weight packing for the tensor-core path: Bp[b][t*A + a] = tf32(master[a*sa + b*sb + tapidx[t]])
 // ------------------------------------------------------------------------------------------
 size_t tc_packed_elems(int ntaps, int A, int B) { return (size_t)ntaps * A * B; }
-int tc_bt_rows(int B) { return std::min((B + 15) / 16 * 16, 128); }
+// N tile of the per-tap kernel: up to 128 couts.  (256-cout tiles -- one 128 x 256 accumulator, one CTA per SM, the A tile fetched
+// once per 256 couts -- were measured on B200 and are slower: D conv 128->256 forward 81 -> 93 us, C 128->256 at C1b 611 -> 639 us;
+// two resident 128-wide CTAs overlap one's epilogue with the other's MMAs.  DCGANSR_TC_BN256=1 re-enables them for experiments.)
+static int tc_max_bn() { static int v = getenv("DCGANSR_TC_BN256") ? 256 : 128; return v; }
+int tc_bt_rows(int B) { const int b16 = (B + 15) / 16 * 16; return b16 >= 256 ? tc_max_bn() : std::min(b16, 128); }
 size_t tc_bt_elems(int ntaps, int A, int B) {
   const int bn = tc_bt_rows(B);
   return (size_t)((B + bn - 1) / bn) * ((size_t)ntaps * A / 32) * bn * 32;
@@ -108,6 +112,8 @@ struct TcParams {
   int KB, kchunks, BN, nstage;
   int ncls, oy0[TC_MAXCLS], ox0[TC_MAXCLS], ntaps[TC_MAXCLS];      // sub-pixel classes: blockIdx.z / ksplit
   int ksplit;                                                      // K splits per tile: blockIdx.z % ksplit
+  int cs;                                                          // cluster size along blockIdx.x (1, 2 or 4): the CTAs of a cluster work on
+                                                                   // different pixel tiles and share every weight tile by TMA multicast
   const float* bt[TC_MAXCLS];                                      // pre-tiled weight images (bulk-copy source) or null -> TMA 2-D
   int a_stage_bytes, b_stage_bytes, tmem_cols;
   int act;
@@ -150,10 +156,16 @@ __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_con
   const int b0 = tile * p.TB, gy0 = ty * p.TH, gx0 = tx * p.TW;
   const int n0 = blockIdx.y * p.BN;
 
+  // cluster of cs CTAs along x (cs == 1: plain launch): a stage of THIS CTA is written by its own TMA (A tile, 1/cs of the weight
+  // tile) and by the peers' multicasts (the other parts of the weight tile), so it is free again only when the MMAs of EVERY CTA
+  // of the cluster have read that stage: each issuer's tcgen05.commit arrives on the empty barrier of all cs CTAs
+  uint32_t crank = 0;
+  if (p.cs > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const uint16_t cmask = (uint16_t)((1u << p.cs) - 1u);
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapsB.b[cls]) : "memory");
-    for (int s = 0; s < p.nstage; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
+    for (int s = 0; s < p.nstage; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), (uint32_t)p.cs); }
     mbar_init(smem_u32(tmem_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -164,6 +176,10 @@ __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cs > 1) {          // every CTA's barriers are initialised before any peer multicasts into this CTA or signals them
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -173,6 +189,7 @@ __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_con
       int s = 0;
       uint32_t ph = 0;
       const uint32_t bytes = (uint32_t)(128 * p.KB * 4 + p.BN * p.KB * 4);
+      const uint32_t bpart = (uint32_t)(p.BN / p.cs) * (uint32_t)p.KB * 4u;       // this CTA's share of a weight tile (rows crank*BN/cs ...)
       for (int kb = kb_beg; kb < kb_end; ++kb) {
         const int t = kb / p.kchunks, c = kb - t * p.kchunks;
         mbar_wait(smem_u32(&empty[s]), ph ^ 1);
@@ -183,10 +200,17 @@ __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_con
           tma_load_4d(da, &mapA, fb, c * p.KB, gx0 + p.ox[cls][t], gy0 + p.oy[cls][t], b0);
         else
           tma_load_5d(da, &mapA, fb, p.px[cls][t] * p.Ci + c * p.KB, gx0 + p.ox[cls][t], p.py[cls][t], gy0 + p.oy[cls][t], b0);
-        if (p.bt[cls])    // one contiguous 1-D bulk copy of the whole BN x 32 tile image instead of BN 128-byte TMA rows
-          bulk_load(smem_u32(sB + (size_t)s * p.b_stage_bytes), p.bt[cls] + ((size_t)blockIdx.y * nk_all + kb) * (p.BN * 32), (uint32_t)(p.BN * 128), fb);
+        const uint32_t db = smem_u32(sB + (size_t)s * p.b_stage_bytes);
+        if (p.cs > 1) {
+          // 1/cs of the weight tile, multicast to the same shared-memory offset (and the same full barrier) of every CTA of the cluster
+          if (p.bt[cls])
+            bulk_load_mc(db + crank * bpart, p.bt[cls] + ((size_t)blockIdx.y * nk_all + kb) * (p.BN * 32) + (size_t)crank * (bpart / 4), bpart, fb, cmask);
+          else
+            tma_load_2d_mc(db + crank * bpart, &mapsB.b[cls], fb, t * p.Ci + c * p.KB, n0 + (int)crank * (p.BN / p.cs), cmask);
+        } else if (p.bt[cls])    // one contiguous 1-D bulk copy of the whole BN x 32 tile image instead of BN 128-byte TMA rows
+          bulk_load(db, p.bt[cls] + ((size_t)blockIdx.y * nk_all + kb) * (p.BN * 32), (uint32_t)(p.BN * 128), fb);
         else
-          tma_load_2d(smem_u32(sB + (size_t)s * p.b_stage_bytes), &mapsB.b[cls], fb, t * p.Ci + c * p.KB, n0);
+          tma_load_2d(db, &mapsB.b[cls], fb, t * p.Ci + c * p.KB, n0);
         if (++s == p.nstage) { s = 0; ph ^= 1; }
       }
     }
@@ -208,7 +232,8 @@ __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_con
         const uint64_t bd = make_kmajor_desc(smem_u32(sB + (size_t)s * p.b_stage_bytes), p.KB);
         for (int k = 0; k < ksteps; ++k)
           umma_tf32(tmem_base, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);   // +32 B per K step
-        umma_commit(smem_u32(&empty[s]));
+        if (p.cs > 1) umma_commit_mc(smem_u32(&empty[s]), cmask);
+        else umma_commit(smem_u32(&empty[s]));
         if (kb == nk - 1) umma_commit(smem_u32(tmem_full));
       }
       __syncwarp();
@@ -307,6 +332,10 @@ __global__ void __launch_bounds__(TC_THREADS) tapconv_tc_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (p.cs > 1) {          // no CTA leaves while a peer may still multicast into its shared memory or arrive on its barriers
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
@@ -348,14 +377,14 @@ bool k_tapconv_tc_multi(St st, const TapGeom* cls, int ncls, const float* const*
   p.tiles_y = (g.Hg + p.TH - 1) / p.TH;
   const int tiles_b = (g.N + p.TB - 1) / p.TB;
   const int co16 = (g.Co + 15) / 16 * 16;
-  p.BN = std::min(co16, 128);
+  p.BN = tc_bt_rows(g.Co);
   const int ntiles_n = (g.Co + p.BN - 1) / p.BN;
   p.a_stage_bytes = 128 * p.KB * 4;
   p.b_stage_bytes = (p.BN * p.KB * 4 + 1023) / 1024 * 1024;
   const int stage = p.a_stage_bytes + p.b_stage_bytes;
   // small grids (<= one CTA per SM) take the whole shared memory for a deeper TMA ring; larger ones keep two CTAs per SM
   const long long nctas = (long long)tiles_b * p.tiles_y * p.tiles_x * ntiles_n * ncls;
-  const int budget = nctas <= NSM ? 200 * 1024 : 96 * 1024;
+  const int budget = (nctas <= NSM || p.BN > 128) ? 200 * 1024 : 96 * 1024;
   p.nstage = std::max(2, std::min(8, budget / stage));
   p.tmem_cols = std::max(32, pow2_ge(p.BN));
   // split-K when the grid leaves most SMs idle and the contraction is long
@@ -370,6 +399,18 @@ bool k_tapconv_tc_multi(St st, const TapGeom* cls, int ncls, const float* const*
       while (ks > 1 && ((size_t)nctas * ks * 128 * p.BN * sizeof(float) > st.ws->part_bytes || nctas > st.ws->ncounters)) --ks;
       p.ksplit = std::max(1, ks);
     }
+  }
+  // Clusters of 2 / 4 CTAs along x can share the weight tiles by TMA multicast (a cluster of cs moves 16 + 16/cs KB per
+  // 128 x 128 x 32 MMA group instead of 32 KB from L2).  Measured on B200 (tests/test_gpu_tiles.py covers the path): no gain --
+  // D conv 64->128 forward 113 / 117 / 120 us and C1b FC 256->128 forward 786 / 782 / 826 us at cs = 1 / 2 / 4 -- so the per-tap
+  // kernel is not bound by L2 bandwidth but by the bytes it can keep in flight in shared memory (6 stages x 32 KB per SM cover
+  // ~0.8 us of L2 latency at full tensor rate).  Off by default; DCGANSR_TC_CLUSTER=2|4 enables it.
+  p.cs = 1;
+  {
+    const long long gx = (long long)tiles_b * p.tiles_y * p.tiles_x;
+    int want = 1;
+    if (const char* e = getenv("DCGANSR_TC_CLUSTER")) want = atoi(e);
+    if (want > 1 && p.ksplit == 1 && gx >= 2 * want && nctas >= 2 * NSM && p.BN % (16 * want) == 0) p.cs = want == 4 ? 4 : 2;
   }
   p.act = act; p.neg = negval;
   for (int i = 0; i < ncls; ++i) {
@@ -409,7 +450,7 @@ bool k_tapconv_tc_multi(St st, const TapGeom* cls, int ncls, const float* const*
     const cuuint64_t ktot = (cuuint64_t)cls[i].ntaps * g.Ci;
     cuuint64_t dims[2] = {ktot, (cuuint64_t)g.Co};
     cuuint64_t strides[1] = {ktot * 4};
-    cuuint32_t box[2] = {(cuuint32_t)p.KB, (cuuint32_t)p.BN};
+    cuuint32_t box[2] = {(cuuint32_t)p.KB, (cuuint32_t)(p.BN / p.cs)};
     r = g_encode(&maps.b[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)bp[i], dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
                  swz_of(p.KB), CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled(B) failed: " + std::to_string((int)r); return false; }
@@ -425,8 +466,25 @@ bool k_tapconv_tc_multi(St st, const TapGeom* cls, int ncls, const float* const*
     }
     configured = true;
   }
-  dim3 grid((unsigned)(tiles_b * p.tiles_y * p.tiles_x), (unsigned)ntiles_n, (unsigned)(ncls * p.ksplit));
-  tapconv_tc_kernel<<<grid, TC_THREADS, smem, st.s>>>(mapA, maps, p, out, st.ws ? st.ws->part : nullptr, st.ws ? st.ws->counters : nullptr);
+  const unsigned gx = (unsigned)(tiles_b * p.tiles_y * p.tiles_x);
+  dim3 grid((gx + p.cs - 1) / p.cs * p.cs, (unsigned)ntiles_n, (unsigned)(ncls * p.ksplit));      // padded to whole clusters: the extra CTAs'
+                                                                                                 // pixels are out of range (loads zero-filled, stores masked)
+  if (p.cs > 1) {
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = grid; lc.blockDim = dim3(TC_THREADS); lc.dynamicSmemBytes = smem; lc.stream = st.s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)p.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    float* partp = st.ws ? st.ws->part : nullptr;
+    int* cntp = st.ws ? st.ws->counters : nullptr;
+    if (cudaLaunchKernelEx(&lc, tapconv_tc_kernel, mapA, maps, p, out, partp, cntp) != cudaSuccess) {
+      if (err) *err = std::string("cluster launch failed: ") + cudaGetErrorString(cudaGetLastError());
+      return false;
+    }
+  } else
+    tapconv_tc_kernel<<<grid, TC_THREADS, smem, st.s>>>(mapA, maps, p, out, st.ws ? st.ws->part : nullptr, st.ws ? st.ws->counters : nullptr);
   DSR_LAUNCHED(st, "tapconv_tc", flops, WORK_FLOPS);
   return true;
 }

@@ -55,3 +55,41 @@ def test_big_layer_fwd_dgrad_wgrad(ctx, ctx_fast, shape, mode):
     L.check(getattr(lib, pre + "wgrad")(hc, ptr(x), ptr(dy), ptr(dw), *args), hc)
     ref = (ops.fullconv2d_wgrad(X, DY, wt.shape, s, p) if full else ops.conv2d_wgrad(X, DY, wt.shape, s, p)).numpy()
     assert rel_err(dw, ref) <= tol, ("wgrad", rel_err(dw, ref))
+
+
+# grids of >= 2 x 148 CTAs on the per-tap kernel: thread-block clusters of 2 / 4 CTAs share every weight tile by TMA multicast
+CLUSTER_SHAPES = [
+    ("conv", 40, 64, 64, 64, 128, 4, 2, 1),     # D layer 2 (train.lua:124) at 64^2: TMA 2-D weight boxes (stride-2 parity view), dgrad 4 classes
+    ("full", 16, 128, 32, 32, 64, 4, 2, 1),     # C1b G layer 3 shape class: pre-tiled weight images (1-D bulk multicast)
+    ("conv", 37, 128, 32, 32, 256, 4, 2, 1),    # two N tiles, odd tile count (the grid is padded to whole clusters)
+]
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4])
+@pytest.mark.parametrize("shape", CLUSTER_SHAPES)
+def test_per_tap_kernel_clusters(ctx_fast, shape, cluster, monkeypatch):
+    monkeypatch.setenv("DCGANSR_TC_CLUSTER", str(cluster))
+    monkeypatch.setenv("DCGANSR_NO_HALO", "1")          # keep these shapes on the per-tap kernel
+    kind, n, cin, h, w, cout, k, s, p = shape
+    full = kind == "full"
+    r = rng(hash(shape[1:]) % 2**31)
+    x = r.standard_normal((n, cin, h, w)).astype(np.float32)
+    wt = (0.1 * r.standard_normal((cin, cout, k, k) if full else (cout, cin, k, k))).astype(np.float32)
+    ho, wo = ((h - 1) * s - 2 * p + k, (w - 1) * s - 2 * p + k) if full else ((h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1)
+    dy = r.standard_normal((n, cout, ho, wo)).astype(np.float32)
+    lib, hc = ctx_fast.lib, ctx_fast.h
+    pre = "dcgansr_fullconv2d_" if full else "dcgansr_conv2d_"
+    args = (n, cin, h, w, cout, k, s, p)
+    X, W, DY = t64(x), t64(wt), t64(dy)
+    y = np.empty((n, cout, ho, wo), np.float32)
+    L.check(getattr(lib, pre + "fwd")(hc, ptr(x), ptr(wt), ptr(y), *args), hc)
+    ref = (ops.fullconv2d_fwd(X, W, s, p) if full else ops.conv2d_fwd(X, W, s, p)).numpy()
+    assert rel_err(y, ref) <= FAST_TOL, ("fwd", rel_err(y, ref))
+    for i in range(0, n, 7):
+        assert rel_err(y[i], ref[i]) <= 2 * FAST_TOL, ("fwd image", i)
+    dx = np.empty_like(x)
+    L.check(getattr(lib, pre + "dgrad")(hc, ptr(dy), ptr(wt), ptr(dx), *args), hc)
+    ref = (ops.fullconv2d_dgrad(DY, W, s, p) if full else ops.conv2d_dgrad(DY, W, x.shape, s, p)).numpy()
+    assert rel_err(dx, ref) <= FAST_TOL, ("dgrad", rel_err(dx, ref))
+    for i in range(0, n, 7):
+        assert rel_err(dx[i], ref[i]) <= 2 * FAST_TOL, ("dgrad image", i)
