@@ -13,6 +13,7 @@
 //     master gradient in fixed order (deterministic, accumulating like accGradParameters).
 #include "common.h"
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -419,6 +420,61 @@ __global__ void __launch_bounds__(256) thin_in_kernel(const ThinIn p, const floa
   else run(ActC<-1>{});
 }
 
+// Pixel-per-thread variant for few-channel inputs with more than one channel (RGB: D's first conv 3->64, FC 3->96, the dgrad of
+// C 12->3; train.lua:99,111,121).  One thread = one output pixel of one sub-pixel class x CH consecutive couts: the CH weights of a
+// (tap, ci) are one conflict-free BROADCAST read of shared memory per warp (every lane the same address) feeding CH FMAs per
+// lane, where thin_in_kernel spends one 512-byte shared-memory read per 4 FMAs per lane (it is shared-memory bound at CI = 3:
+// D conv 3->64 615 us for 318 MB at C3b).  Lanes are consecutive pixels of a row: coalesced 12 B-strided input reads through L1,
+// 4*CH-byte output segments.
+template <int CI, int CH>
+__global__ void __launch_bounds__(256) thin_in_px_kernel(const ThinIn p, const float* __restrict__ in, float* __restrict__ out) {
+  extern __shared__ __align__(16) float sw[];                  // [t][ci][CH] of this (class, cout chunk)
+  const int nchunk = p.Co / CH;
+  const int cls = blockIdx.y / nchunk, chunk = blockIdx.y - cls * nchunk;
+  const ThinInCls& c = p.c[cls];
+  for (int i = threadIdx.x; i < c.ntaps * CI * CH; i += 256) {
+    const int tc = i / CH, j = i - tc * CH;
+    sw[i] = c.wp[(int64_t)tc * p.Co + chunk * CH + j];
+  }
+  __syncthreads();
+  const int64_t npix = (int64_t)p.N * c.Hg * c.Wg;
+  auto run = [&](auto actc) {
+  constexpr int A = decltype(actc)::value;
+  for (int64_t pix = (int64_t)blockIdx.x * 256 + threadIdx.x; pix < npix; pix += (int64_t)gridDim.x * 256) {
+    int64_t q = pix;
+    const int gx = (int)(q % c.Wg); q /= c.Wg;
+    const int gy = (int)(q % c.Hg);
+    const int n = (int)(q / c.Hg);
+    float4 acc[CH / 4];
+#pragma unroll
+    for (int j = 0; j < CH / 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < c.ntaps; ++t) {
+      const int iy = gy * p.si + c.dy[t], ix = gx * p.si + c.dx[t];
+      if (iy < 0 || iy >= p.Hi || ix < 0 || ix >= p.Wi) continue;
+      const float* ip = in + ((int64_t)(n * p.Hi + iy) * p.Wi + ix) * CI;
+      const float4* w = reinterpret_cast<const float4*>(sw + t * CI * CH);
+#pragma unroll
+      for (int ci = 0; ci < CI; ++ci) {
+        const float x = __ldg(ip + ci);
+#pragma unroll
+        for (int j = 0; j < CH / 4; ++j) {
+          const float4 wv = w[ci * (CH / 4) + j];
+          acc[j].x = fmaf(x, wv.x, acc[j].x); acc[j].y = fmaf(x, wv.y, acc[j].y);
+          acc[j].z = fmaf(x, wv.z, acc[j].z); acc[j].w = fmaf(x, wv.w, acc[j].w);
+        }
+      }
+    }
+    float* o = out + ((int64_t)(n * p.Ho + gy * p.so + c.oy0) * p.Wo + gx * p.so + c.ox0) * p.Co + chunk * CH;
+#pragma unroll
+    for (int j = 0; j < CH / 4; ++j) *reinterpret_cast<float4*>(o + 4 * j) = thin_act4<A>(acc[j], p.act, p.neg);
+  }
+  };
+  if (p.act == ACT_NONE) run(ActC<ACT_NONE>{});
+  else if (p.act == ACT_RELU) run(ActC<ACT_RELU>{});
+  else if (p.act == ACT_LRELU) run(ActC<ACT_LRELU>{});
+  else run(ActC<-1>{});
+}
+
 bool thin_in_supported(const TapGeom* cls, int ncls) {
   if (ncls < 1 || ncls > 4) return false;
   const TapGeom& g = cls[0];
@@ -456,6 +512,43 @@ bool k_tapconv_thin_in(St st, const TapGeom* cls, int ncls, const float* const* 
   }
   if (maxtot <= 0) return true;
   bytes += 4.0 * g.N * g.Hi * g.Wi * g.Ci;
+  // Long per-output contractions (taps x Ci >= 16: the stride-2 convs, where thin_in_kernel is bound by its shared-memory weight
+  // reads) and few-cout RGB layers take the pixel-per-thread kernel; measured on B200 at C3b / C2 sizes: D conv 3->64 forward
+  // 312 -> 171 us, C 12->3 dgrad 460 -> 314 us, D conv 1->64 25 -> 17 us.  Short contractions with many couts stay on
+  // thin_in_kernel, whose lanes run along the couts (FC 3->96 forward 287 us vs 471, FC 1->64 48 vs 99: output-write bound).
+  // DCGANSR_THIN_IN_PX=0 / 1 forces the choice for A/B runs.
+  {
+    int maxt1 = 1;
+    for (int i = 0; i < ncls; ++i) maxt1 = std::max(maxt1, cls[i].ntaps);
+    const char* e = getenv("DCGANSR_THIN_IN_PX");
+    const bool px = e ? atoi(e) != 0 : (maxt1 * g.Ci >= 16 || (g.Ci >= 2 && g.Co <= 16));
+    const int CH = g.Co % 16 == 0 ? 16 : (g.Co % 12 == 0 ? 12 : (g.Co % 8 == 0 ? 8 : 4));
+    if (px) {
+      int64_t maxpix = 0;
+      int maxt2 = 1;
+      for (int i = 0; i < ncls; ++i) { maxpix = std::max<int64_t>(maxpix, (int64_t)g.N * cls[i].Hg * cls[i].Wg); maxt2 = std::max(maxt2, cls[i].ntaps); }
+      dim3 grid2((unsigned)std::min<int64_t>((maxpix + 255) / 256, NSM * 8), (unsigned)(ncls * (g.Co / CH)));
+      const size_t smem2 = (size_t)maxt2 * g.Ci * CH * sizeof(float);
+#define THIN_PX_LAUNCH(CI_, CH_) thin_in_px_kernel<CI_, CH_><<<grid2, 256, smem2, st.s>>>(p, in, out)
+#define THIN_PX_CH(CI_)                                         \
+      do {                                                      \
+        if (CH == 16) THIN_PX_LAUNCH(CI_, 16);                  \
+        else if (CH == 12) THIN_PX_LAUNCH(CI_, 12);             \
+        else if (CH == 8) THIN_PX_LAUNCH(CI_, 8);               \
+        else THIN_PX_LAUNCH(CI_, 4);                            \
+      } while (0)
+      switch (g.Ci) {
+        case 1: THIN_PX_CH(1); break;
+        case 2: THIN_PX_CH(2); break;
+        case 3: THIN_PX_CH(3); break;
+        default: THIN_PX_CH(4); break;
+      }
+#undef THIN_PX_CH
+#undef THIN_PX_LAUNCH
+      DSR_LAUNCHED(st, "tapconv_thin_in", bytes, WORK_BYTES);
+      return true;
+    }
+  }
   int vp = 1;
   while (vp < g.Co / 4) vp <<= 1;
   p.vpad = vp;
