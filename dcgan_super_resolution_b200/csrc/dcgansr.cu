@@ -528,6 +528,12 @@ struct dcgansr_net {
   int in_c = 0, in_h = 0, in_w = 0, max_batch = 0;
   int64_t nparams = 0, nbn = 0;
   float *params = nullptr, *grads = nullptr, *adam_m = nullptr, *adam_v = nullptr;
+  // data parallel: [stage | grads] is ONE allocation.  stage = (running_mean, running_var) / world [+ the 3 step losses], packed right
+  // before the backward walk, so that the all-reduce of the walk's LAST gradient bucket (the first conv's, at offset 0) carries
+  // them too: one collective instead of five latency-bound ones per step
+  float* grads_base = nullptr;
+  int64_t stage_len = 0;
+  bool stage_live = false;                            // the stage holds packed values waiting for their all-reduce
   int64_t* adam_t = nullptr;
   float* adam_step = nullptr;
   float *bn_rmean = nullptr, *bn_rvar = nullptr, *bn_save = nullptr;
@@ -567,11 +573,12 @@ static void net_release_device(dcgansr_net* net) {
     if (m.owns_out && m.out) cudaFree(m.out);
     m.out = nullptr; m.owns_out = false; m.save_mean = nullptr; m.save_invstd = nullptr;
   }
-  void** ptrs[] = {(void**)&net->params, (void**)&net->grads, (void**)&net->adam_m, (void**)&net->adam_v, (void**)&net->adam_t,
+  void** ptrs[] = {(void**)&net->params, (void**)&net->grads_base, (void**)&net->adam_m, (void**)&net->adam_v, (void**)&net->adam_t,
                    (void**)&net->adam_step, (void**)&net->bn_rmean, (void**)&net->bn_rvar, (void**)&net->bn_save, (void**)&net->in_buf,
                    (void**)&net->gbuf[0], (void**)&net->gbuf[1], (void**)&net->bn_partials, (void**)&net->bn_sums,
                    (void**)&net->bn_sums_total, (void**)&net->bn_fmeans, (void**)&net->wscratch, (void**)&net->pack_jobs};
   for (void** p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
+  net->grads = nullptr;
   net->last_out = nullptr; net->last_batch = 0;
   net->ctx = nullptr;
 }
@@ -676,7 +683,10 @@ static int bucket_allreduce_async(dcgansr_ctx* ctx, dcgansr_net* net, int bucket
   }
   CK(ctx, cudaEventRecord(ctx->bucket_ev[k], ctx->stream));
   CK(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->bucket_ev[k], 0));
-  if (int rc = nccl_allreduce(ctx, net->grads + net->buckets[bucket].first, net->buckets[bucket].second, ncclFloat, ctx->comm_stream)) return rc;
+  float* ptr = net->grads + net->buckets[bucket].first;
+  int64_t cnt = net->buckets[bucket].second;
+  if (bucket == 0 && net->stage_live && net->buckets[0].first == 0) { ptr -= net->stage_len; cnt += net->stage_len; net->stage_live = false; }
+  if (int rc = nccl_allreduce(ctx, ptr, cnt, ncclFloat, ctx->comm_stream)) return rc;
   ++ctx->buckets_in_flight;
   return 0;
 }
@@ -1101,7 +1111,9 @@ int dcgansr_net_create(dcgansr_ctx* ctx, const dcgansr_layer* layers, int n_laye
   };
   cudaError_t e = cudaSuccess;
   auto A = [&](float** p, int64_t n) { if (e == cudaSuccess) e = dalloc(p, n); };
-  A(&net->params, np4); A(&net->grads, np4); A(&net->adam_m, np4); A(&net->adam_v, np4);
+  net->stage_len = (2 * net->nbn + 4 + 3) / 4 * 4;
+  A(&net->params, np4); A(&net->grads_base, np4 + net->stage_len); A(&net->adam_m, np4); A(&net->adam_v, np4);
+  if (e == cudaSuccess) net->grads = net->grads_base + net->stage_len;
   A(&net->adam_step, 4);
   A(&net->bn_rmean, net->nbn); A(&net->bn_rvar, net->nbn); A(&net->bn_save, 4 * net->nbn);          // (mean, invstd) x 2 sample groups
   if (e == cudaSuccess) e = cudaMalloc((void**)&net->adam_t, sizeof(int64_t));
@@ -1301,19 +1313,31 @@ int dcgansr_net_adam(dcgansr_net* net, double lr, double beta1, double beta2, do
 // ---- the fused step ---------------------------------------------------------------------------
 static bool overlap_on(dcgansr_ctx* ctx) { return ctx->world() > 1 && !getenv("DCGANSR_NO_OVERLAP"); }
 
+// Stage = what rides along with the gradient exchange of a net (local-batch-statistics mode: the running statistics averaged over
+// the ranks; for G also the three step losses).  Packed on the main stream before the backward walk whose last bucket carries it.
+static void stage_pack(dcgansr_ctx* ctx, dcgansr_net* net, const float* losses) {
+  if (ctx->world() <= 1) return;
+  k_stage_pack(ctx->st(), net->bn_rmean, net->bn_rvar, (int)net->nbn, losses, net->grads_base, 1.f / ctx->world());
+  net->stage_live = true;
+}
 // bucketed == true: the backward walk already issued every bucket on the communication stream -> just join
-static int allreduce_grads(dcgansr_ctx* ctx, dcgansr_net* net, bool bucketed = false) {
+static int allreduce_grads(dcgansr_ctx* ctx, dcgansr_net* net, bool bucketed, float* losses) {
   if (ctx->world() <= 1) return 0;
+  const bool staged = net->stage_live || bucketed;       // bucketed: bucket 0 took the stage with it (stage_live already cleared)
   if (bucketed) {
     if (int rc = bucket_join(ctx)) return rc;
-  } else if (int rc = nccl_allreduce(ctx, net->grads, net->nparams, ncclFloat, ctx->stream)) return rc;
-  if (!ctx->cfg.sync_bn && net->nbn > 0) {
-    // running statistics averaged at the gradient exchange point (local batch statistics mode)
-    if (int rc = nccl_allreduce(ctx, net->bn_rmean, net->nbn, ncclFloat, ctx->stream)) return rc;
-    if (int rc = nccl_allreduce(ctx, net->bn_rvar, net->nbn, ncclFloat, ctx->stream)) return rc;
-    k_scale(ctx->st(), net->bn_rmean, net->nbn, 1.f / ctx->world());
-    k_scale(ctx->st(), net->bn_rvar, net->nbn, 1.f / ctx->world());
+    if (net->stage_live) {      // no bucket 0 at offset 0 (should not happen with these graphs): the stage travels alone
+      if (int rc = nccl_allreduce(ctx, net->grads_base, net->stage_len, ncclFloat, ctx->stream)) return rc;
+      net->stage_live = false;
+    }
+  } else {
+    float* ptr = net->grads;
+    int64_t cnt = net->nparams;
+    if (net->stage_live) { ptr = net->grads_base; cnt += net->stage_len; net->stage_live = false; }
+    if (int rc = nccl_allreduce(ctx, ptr, cnt, ncclFloat, ctx->stream)) return rc;
   }
+  if (staged) k_stage_unpack(ctx->st(), net->grads_base, ctx->cfg.sync_bn ? nullptr : net->bn_rmean, ctx->cfg.sync_bn ? nullptr : net->bn_rvar,
+                             (int)net->nbn, losses);
   return 0;
 }
 
@@ -1346,6 +1370,7 @@ static int step_body(dcgansr_ctx* ctx, dcgansr_net* G, dcgansr_net* D, const dcg
     }
     if (int rc = net_forward_dev(D, fake, B)) return rc;                              // :242-243
     k_loss(st, lossk, D->last_out, dcount, lvec, per, cfg->fake_label, n_total, ctx->d_losses + 1, D->gbuf[0]);
+    stage_pack(ctx, D, nullptr);
     if (int rc = net_backward_dev(D, fake, D->gbuf[0], B, true, false, &dxd, 1, 0, overlap_on(ctx))) return rc;      // second pass: grads final
   } else {
     // D(real) and D(fake) as ONE pass over [real; fake] (D was created for >= 2B samples): the generator forward does not
@@ -1367,9 +1392,10 @@ static int step_body(dcgansr_ctx* ctx, dcgansr_net* G, dcgansr_net* D, const dcg
     if (int rc = net_forward_dev(D, D->in_buf, B, 2)) return rc;
     k_loss(st, lossk, D->last_out, dcount, nullptr, per, cfg->real_label, n_total, ctx->d_losses + 0, D->gbuf[0]);
     k_loss(st, lossk, D->last_out + dcount, dcount, lvec, per, cfg->fake_label, n_total, ctx->d_losses + 1, D->gbuf[0] + dcount);
+    stage_pack(ctx, D, nullptr);
     if (int rc = net_backward_dev(D, D->in_buf, D->gbuf[0], B, true, false, &dxd, 2, 0, overlap_on(ctx))) return rc;
   }
-  if (int rc = allreduce_grads(ctx, D, overlap_on(ctx))) return rc;
+  if (int rc = allreduce_grads(ctx, D, overlap_on(ctx), nullptr)) return rc;
   if (int rc = net_adam_dev(D, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps)) return rc;   // optim.adam(fDx) :280
 
   // ---------------- fGx (train.lua:256-272) ----------------
@@ -1379,11 +1405,11 @@ static int step_body(dcgansr_ctx* ctx, dcgansr_net* G, dcgansr_net* D, const dcg
   k_loss(st, lossk, dout_fake, dcount, nullptr, per, cfg->gen_label, n_total, ctx->d_losses + 2, D->gbuf[0]);
   if (int rc = net_backward_dev(D, fake, D->gbuf[0], B, false, true, &dxd, 1, fake_group)) return rc;  // netD:updateGradInput :268
   const float* dummy = nullptr;
+  stage_pack(ctx, G, ctx->d_losses);                  // the three loss scalars (each rank's share of the global mean) ride with G's gradients
   if (int rc = net_backward_dev(G, ctx->lr_buf, dxd, B, true, false, &dummy, 1, 0, overlap_on(ctx))) return rc; // netG:backward :270
-  if (int rc = allreduce_grads(ctx, G, overlap_on(ctx))) return rc;
+  if (int rc = allreduce_grads(ctx, G, overlap_on(ctx), ctx->d_losses)) return rc;
   if (int rc = net_adam_dev(G, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps)) return rc;   // optim.adam(fGx) :283
-  if (world > 1)
-    if (int rc = nccl_allreduce(ctx, ctx->d_losses, 3, ncclFloat, ctx->stream)) return rc;
+  (void)world;
   return 0;
 }
 

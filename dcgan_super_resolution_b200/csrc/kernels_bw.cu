@@ -14,6 +14,7 @@
 //   calMSE loop                   train.lua:193-195,237-239     optim.adam   train.lua:280
 #include "common.h"
 #include <math.h>
+#include <algorithm>
 
 #define NSM 148
 
@@ -858,6 +859,27 @@ void k_adam(St st, float* p, const float* g, float* m, float* v, int64_t count, 
 __global__ void fill_kernel(float* __restrict__ p, int64_t count, float v) {
   int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) p[i] = v;
+}
+// stage = [rmean * inv_world (nbn) | rvar * inv_world (nbn) | losses (3, as they are) | pad]: what a net's last gradient bucket carries
+__global__ void stage_pack_kernel(const float* __restrict__ rmean, const float* __restrict__ rvar, int nbn, const float* __restrict__ losses,
+                                  float* __restrict__ stage, float inv_world) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nbn) { stage[i] = rmean[i] * inv_world; stage[nbn + i] = rvar[i] * inv_world; }
+  if (i < 4) stage[2 * nbn + i] = (losses && i < 3) ? losses[i] : 0.f;
+}
+__global__ void stage_unpack_kernel(const float* __restrict__ stage, float* __restrict__ rmean, float* __restrict__ rvar, int nbn,
+                                    float* __restrict__ losses) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nbn && rmean) { rmean[i] = stage[i]; rvar[i] = stage[nbn + i]; }
+  if (i < 3 && losses) losses[i] = stage[2 * nbn + i];
+}
+void k_stage_pack(St st, const float* rmean, const float* rvar, int nbn, const float* losses, float* stage, float inv_world) {
+  stage_pack_kernel<<<(std::max(nbn, 4) + 255) / 256, 256, 0, st.s>>>(rmean, rvar, nbn, losses, stage, inv_world);
+  DSR_LAUNCHED(st, "stage_pack", 16.0 * nbn + 32, WORK_BYTES);
+}
+void k_stage_unpack(St st, const float* stage, float* rmean, float* rvar, int nbn, float* losses) {
+  stage_unpack_kernel<<<(std::max(nbn, 4) + 255) / 256, 256, 0, st.s>>>(stage, rmean, rvar, nbn, losses);
+  DSR_LAUNCHED(st, "stage_unpack", 16.0 * nbn + 32, WORK_BYTES);
 }
 void k_fill(St st, float* p, int64_t count, float v) {
   if (count <= 0) return;
