@@ -129,6 +129,7 @@ void k_adam(St st, float* p, const float* g, float* m, float* v, int64_t count, 
             double beta1, double beta2, double eps);
 void k_stage_pack(St st, const float* rmean, const float* rvar, int nbn, const float* losses, float* stage, float inv_world);
 void k_stage_unpack(St st, const float* stage, float* rmean, float* rvar, int nbn, float* losses);
+void k_dacc(St st, double* dst, const double* src, int n);
 void k_fill(St st, float* p, int64_t count, float v);
 void k_scale(St st, float* p, int64_t count, float s);
 void k_flush(St st, float* buf, int64_t count);

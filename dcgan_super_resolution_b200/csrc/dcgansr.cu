@@ -68,6 +68,8 @@ struct dcgansr_ctx {
   size_t label_cap = 0;
   float* lr_buf = nullptr;     // 2x2 box down-sampled batch (train.lua:225-230)
   size_t lr_cap = 0;
+  float* fake_buf = nullptr;   // generator output of the whole batch when G runs micro-batched and D is not paired
+  size_t fake_cap = 0;
   NcclApi nccl;
   ncclComm_t comm = nullptr;
   // CUDA graphs of the step (cfg.use_graph), one per (nets, staged batch, batch size, step cfg)
@@ -541,6 +543,7 @@ struct dcgansr_net {
   float* gbuf[2] = {nullptr, nullptr};
   int64_t gelems = 0;
   double *bn_partials = nullptr, *bn_sums = nullptr, *bn_sums_total = nullptr;
+  double *mb_fsum = nullptr, *mb_bsum = nullptr;       // micro-batched execution: whole-batch BN sums (forward / backward), 2 x nbn each
   float* bn_fmeans = nullptr;                         // (float)(sum / n) of the BN backward reductions, 2 groups x 2C
   float* wscratch = nullptr;
   size_t wscratch_bytes = 0;
@@ -576,7 +579,7 @@ static void net_release_device(dcgansr_net* net) {
   void** ptrs[] = {(void**)&net->params, (void**)&net->grads_base, (void**)&net->adam_m, (void**)&net->adam_v, (void**)&net->adam_t,
                    (void**)&net->adam_step, (void**)&net->bn_rmean, (void**)&net->bn_rvar, (void**)&net->bn_save, (void**)&net->in_buf,
                    (void**)&net->gbuf[0], (void**)&net->gbuf[1], (void**)&net->bn_partials, (void**)&net->bn_sums,
-                   (void**)&net->bn_sums_total, (void**)&net->bn_fmeans, (void**)&net->wscratch, (void**)&net->pack_jobs};
+                   (void**)&net->bn_sums_total, (void**)&net->mb_fsum, (void**)&net->mb_bsum, (void**)&net->bn_fmeans, (void**)&net->wscratch, (void**)&net->pack_jobs};
   for (void** p : ptrs) { if (*p) cudaFree(*p); *p = nullptr; }
   net->grads = nullptr;
   net->last_out = nullptr; net->last_batch = 0;
@@ -610,13 +613,19 @@ static void net_pack_all(dcgansr_net* net) {
 // groups > 1: the batch holds `groups` independent minibatches of B samples each (the fused step runs D(real) and D(fake)
 // as ONE pass over 2B samples): convolutions see groups*B samples, every BatchNorm normalises each group with its own
 // statistics and updates the running statistics group after group -- exactly what `groups` separate forwards would do.
-static int net_forward_dev(dcgansr_net* net, const float* in, int B, int groups = 1) {
+// stop >= 0: run the modules [0, stop) only and return the input of module `stop` in *stop_in (micro-batched statistics passes).
+// bn_frozen: BatchNorm modules normalise with the statistics already in save_mean / save_invstd (whole-batch statistics of a
+// micro-batched step) and leave the running statistics alone.
+static int net_forward_dev(dcgansr_net* net, const float* in, int B, int groups = 1, int stop = -1, bool bn_frozen = false,
+                           const float** stop_in = nullptr) {
   dcgansr_ctx* ctx = net->ctx;
   St st = ctx->st();
   const float* cur = in;
   const bool sync = ctx->cfg.sync_bn && ctx->world() > 1;
   const int NB = B * groups;
-  for (auto& m : net->mods) {
+  for (size_t mi = 0; mi < net->mods.size(); ++mi) {
+    Mod& m = net->mods[mi];
+    if ((int)mi == stop) { if (stop_in) *stop_in = cur; CKLAST(ctx); return 0; }
     switch (m.kind) {
       case DCGANSR_UPNEAREST:
         k_upnearest_fwd(st, cur, m.out, NB, m.hin, m.win, m.cin, m.L.scale);
@@ -630,6 +639,12 @@ static int net_forward_dev(dcgansr_net* net, const float* in, int B, int groups 
       case DCGANSR_BN: {
         int64_t P = (int64_t)B * m.hin * m.win;
         int C = m.cin;
+        if (bn_frozen) {
+          k_bn_apply_act(st, cur, m.out, P * groups, C, net->params + m.p_off, net->params + m.p_off + C, m.save_mean, m.save_invstd,
+                         m.fused_act, m.fused_neg);
+          cur = m.out;
+          break;
+        }
         if (!sync) {
           k_bn_fwd_grouped(st, cur, m.out, P, C, groups, net->params + m.p_off, net->params + m.p_off + C, m.save_mean, m.save_invstd,
                            2 * net->nbn, net->bn_rmean + m.bn_off, net->bn_rvar + m.bn_off, m.L.eps, m.L.momentum, m.fused_act, m.fused_neg,
@@ -703,8 +718,12 @@ static int bucket_join(dcgansr_ctx* ctx) {
 // Returns the gradient w.r.t. the net input in *dx_out (nullptr when need_dx is false).
 // groups / goff: the cached activations hold several B-sample groups (see net_forward_dev); this walk covers groups
 // [goff, goff + groups): `in` and `dy` point at the first sample of group goff, cached module outputs are offset likewise.
+// Micro-batched walk (mb != nullptr): BatchNorm modules use the whole-batch sums in net->mb_bsum (n = b_total * H * W), exactly
+// like the sync_bn path uses the all-reduced ones.  stop_mod >= 0: the walk ends at that BatchNorm module after adding this
+// micro-batch's (sum g, sum g*xhat) to its whole-batch sums.  param_grads: add dgamma / dbeta (once per step, from the totals).
+struct MbWalk { int b_total; int stop_mod; bool param_grads; };
 static int net_backward_dev(dcgansr_net* net, const float* in, const float* dy, int B, bool acc, bool need_dx,
-                            const float** dx_out, int groups = 1, int goff = 0, bool reduce_buckets = false) {
+                            const float** dx_out, int groups = 1, int goff = 0, bool reduce_buckets = false, const MbWalk* mb = nullptr) {
   dcgansr_ctx* ctx = net->ctx;
   St st = ctx->st();
   const bool sync = ctx->cfg.sync_bn && ctx->world() > 1;
@@ -748,6 +767,20 @@ static int net_backward_dev(dcgansr_net* net, const float* in, const float* dy, 
         // read), else from the cached output (fGx walks D with post-Adam weights and pre-Adam activations, train.lua:264-270)
         const bool remask = net->fwd_ver == net->params_ver && (m.fused_act == ACT_RELU || m.fused_act == ACT_LRELU) && !getenv("DCGANSR_BN_READ_Y");
         const float* yact = (m.fused_act != ACT_NONE && !remask) ? mout : nullptr;
+        if (mb) {
+          double* tot = net->mb_bsum + 2 * m.bn_off;
+          if (i == mb->stop_mod) {
+            k_bn_bwd_reduce(st, cur, yact, inp, P, C, gamma, beta, m.save_mean, m.save_invstd, m.fused_act, m.fused_neg, net->bn_partials, net->bn_sums);
+            k_dacc(st, tot, net->bn_sums, 2 * C);
+            CKLAST(ctx);
+            return 0;
+          }
+          if (acc && mb->param_grads) k_bn_bwd_param(st, tot, C, net->grads + m.p_off, net->grads + m.p_off + C);
+          k_bn_bwd_apply(st, cur, yact, inp, gall, P, C, gamma, beta, m.save_mean, m.save_invstd, m.fused_act, m.fused_neg, tot,
+                         (double)mb->b_total * m.hin * m.win, net->bn_fmeans);
+          cur = gall;
+          break;
+        }
         if (!sync) {
           k_bn_bwd_grouped(st, cur, yact, inp, gall, P, C, groups, gamma, beta,
                            m.save_mean + (int64_t)goff * 2 * net->nbn, m.save_invstd + (int64_t)goff * 2 * net->nbn, 2 * net->nbn,
@@ -788,6 +821,73 @@ static int net_backward_dev(dcgansr_net* net, const float* in, const float* dy, 
     }
   }
   if (dx_out) *dx_out = cur;
+  CKLAST(ctx);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Micro-batched execution with EXACT whole-batch BatchNorm (BASELINE config C5: the activations of 128 samples of the
+// ngf = 128 generator do not fit 180 GB).  A net created for max_batch = b runs a batch B = k*b as k micro-batches; what
+// couples the samples of a batch is only BatchNorm, whose batch sums are accumulated over the micro-batches before they are
+// used -- the same structure as sync_bn, with time in the place of ranks.  Activations are recomputed instead of kept:
+//   forward : for every BatchNorm j in turn, all micro-batches run up to its input (earlier BatchNorms frozen at their final
+//             statistics) and add (sum x, sum x^2) to its whole-batch sums; then one more pass produces the outputs;
+//   backward: for every BatchNorm j from the last to the first, all micro-batches are re-forwarded and walked back down to j
+//             (later BatchNorms use their whole-batch sums) adding (sum g, sum g*xhat); the final pass walks all the way,
+//             accumulating the parameter gradients.
+// Cost: about (J + 1) forward and backward passes for J BatchNorms; result = the single-batch step up to summation order.
+// ------------------------------------------------------------------------------------------
+static int net_forward_mb(dcgansr_net* net, const float* in_all, int B, float* out_all) {
+  dcgansr_ctx* ctx = net->ctx;
+  St st = ctx->st();
+  const int b = net->max_batch, k = B / b;
+  const int64_t ie = (int64_t)b * net->in_c * net->in_h * net->in_w, oe = (int64_t)b * net->out_c * net->out_h * net->out_w;
+  if (net->nbn > 0) CK(ctx, cudaMemsetAsync(net->mb_fsum, 0, 2 * net->nbn * sizeof(double), ctx->stream));
+  for (size_t j = 0; j < net->mods.size(); ++j) {
+    Mod& m = net->mods[j];
+    if (m.kind != DCGANSR_BN) continue;
+    const int C = m.cin;
+    const int64_t P = (int64_t)b * m.hin * m.win;
+    for (int mi = 0; mi < k; ++mi) {
+      const float* x = nullptr;
+      if (int rc = net_forward_dev(net, in_all + mi * ie, b, 1, (int)j, true, &x)) return rc;
+      k_bn_stats(st, x, P, C, net->bn_partials, net->bn_sums);
+      k_dacc(st, net->mb_fsum + 2 * m.bn_off, net->bn_sums, 2 * C);
+    }
+    k_bn_finalize(st, net->mb_fsum + 2 * m.bn_off, C, (double)P * k, m.L.eps, m.L.momentum, m.save_mean, m.save_invstd,
+                  net->bn_rmean + m.bn_off, net->bn_rvar + m.bn_off);
+  }
+  for (int mi = 0; mi < k; ++mi) {
+    if (int rc = net_forward_dev(net, in_all + mi * ie, b, 1, -1, true)) return rc;
+    CK(ctx, cudaMemcpyAsync(out_all + mi * oe, net->last_out, oe * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  net->last_out = nullptr;           // the cached activations are those of the LAST micro-batch only
+  net->last_batch = 0;
+  CKLAST(ctx);
+  return 0;
+}
+
+static int net_backward_mb(dcgansr_net* net, const float* in_all, const float* dy_all, int B, bool reduce_buckets) {
+  dcgansr_ctx* ctx = net->ctx;
+  const int b = net->max_batch, k = B / b;
+  const int64_t ie = (int64_t)b * net->in_c * net->in_h * net->in_w, oe = (int64_t)b * net->out_c * net->out_h * net->out_w;
+  if (net->nbn > 0) CK(ctx, cudaMemsetAsync(net->mb_bsum, 0, 2 * net->nbn * sizeof(double), ctx->stream));
+  const float* dxd = nullptr;
+  for (int j = (int)net->mods.size() - 1; j >= 0; --j) {
+    if (net->mods[j].kind != DCGANSR_BN) continue;
+    MbWalk w{B, j, false};
+    for (int mi = 0; mi < k; ++mi) {
+      if (int rc = net_forward_dev(net, in_all + mi * ie, b, 1, -1, true)) return rc;
+      CK(ctx, cudaMemcpyAsync(net->gbuf[0], dy_all + mi * oe, oe * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+      if (int rc = net_backward_dev(net, in_all + mi * ie, net->gbuf[0], b, false, false, &dxd, 1, 0, false, &w)) return rc;
+    }
+  }
+  for (int mi = 0; mi < k; ++mi) {
+    MbWalk w{B, -1, mi == 0};
+    if (int rc = net_forward_dev(net, in_all + mi * ie, b, 1, -1, true)) return rc;
+    CK(ctx, cudaMemcpyAsync(net->gbuf[0], dy_all + mi * oe, oe * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (int rc = net_backward_dev(net, in_all + mi * ie, net->gbuf[0], b, true, false, &dxd, 1, 0, reduce_buckets && mi == k - 1, &w)) return rc;
+  }
   CKLAST(ctx);
   return 0;
 }
@@ -877,6 +977,7 @@ void dcgansr_ctx_destroy(dcgansr_ctx* ctx) {
   if (ctx->tmp) cudaFree(ctx->tmp);
   if (ctx->label_vec) cudaFree(ctx->label_vec);
   if (ctx->lr_buf) cudaFree(ctx->lr_buf);
+  if (ctx->fake_buf) cudaFree(ctx->fake_buf);
   if (ctx->d_losses) cudaFree(ctx->d_losses);
   if (ctx->h_losses) cudaFreeHost(ctx->h_losses);
   for (cudaEvent_t e : ctx->prof.pool) cudaEventDestroy(e);
@@ -1157,6 +1258,8 @@ int dcgansr_net_create(dcgansr_ctx* ctx, const dcgansr_layer* layers, int n_laye
     A(&tmpf, (int64_t)maxC * 4 * 2 + 4); net->bn_sums = (double*)tmpf; tmpf = nullptr;
     A(&tmpf, (int64_t)maxC * 4 + 4); net->bn_sums_total = (double*)tmpf;
     A(&net->bn_fmeans, (int64_t)maxC * 4 + 4);
+    A(&tmpf, net->nbn * 4 + 4); net->mb_fsum = (double*)tmpf; tmpf = nullptr;
+    A(&tmpf, net->nbn * 4 + 4); net->mb_bsum = (double*)tmpf; tmpf = nullptr;
   }
   net->wscratch_bytes = wsc;
   A(&net->wscratch, (int64_t)(wsc / sizeof(float)) + 4);
@@ -1349,6 +1452,7 @@ static int step_body(dcgansr_ctx* ctx, dcgansr_net* G, dcgansr_net* D, const dcg
   const double n_total = (double)dcount * world;
   const int lossk = cfg->loss == DCGANSR_LOSS_BCE ? LOSS_BCE : LOSS_MSE;
   const float* dxd = nullptr;
+  const bool gmb = B > G->max_batch;                  // generator micro-batched with exact whole-batch BatchNorm (config C5)
 
   // ---------------- fDx (train.lua:208-253) ----------------
   CK(ctx, cudaMemsetAsync(D->grads, 0, D->nparams * sizeof(float), ctx->stream));
@@ -1361,8 +1465,13 @@ static int step_body(dcgansr_ctx* ctx, dcgansr_net* G, dcgansr_net* D, const dcg
     if (int rc = net_backward_dev(D, real, D->gbuf[0], B, true, false, &dxd)) return rc;
 
     k_avgpool2(st, real, ctx->lr_buf, B, D->in_h, D->in_w, D->in_c);                  // train.lua:225-230
-    if (int rc = net_forward_dev(G, ctx->lr_buf, B)) return rc;                       // :233-234
-    fake = G->last_out;
+    if (gmb) {
+      if (int rc = net_forward_mb(G, ctx->lr_buf, B, ctx->fake_buf)) return rc;
+      fake = ctx->fake_buf;
+    } else {
+      if (int rc = net_forward_dev(G, ctx->lr_buf, B)) return rc;                     // :233-234
+      fake = G->last_out;
+    }
     const float* lvec = nullptr;
     if (cfg->pixel_label) {                                                           // :237-239,245
       k_pixel_mse(st, real, fake, ctx->label_vec, B, (int64_t)D->in_c * D->in_h * D->in_w, cfg->pixel_div);
@@ -1378,10 +1487,14 @@ static int step_body(dcgansr_ctx* ctx, dcgansr_net* G, dcgansr_net* D, const dcg
     // B samples), BatchNorm keeps per-minibatch statistics (groups = 2) and updates the running statistics real-then-fake,
     // gradients accumulate over both halves exactly as the two reference backward calls do (train.lua:218-248).
     k_avgpool2(st, real, ctx->lr_buf, B, D->in_h, D->in_w, D->in_c);
-    if (int rc = net_forward_dev(G, ctx->lr_buf, B)) return rc;
     const int64_t isz = (int64_t)B * D->in_c * D->in_h * D->in_w;
     if (real != D->in_buf) CK(ctx, cudaMemcpyAsync(D->in_buf, real, isz * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
-    CK(ctx, cudaMemcpyAsync(D->in_buf + isz, G->last_out, isz * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    if (gmb) {
+      if (int rc = net_forward_mb(G, ctx->lr_buf, B, D->in_buf + isz)) return rc;     // micro-batches write straight into D's fake half
+    } else {
+      if (int rc = net_forward_dev(G, ctx->lr_buf, B)) return rc;
+      CK(ctx, cudaMemcpyAsync(D->in_buf + isz, G->last_out, isz * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
     fake = D->in_buf + isz;
     fake_group = 1;
     const float* lvec = nullptr;
@@ -1406,7 +1519,9 @@ static int step_body(dcgansr_ctx* ctx, dcgansr_net* G, dcgansr_net* D, const dcg
   if (int rc = net_backward_dev(D, fake, D->gbuf[0], B, false, true, &dxd, 1, fake_group)) return rc;  // netD:updateGradInput :268
   const float* dummy = nullptr;
   stage_pack(ctx, G, ctx->d_losses);                  // the three loss scalars (each rank's share of the global mean) ride with G's gradients
-  if (int rc = net_backward_dev(G, ctx->lr_buf, dxd, B, true, false, &dummy, 1, 0, overlap_on(ctx))) return rc; // netG:backward :270
+  if (gmb) {
+    if (int rc = net_backward_mb(G, ctx->lr_buf, dxd, B, overlap_on(ctx))) return rc;
+  } else if (int rc = net_backward_dev(G, ctx->lr_buf, dxd, B, true, false, &dummy, 1, 0, overlap_on(ctx))) return rc; // netG:backward :270
   if (int rc = allreduce_grads(ctx, G, overlap_on(ctx), ctx->d_losses)) return rc;
   if (int rc = net_adam_dev(G, cfg->lr, cfg->beta1, cfg->beta2, cfg->eps)) return rc;   // optim.adam(fGx) :283
   (void)world;
@@ -1416,7 +1531,11 @@ static int step_body(dcgansr_ctx* ctx, dcgansr_net* G, dcgansr_net* D, const dcg
 static int check_step_args(dcgansr_ctx* ctx, dcgansr_net* G, dcgansr_net* D, const dcgansr_step_cfg* cfg, int B) {
   if (!ctx || !G || !D || !cfg) return fail(ctx, DCGANSR_ERR_INVALID, "null argument");
   if (G->ctx != ctx || D->ctx != ctx) return fail(ctx, DCGANSR_ERR_INVALID, "nets belong to another context");
-  if (B <= 0 || B > G->max_batch || B > D->max_batch) return fail(ctx, DCGANSR_ERR_INVALID, "batch exceeds max_batch");
+  if (B <= 0 || B > D->max_batch) return fail(ctx, DCGANSR_ERR_INVALID, "batch exceeds max_batch");
+  if (B > G->max_batch) {      // the generator runs micro-batched (net_forward_mb / net_backward_mb)
+    if (B % G->max_batch) return fail(ctx, DCGANSR_ERR_INVALID, "batch must be a multiple of netG's max_batch (its micro-batch size)");
+    if (ctx->cfg.sync_bn && ctx->cfg.world_size > 1) return fail(ctx, DCGANSR_ERR_UNSUPPORTED, "micro-batched generator with sync_bn");
+  }
   if (D->in_h % 2 || D->in_w % 2) return fail(ctx, DCGANSR_ERR_INVALID, "D input must have even spatial size");
   if (G->in_c != D->in_c || G->in_h * 2 != D->in_h || G->in_w * 2 != D->in_w)
     return fail(ctx, DCGANSR_ERR_INVALID, "G input must be the 2x2 down-sampled D input");
@@ -1434,6 +1553,8 @@ static int step_run(dcgansr_ctx* ctx, dcgansr_net* G, dcgansr_net* D, const dcga
   size_t lr_bytes = (size_t)B * G->in_c * G->in_h * G->in_w * sizeof(float);
   if (int rc = ensure(ctx, &ctx->lr_buf, &ctx->lr_cap, std::max<size_t>(lr_bytes, 16))) return rc;
   if (int rc = ensure(ctx, &ctx->label_vec, &ctx->label_cap, std::max<size_t>((size_t)B * sizeof(float), 16))) return rc;
+  if (B > G->max_batch)
+    if (int rc = ensure(ctx, &ctx->fake_buf, &ctx->fake_cap, (size_t)B * D->in_c * D->in_h * D->in_w * sizeof(float))) return rc;
   if (ctx->cfg.use_graph && !ctx->prof.on) {       // the per-launch event profiler needs eager launches
     GraphEntry* ge = nullptr;
     for (auto& g : ctx->graphs)

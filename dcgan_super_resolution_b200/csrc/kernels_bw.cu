@@ -881,6 +881,15 @@ void k_stage_unpack(St st, const float* stage, float* rmean, float* rvar, int nb
   stage_unpack_kernel<<<(std::max(nbn, 4) + 255) / 256, 256, 0, st.s>>>(stage, rmean, rvar, nbn, losses);
   DSR_LAUNCHED(st, "stage_unpack", 16.0 * nbn + 32, WORK_BYTES);
 }
+__global__ void dacc_kernel(double* __restrict__ dst, const double* __restrict__ src, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+// dst[i] += src[i] (whole-batch BatchNorm sums accumulated over micro-batches)
+void k_dacc(St st, double* dst, const double* src, int n) {
+  dacc_kernel<<<(n + 255) / 256, 256, 0, st.s>>>(dst, src, n);
+  DSR_LAUNCHED(st, "bn_dacc", 24.0 * n, WORK_BYTES);
+}
 void k_fill(St st, float* p, int64_t count, float v) {
   if (count <= 0) return;
   fill_kernel<<<sc_grid(count), 256, 0, st.s>>>(p, count, v);
