@@ -345,18 +345,22 @@ def run_workload(env, ctx, workload, B, steps, warmup, precision, legs=("staged"
     from dcgan_super_resolution_b200 import init, models
     cfg = models.config(workload)
     world, rank = env.world, env.rank
-    G = dsr.Sequential.from_specs(cfg["G"]).cuda(ctx, (cfg["nc"], cfg["hr"] // 2, cfg["hr"] // 2), B)
+    # a workload may ask for a micro-batched generator (C5): netG is created for the micro-batch, the step still sees B samples
+    gmb = cfg.get("g_microbatch", 0)
+    gB = gmb if gmb and B > gmb and B % gmb == 0 else B
+    G = dsr.Sequential.from_specs(cfg["G"]).cuda(ctx, (cfg["nc"], cfg["hr"] // 2, cfg["hr"] // 2), gB)
     # D holds 2B samples: the step then runs D(real) and D(fake) as one grouped pass (dcgansr.cu:step_body)
     D = dsr.Sequential.from_specs(cfg["D"]).cuda(ctx, (cfg["nc"], cfg["hr"], cfg["hr"]), 2 * B)
     G.set_params(init.weights_init(cfg["G"], 4321))
     D.set_params(init.weights_init(cfg["D"], 8765))
     scfg = dsr.make_step_cfg(**cfg["step"])
-    NPOOL = 8 if B * cfg["nc"] * cfg["hr"] ** 2 * 4 <= (64 << 20) else 4
+    NPOOL = 8 if B * cfg["nc"] * cfg["hr"] ** 2 * 4 <= (64 << 20) else (4 if gB == B else 2)
     pool = synth_batches(cfg, B, NPOOL, 1234 + rank)
     for i, b in enumerate(pool):
         dsr.stage_batch(ctx, D, b, i)
     ctx.synchronize()
-    res = {"workload": workload_name(workload, cfg, B), "global_batch": world * B, "precision": precision, "steps": steps, "warmup": warmup}
+    res = {"workload": workload_name(workload, cfg, B), "global_batch": world * B, "precision": precision, "steps": steps, "warmup": warmup,
+           "generator_microbatch": gB if gB != B else None}
     flops = models.step_flops(cfg, B)
     res["algorithmic_gflop_per_step_per_gpu"] = flops / 1e9
 
@@ -499,6 +503,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the workloads[] / strict / dp_check legs")
     ap.add_argument("--extra", default="", help="comma-separated workloads for workloads[] (default: the BASELINE configurations)")
     ap.add_argument("--cpu-sample-batch", type=int, default=0, help="batch of the CPU arms (bounded sample of the workload)")
+    ap.add_argument("--legs", default="staged,e2e,profile", help="legs of the headline workload (C5: staged,profile keeps the run short)")
     ap.add_argument("--profile-steps", type=int, default=2)
     ap.add_argument("--profile-out", default="", help="write the full per-kernel profile table (JSON) here")
     args = ap.parse_args()
@@ -517,8 +522,8 @@ def main():
     B = args.batch or cfg["batch"]
 
     ctx = env.new_ctx(args.precision, graph=bool(args.graph), sync_bn=bool(args.sync_bn))
-    head = run_workload(env, ctx, args.workload, B, args.steps, args.warmup, args.precision, sample_clocks=True,
-                        profile_steps=args.profile_steps, profile_out=args.profile_out)
+    head = run_workload(env, ctx, args.workload, B, args.steps, args.warmup, args.precision, legs=tuple(args.legs.split(",")),
+                        sample_clocks=True, profile_steps=args.profile_steps, profile_out=args.profile_out)
 
     extras, strict, dpc = [], None, None
     if not args.no_extra:
@@ -555,13 +560,13 @@ def main():
         "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
         "config": make_config(args.workload, cfg, B, world),
         "run": {"precision": args.precision, "cuda_graph": bool(args.graph), "graph_prime_steps": head.get("graph_prime_steps"),
-                "sync_bn": bool(args.sync_bn), "control_plane": "gloo (the only NCCL communicators are libdcgansr's)" if world > 1 else "single process",
+                "sync_bn": bool(args.sync_bn), "generator_microbatch": head.get("generator_microbatch"), "control_plane": "gloo (the only NCCL communicators are libdcgansr's)" if world > 1 else "single process",
                 "l2": f"no flush: per-step working set (conv outputs {head['conv_out_mb_per_rank']:.0f} MB fp32 per rank, rotating staged input "
                       "batches) exceeds the 126 MB L2",
                 "algorithmic_gflop_per_step_per_gpu": head["algorithmic_gflop_per_step_per_gpu"]},
         "step_tflops": head["step_tflops"],
         "clocks": head.get("clocks"),
-        "e2e": head["e2e"],
+        "e2e": head.get("e2e"),
         "gpu_launches": head["gpu_launches"],
         "roofline": head.get("roofline"),
         "kernels": head.get("kernels"),

@@ -180,8 +180,15 @@ bool k_tapconv_tc(St st, const TapGeom& g, const float* in, const float* bp, flo
                   std::string* err);
 // ---- kernels_halo.cu : weights-resident halo-tile kernel (all sub-pixel classes of a module in one launch) ----
 bool halo_tapconv_supported(const TapGeom* classes, int ncls);
+// stats != nullptr (and halo_stats_rows(...) > 0): the epilogue also writes per-CTA BatchNorm partial sums of the output,
+// rows [stats_row0, stats_row0 + halo_stats_rows) of a [rows][2*Co] double matrix (sum y | sum y^2)
+int halo_stats_rows(const TapGeom* classes, int ncls);
 bool k_tapconv_halo(St st, const TapGeom* classes, int ncls, const float* const* bp, const float* in, float* out, int act,
-                    float negval, std::string* err);
+                    float negval, std::string* err, double* stats = nullptr, int stats_row0 = 0);
+// BatchNorm forward from partial sums some other kernel produced (nb rows of [2C]): column sums + finalize, then apply
+void k_bn_fwd_from_partials(St st, const float* x, float* y, int64_t P, int C, int nb, const float* gamma, const float* beta, float* save_mean,
+                            float* save_invstd, float* running_mean, float* running_var, float eps, float momentum, int act, float negval,
+                            const double* partials);
 // ---- kernels_wgrad_halo.cu : stacked-shift halo-tile wgrad ----
 bool wgrad_halo_supported(const WgradGeom& g);
 size_t wgrad_halo_scratch_bytes(const WgradGeom& g);

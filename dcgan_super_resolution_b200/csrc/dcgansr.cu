@@ -397,7 +397,9 @@ struct ConvPlan {
           }
         }
   }
-  static void run_classes(dcgansr_ctx* ctx, std::vector<TapClass>& v, int hmode, const float* in, float* out, int N, int act, float neg) {
+  // stats / stats_rows: see k_tapconv_halo; *stats_rows stays 0 unless the single-launch halo path ran with fused statistics
+  static void run_classes(dcgansr_ctx* ctx, std::vector<TapClass>& v, int hmode, const float* in, float* out, int N, int act, float neg,
+                          double* stats = nullptr, int* stats_rows = nullptr) {
     // 1..4-channel side: streaming fp32 kernels (both precisions)
     if (!v.empty() && v.size() <= 4 && !getenv("DCGANSR_NO_THIN")) {
       TapGeom gs[4];
@@ -426,7 +428,11 @@ struct ConvPlan {
       const int hm = (all_tc && !v[0].bt) ? (hmode >= 0 ? hmode : halo_mode(gs, (int)v.size())) : 0;    // (groups with pre-tiled images belong to the per-tap kernel)
       if (hm == 2) {
         std::string e;
-        if (k_tapconv_halo(ctx->st(), gs, (int)v.size(), bps, in, out, act, neg, &e)) return;
+        const int rows = (stats && stats_rows) ? halo_stats_rows(gs, (int)v.size()) : 0;
+        if (k_tapconv_halo(ctx->st(), gs, (int)v.size(), bps, in, out, act, neg, &e, rows > 0 ? stats : nullptr, 0)) {
+          if (rows > 0) *stats_rows = rows;
+          return;
+        }
         ctx->err = "tcgen05 halo path: " + e;
         ctx->tc_failed = true;
         return;
@@ -467,7 +473,9 @@ struct ConvPlan {
       k_tapconv_simt(ctx->st(), g, in, c.wp, out, act, neg);
     }
   }
-  void forward(dcgansr_ctx* ctx, const float* in, float* out, int N, int act, float neg) { run_classes(ctx, fwd, hmode_fwd, in, out, N, act, neg); }
+  void forward(dcgansr_ctx* ctx, const float* in, float* out, int N, int act, float neg, double* stats = nullptr, int* stats_rows = nullptr) {
+    run_classes(ctx, fwd, hmode_fwd, in, out, N, act, neg, stats, stats_rows);
+  }
   void dgrad_run(dcgansr_ctx* ctx, const float* dy, float* dx, int N) { run_classes(ctx, dgrad, hmode_dgrad, dy, dx, N, ACT_NONE, 0.f); }
   bool fast = false;       // FAST_TF32: tensor-core wgrad when the geometry allows
   size_t wscratch_bytes(int N) const {
@@ -522,6 +530,7 @@ struct Mod {
   bool fused_into_prev = false;  // ACT module executed by its producer
   int act = ACT_NONE;            // ACT modules: own kind
   float *save_mean = nullptr, *save_invstd = nullptr;
+  int stats_rows = 0;            // BN modules: rows of net->bn_partials the producing convolution's epilogue has filled (0: none)
 };
 
 struct dcgansr_net {
@@ -632,16 +641,33 @@ static int net_forward_dev(dcgansr_net* net, const float* in, int B, int groups 
         cur = m.out;
         break;
       case DCGANSR_CONV:
-      case DCGANSR_FULLCONV:
-        m.conv->forward(ctx, cur, m.out, NB, m.fused_act, m.fused_neg);
+      case DCGANSR_FULLCONV: {
+        // a BatchNorm right behind a halo-kernel convolution gets its batch sums from that kernel's epilogue (one read of the
+        // tensor less); single sample group, local statistics, statistics actually wanted (not a frozen micro-batch pass)
+        Mod* nb = mi + 1 < net->mods.size() && net->mods[mi + 1].kind == DCGANSR_BN ? &net->mods[mi + 1] : nullptr;
+        int rows = 0;
+        if (nb && groups == 1 && !sync && !bn_frozen && (int)mi + 1 != stop && m.fused_act == ACT_NONE)
+          m.conv->forward(ctx, cur, m.out, NB, m.fused_act, m.fused_neg, net->bn_partials, &rows);
+        else
+          m.conv->forward(ctx, cur, m.out, NB, m.fused_act, m.fused_neg);
+        if (nb) nb->stats_rows = rows;
         cur = m.out;
         break;
+      }
       case DCGANSR_BN: {
         int64_t P = (int64_t)B * m.hin * m.win;
         int C = m.cin;
         if (bn_frozen) {
           k_bn_apply_act(st, cur, m.out, P * groups, C, net->params + m.p_off, net->params + m.p_off + C, m.save_mean, m.save_invstd,
                          m.fused_act, m.fused_neg);
+          cur = m.out;
+          break;
+        }
+        if (!sync && m.stats_rows > 0 && groups == 1) {
+          k_bn_fwd_from_partials(st, cur, m.out, P, C, m.stats_rows, net->params + m.p_off, net->params + m.p_off + C, m.save_mean, m.save_invstd,
+                                 net->bn_rmean + m.bn_off, net->bn_rvar + m.bn_off, m.L.eps, m.L.momentum, m.fused_act, m.fused_neg,
+                                 net->bn_partials);
+          m.stats_rows = 0;
           cur = m.out;
           break;
         }
@@ -1252,7 +1278,8 @@ int dcgansr_net_create(dcgansr_ctx* ctx, const dcgansr_layer* layers, int n_laye
   {
     int64_t rows = 0;
     for (auto& m : net->mods)
-      if (m.kind == DCGANSR_BN) rows = std::max<int64_t>(rows, (int64_t)bn_partial_rows(B * m.hin * m.win, m.cin) * 2 * m.cin);
+      if (m.kind == DCGANSR_BN)      // rows of the BN kernels' own partials, or one row per persistent CTA of a producing halo-kernel convolution
+        rows = std::max<int64_t>(rows, (int64_t)std::max(bn_partial_rows(B * m.hin * m.win, m.cin), 160) * 2 * m.cin);
     float* tmpf = nullptr;
     A(&tmpf, std::max<int64_t>(rows, 2) * 2 * 2); net->bn_partials = (double*)tmpf; tmpf = nullptr;     // x 2 sample groups
     A(&tmpf, (int64_t)maxC * 4 * 2 + 4); net->bn_sums = (double*)tmpf; tmpf = nullptr;

@@ -619,6 +619,15 @@ void k_bn_fwd_grouped(St st, const float* x, float* y, int64_t P, int C, int gro
   DSR_LAUNCHED(st, "bn_apply_act", 8.0 * P * C * groups, WORK_BYTES);
 }
 
+void k_bn_fwd_from_partials(St st, const float* x, float* y, int64_t P, int C, int nb, const float* gamma, const float* beta, float* save_mean,
+                            float* save_invstd, float* running_mean, float* running_var, float eps, float momentum, int act, float negval,
+                            const double* partials) {
+  bn_fwd_tail_kernel<<<(C + 31) / 32, dim3(32, BN_TAIL_Y), 0, st.s>>>(partials, nb, C, 1, (double)P, eps, momentum, save_mean, save_invstd, 0,
+                                                               running_mean, running_var);
+  DSR_LAUNCHED(st, "bn_fwd_tail", 16.0 * nb * C, WORK_BYTES);
+  k_bn_apply_act(st, x, y, P, C, gamma, beta, save_mean, save_invstd, act, negval);
+}
+
 // sums[g][2C] = column sums of group g's partial rows; dbeta += sum_g sums[g][c], dgamma += sum_g sums[g][C + c]
 __global__ void bn_bwd_tail_kernel(const double* __restrict__ partials, int nb, int C, int groups, double* __restrict__ sums,
                                    float* __restrict__ dgamma, float* __restrict__ dbeta, float* __restrict__ fmeans, double n_total) {

@@ -77,6 +77,8 @@ struct HaloParams {
                                          // classes of a row parity are staged side by side (rows of 2*Co floats: wider global segments)
   short st_cblk[HALO_MAXCLS], st_coff[HALO_MAXCLS];      // class -> staging block, float offset inside the staged row
   short st_bc0[HALO_MAXCLS], st_bpy[HALO_MAXCLS];        // box -> channel coordinate, row-parity coordinate
+  double* stats;                         // != nullptr: BatchNorm statistics of the OUTPUT fused into the epilogue: row (stats_row0 + blockIdx.x) of
+  int stats_row0;                        // [rows][2*Co] doubles receives this CTA's (sum y, sum y^2) per output channel (its cout slice)
   int dbg;                               // DCGANSR_HALO_DBG (timing experiments only): 1 skip MMAs, 2 skip stores, 4 skip the halo TMA loads
 };
 
@@ -100,13 +102,19 @@ __device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr, uint32_t sbo, ui
 template <int ACT>
 __device__ __forceinline__ void halo_epilogue(const HaloParams& p, float* __restrict__ out, uint32_t tmem_base, uint64_t* acc_full,
                                               uint64_t* acc_empty, int warp, int half, int lane, int n0, const CUtensorMap* mapO,
-                                              uint32_t sO) {
+                                              uint32_t sO, float* sred) {
   const int q = warp & 3;                       // TMEM lane quarter this warp may access
   const int r = q * 32 + lane;                  // tile row = pixel
   const int w = r % HALO_TW, h = r / HALO_TW;
   const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
   const int chunks = p.Npad >> 4;
   const int nitems = p.ncls * chunks;
+  // fused BatchNorm statistics (chunks <= 2: every item of this warp half is the same 16-column chunk): per-thread fp32 sums over
+  // this thread's pixel row of all its tiles, reduced once at the end
+  const bool dostats = p.stats != nullptr;
+  float s1[16], s2[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   int it = 0;
   for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
     const int buf = it % p.nacc;
@@ -155,6 +163,10 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams& p, float* __rest
           v[j] = __float_as_uint(sum);
         }
       }
+      if (dostats && gy < p.Hg && gx < p.Wg) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { const float y = __uint_as_float(v[j]); s1[j] += y; s2[j] = fmaf(y, y, s2[j]); }
+      }
       if (p.tstore) {
         // row r of class c: st_row floats (this CTA's cout slice), dense, inside the (1 KB aligned) class block.  A swizzled
         // store map (rows of exactly 128 / 64 / 32 bytes) expects byte offset o at o ^ (((o >> 7) & st_xor) << 4): the 16-byte
@@ -191,6 +203,33 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams& p, float* __rest
     }
   }
   if (p.tstore && warp == p.ngrp + 1 && lane == 0) tma_store_wait_all();
+  if (dostats) {
+    // rows (lanes) of a warp, then the four lane-quarter warps of this half: one (sum, sum^2) per channel of the half's chunk
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o); s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o); }
+    }
+    const int ew = half * 4 + q;                 // 0..7
+    if (lane == 0) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) { sred[ew * 32 + j] = s1[j]; sred[ew * 32 + 16 + j] = s2[j]; }
+    }
+    named_bar_sync(4, 256);
+    const int t = (half * 4 + q) * 32 + lane;    // 256 epilogue threads
+    if (t < 64) {
+      // t = h2*32 + k: half h2, k < 16 -> sum of channel k of that half's chunk, k >= 16 -> sum of squares
+      const int h2 = t >> 5, k = t & 31;
+      const int chunk = chunks == 1 ? 0 : h2;
+      if (!(chunks == 1 && h2 == 1) ) {
+        float a = 0.f;
+        if (chunks == 1) { for (int w8 = 0; w8 < 8; ++w8) a += sred[w8 * 32 + k]; }       // both halves worked on chunk 0
+        else { for (int w4 = 0; w4 < 4; ++w4) a += sred[(h2 * 4 + w4) * 32 + k]; }
+        const int ch = n0 + chunk * 16 + (k & 15);
+        if (ch < p.Co) p.stats[((size_t)(p.stats_row0 + blockIdx.x) * 2 + (k >> 4)) * p.Co + ch] = (double)a;
+      }
+    }
+  }
 }
 
 __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel(const __grid_constant__ CUtensorMap mapA,
@@ -210,6 +249,7 @@ __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel
   uint64_t* a_full = bars + 9;                                           // [HALO_MAXRING]
   uint64_t* a_empty = a_full + HALO_MAXRING;                             // [HALO_MAXRING]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + HALO_MAXRING);
+  float* sred = reinterpret_cast<float*>(tmem_slot + 4);                 // 8 warps x 32 floats (fused BatchNorm statistics)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * p.Npad;
 
@@ -333,11 +373,11 @@ __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel
     const int half = (warp - p.ngrp - 1) >> 2;
     // ===================== epilogue: TMEM -> registers -> activation -> NHWC global =====================
     switch (p.act) {
-      case ACT_RELU: halo_epilogue<ACT_RELU>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut)); break;
-      case ACT_LRELU: halo_epilogue<ACT_LRELU>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut)); break;
-      case ACT_TANH: halo_epilogue<ACT_TANH>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut)); break;
-      case ACT_SIGMOID: halo_epilogue<ACT_SIGMOID>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut)); break;
-      default: halo_epilogue<ACT_NONE>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut)); break;
+      case ACT_RELU: halo_epilogue<ACT_RELU>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut), sred); break;
+      case ACT_LRELU: halo_epilogue<ACT_LRELU>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut), sred); break;
+      case ACT_TANH: halo_epilogue<ACT_TANH>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut), sred); break;
+      case ACT_SIGMOID: halo_epilogue<ACT_SIGMOID>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut), sred); break;
+      default: halo_epilogue<ACT_NONE>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut), sred); break;
     }
   }
   tc_fence_before();
@@ -477,7 +517,7 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
     else { ring[0] = ci[0][0]; ring[1] = ci[0][1]; ring[2] = ci[1][1]; ring[3] = ci[1][0]; ring[4] = ci[0][0]; }
   }
   const int co16 = (p.Co + 15) / 16 * 16;
-  const size_t fixed = 1024 + (16 + 2 * HALO_MAXRING) * sizeof(uint64_t);
+  const size_t fixed = 1024 + (16 + 2 * HALO_MAXRING) * sizeof(uint64_t) + 1024;      // alignment slack, barriers, statistics scratch
   auto set_npad = [&](int npad) {
     p.Npad = npad;
     p.wtile_bytes = npad * p.KBw * 4;            // a multiple of 1024 (npad % 16 == 0, KBw >= 16)
@@ -723,12 +763,20 @@ bool halo_tapconv_supported(const TapGeom* classes, int ncls) {
   return c.nsplit <= 2 && (c.p.nring >= full_ring || (int64_t)c.p.Hg * c.p.Wg >= 4096);
 }
 
+// rows of the partial-statistics matrix a launch on this geometry would write (0: the fused statistics are not available)
+int halo_stats_rows(const TapGeom* classes, int ncls) {
+  HaloCfg c;
+  if (getenv("DCGANSR_NO_FUSED_STATS") || !halo_cfg(classes, ncls, c)) return 0;
+  return c.p.Npad <= 32 ? c.grid_x : 0;
+}
+
 bool k_tapconv_halo(St st, const TapGeom* classes, int ncls, const float* const* bp, const float* in, float* out, int act,
-                    float negval, std::string* err) {
+                    float negval, std::string* err, double* stats, int stats_row0) {
   HaloCfg c;
   if (!halo_cfg(classes, ncls, c)) { if (err) *err = "geometry not supported by the halo kernel"; return false; }
   HaloParams& p = c.p;
   p.act = act; p.neg = negval;
+  p.stats = (stats && p.Npad <= 32) ? stats : nullptr; p.stats_row0 = stats_row0;
   if (const char* d = getenv("DCGANSR_HALO_DBG")) p.dbg = atoi(d);
   const TapGeom& g = classes[0];
   EncodeTiledFn enc = tc_encode_fn();

@@ -110,7 +110,9 @@ def config(name: str):
     if name == "C4a":   # same with the reference's own 8x8 patches
         return dict(G=train_gray_3_G(16), D=patch_D(64), nc=1, hr=8, batch=512, step=_bce_step(), data_range=(0.0, 1.0))
     if name == "C5":    # scaled synthetic RGB 128 -> 256, ngf = ndf = 128
-        return dict(G=train_lua_G(3, 128), D=dcgan64_D(3, 128), nc=3, hr=256, batch=128,
+        # 128 samples of this generator's activations (244 GiB fp32) do not fit one B200: netG is created for 16-sample
+        # micro-batches and the library runs the batch with exact whole-batch BatchNorm (dcgansr.cu:net_forward_mb)
+        return dict(G=train_lua_G(3, 128), D=dcgan64_D(3, 128), nc=3, hr=256, batch=128, g_microbatch=16,
                     step=dict(family="mse", real_label=0.0, fake_label=0.0, gen_label=0.0, pixel_label=True,
                               pixel_div=4.0 * 3 * 256 * 256), data_range=(-1.0, 1.0))
     raise KeyError(name)

@@ -199,3 +199,41 @@ def test_fast_trajectory_200_steps(ctx_fast):
     mean_rel = np.abs(ours.mean(axis=0) - ref.mean(axis=0)) / np.abs(ref.mean(axis=0))
     assert mean_rel.max() <= 0.01, mean_rel
     assert rel.max() <= 0.25, (rel.max(), rel.argmax())
+
+
+@pytest.mark.parametrize("specs,ishape", [
+    ([dict(kind="fullconv", cin=48, cout=24, k=4, s=2, p=1), dict(kind="bn", c=24), dict(kind="relu")], (48, 24, 40)),       # 2 chunks, 4 classes
+    ([dict(kind="conv", cin=24, cout=12, k=4, s=2, p=1), dict(kind="bn", c=12), dict(kind="lrelu", negval=0.2)], (24, 48, 40)),  # 1 chunk, ragged tiles
+    ([dict(kind="fullconv", cin=64, cout=32, k=4, s=2, p=1), dict(kind="bn", c=32), dict(kind="relu")], (64, 32, 24)),
+])
+def test_bn_statistics_fused_into_conv_epilogue(ctx_fast, specs, ishape, monkeypatch):
+    """A BatchNorm behind a halo-kernel convolution takes its batch sums from that kernel's epilogue (dcgansr.cu:net_forward_dev):
+    output, saved statistics (through the backward pass) and running statistics must match the oracle, and the unfused path."""
+    B = 5
+    x = rng(77).standard_normal((B,) + ishape).astype(np.float32)
+    onet = oracle_net(specs, seed=4321)
+    ry = onet.forward(t64(x)).numpy()
+    outs = []
+    for fused in (True, False):
+        if fused:
+            monkeypatch.delenv("DCGANSR_NO_FUSED_STATS", raising=False)
+        else:
+            monkeypatch.setenv("DCGANSR_NO_FUSED_STATS", "1")
+        net = dsr.Sequential.from_specs(specs).cuda(ctx_fast, ishape, B)
+        net.set_params(onet.get_flat_params().numpy().astype(np.float32))
+        l0 = ctx_fast.launch_count()
+        y = net.forward(x)
+        launches = ctx_fast.launch_count() - l0
+        rm, rv = net.get_bn_running()
+        dy = rng(78).standard_normal(y.shape).astype(np.float32)
+        net.zeroGradParameters()
+        dx = net.backward(x, dy)
+        outs.append((y, rm, rv, dx, launches))
+        net.close()
+    orm = torch.cat([m.running_mean for m in onet.bn_modules()]).numpy()
+    orv = torch.cat([m.running_var for m in onet.bn_modules()]).numpy()
+    (y, rm, rv, dx, n_f), (y2, rm2, rv2, dx2, n_u) = outs
+    assert n_f == n_u - 1                                        # the bn_stats launch is gone
+    assert rel_err(y, ry) <= FAST_TOL and rel_err(rm, orm) <= FAST_TOL and rel_err(rv, orv) <= FAST_TOL
+    # fused vs unfused: the same conv values, sums in another order / precision
+    assert rel_err(y, y2) <= 1e-5 and rel_err(rm, rm2) <= 1e-5 and rel_err(rv, rv2) <= 1e-5 and rel_err(dx, dx2) <= 1e-4
