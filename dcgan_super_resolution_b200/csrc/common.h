@@ -198,6 +198,11 @@ bool k_wgrad_halo(St st, const WgradGeom& g, const float* P, const float* Q, flo
 bool tc_tapconv_multi_ok(const TapGeom* classes, int ncls);
 bool k_tapconv_tc_multi(St st, const TapGeom* classes, int ncls, const float* const* bp, const float* in, float* out, int act,
                         float negval, std::string* err, const float* const* bt = nullptr);
+// ---- kernels_tc2.cu : persistent wide-tile per-tap kernel (256 x 128 / 128 x 256 work items, double-buffered TMEM) ----
+// takes a class group when it has pre-tiled weight images, fills the machine and wastes little in its last wave
+bool tc2_tapconv_supported(const TapGeom* classes, int ncls, const float* const* bt);
+bool k_tapconv_tc2(St st, const TapGeom* classes, int ncls, const float* const* bt, const float* in, float* out, int act, float negval,
+                   std::string* err);
 bool tc_wgrad_supported(const WgradGeom& g);
 size_t wgrad_tc_scratch_bytes(const WgradGeom& g);
 bool k_wgrad_tc(St st, const WgradGeom& g, const float* P, const float* Q, float* grad_master, float* scratch, size_t scratch_bytes,

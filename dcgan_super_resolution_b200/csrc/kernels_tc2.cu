@@ -1,0 +1,337 @@
+// kernels_tc2.cu -- persistent, wide-tile per-tap tcgen05 implicit GEMM for the tensor-bound convolutions (FAST_TF32):
+// nn.SpatialConvolution / nn.SpatialFullConvolution forward and updateGradInput of the discriminator's inner layers
+// (train.lua:124-131) and of the generator's inner layers at ngf >= 64 (train-gray-patch.lua:60-70), whose weights do not
+// fit in shared memory (so the weights-resident halo kernel cannot take them).
+//
+// What bounds kernels_tc.cu's one-tile-per-CTA kernel on these layers is the L2 -> SM path: a 128 pixel x 128 cout x 32
+// channel step moves 32 KB of fp32 operands into shared memory for 4 tcgen05.mma (271 tensor cycles) = 118 B/clk/SM, against
+// ~43 B/clk/SM the L2 delivers chip-wide (B300_MICROARCH: LTS cap ~6300 B/clk), which only the L2's merging of concurrent
+// identical requests lifts to the measured 45-56 % of the TF32 peak.  Thread-block-cluster multicast of the weight tile does not
+// help (measured; the L2 already merges what a cluster of <= 4 would share).  Fewer bytes per flop does:
+//
+//   * a work item is 256 x 128 or 128 x 256 (pixels x couts): two pixel tiles share one weight tile, or one pixel tile
+//     meets a 256-cout weight tile -- 48 KB per 542 tensor cycles = 88 B/clk/SM, 25 % less operand traffic per flop;
+//   * one persistent CTA per SM owns all 512 TMEM columns as two accumulator buffers: the epilogue of item i (tcgen05.ld ->
+//     activation -> 256-bit NHWC stores) overlaps the TMA + MMA of item i + 1 (the one-tile kernel needed a second resident
+//     CTA for that, which halved its ring);
+//   * the whole shared memory is one 4-stage ring of {A tile(s), weight tile} stages (192 KB in flight per SM).
+//
+// Operands as in kernels_tc.cu: A = one TMA box of the NHWC activation per (pixel tile, tap, 32-channel chunk) at a shifted
+// coordinate (zero fill = padding; stride-2 gathers through the 5-D parity view), B = the pre-tiled, pre-swizzled weight
+// images (1-D bulk copies), both K-major SWIZZLE_128B, kind::tf32, fp32 accumulation in TMEM.
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2..5 epilogue.
+#include "tc_ptx.cuh"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#define NSM 148
+#define TC2_MAXCLS 4
+#define TC2_THREADS 192
+
+struct Tc2Params {
+  int N, Hg, Wg, Ho, Wo, Co;
+  int so, si, Ci;
+  int TW, TH, TB, tiles_x, tiles_y, ntiles_m;
+  int kchunks, ksteps_last;
+  int MT, BN, ngroups_m, ntiles_n, nwork, nstage;
+  int n_fast;                      // work order: 0 = pixel groups fastest (neighbouring CTAs stream the same weight tiles), 1 = cout tiles fastest
+  int bt_rows, bt_per_n;           // weight images of bt_rows couts; bt_per_n images make one BN-cout stage
+  int a_tile_bytes, stage_bytes, acc_cols, tmem_cols;
+  int ncls, oy0[TC2_MAXCLS], ox0[TC2_MAXCLS], ntaps[TC2_MAXCLS];
+  const float* bt[TC2_MAXCLS];
+  int act;
+  float neg;
+  short oy[TC2_MAXCLS][DSR_MAX_TAPS], ox[TC2_MAXCLS][DSR_MAX_TAPS], py[TC2_MAXCLS][DSR_MAX_TAPS], px[TC2_MAXCLS][DSR_MAX_TAPS];
+};
+
+__device__ __forceinline__ void tc2_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+
+struct Tc2Item { int cls, ntile, mg; };
+__device__ __forceinline__ Tc2Item tc2_item(const Tc2Params& p, int w) {
+  Tc2Item it;
+  if (p.n_fast) { it.ntile = w % p.ntiles_n; w /= p.ntiles_n; it.mg = w % p.ngroups_m; it.cls = w / p.ngroups_m; }
+  else { it.mg = w % p.ngroups_m; w /= p.ngroups_m; it.ntile = w % p.ntiles_n; it.cls = w / p.ntiles_n; }
+  return it;
+}
+
+template <int ACT>
+__device__ __forceinline__ void tc2_epilogue(const Tc2Params& p, float* __restrict__ out, uint32_t tmem_base, uint64_t* acc_full,
+                                             uint64_t* acc_empty, int warp, int lane) {
+  const int q = warp & 3;                       // TMEM lane quarter this warp may access
+  const int r = q * 32 + lane;                  // tile row = pixel
+  const int w = r % p.TW;
+  const int h = (r / p.TW) % p.TH;
+  const int b = r / (p.TW * p.TH);
+  const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+  int it = 0;
+  for (int wi = blockIdx.x; wi < p.nwork; wi += gridDim.x, ++it) {
+    const Tc2Item item = tc2_item(p, wi);
+    const int buf = it & 1;
+    const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+    const int n0 = item.ntile * p.BN;
+    mbar_wait(smem_u32(&acc_full[buf]), aph);
+    tc_fence_after();
+    for (int m = 0; m < p.MT; ++m) {
+      int tile = item.mg * p.MT + m;
+      if (tile >= p.ntiles_m) break;
+      const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+      const int ty = tile % p.tiles_y; tile /= p.tiles_y;
+      const int n = tile * p.TB + b, gy = ty * p.TH + h, gx = tx * p.TW + w;
+      const bool valid = n < p.N && gy < p.Hg && gx < p.Wg;
+      float* orow = out + ((int64_t)(n * p.Ho + gy * p.so + p.oy0[item.cls]) * p.Wo + gx * p.so + p.ox0[item.cls]) * p.Co + n0;
+      const uint32_t cbase = lane_base + (uint32_t)(buf * p.acc_cols + m * p.BN);
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(cbase + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (valid) store_row<ACT, 32>(orow + c0, v, n0 + c0, p.Co, p.neg);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) tc2_arrive(smem_u32(&acc_empty[buf]));
+  }
+}
+
+__global__ void __launch_bounds__(TC2_THREADS, 1) tapconv_tc2_kernel(const __grid_constant__ CUtensorMap mapA, const Tc2Params p,
+                                                                     float* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.nstage * p.stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + p.nstage;
+  uint64_t* acc_full = bars + 2 * p.nstage;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    for (int s = 0; s < p.nstage; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&acc_full[s]), 1); mbar_init(smem_u32(&acc_empty[s]), 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t b_off = (uint32_t)(p.MT * p.a_tile_bytes);          // weight tile inside a stage
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t img_bytes = (uint32_t)p.bt_rows * 128u;
+      const uint32_t bytes = (uint32_t)(p.MT * 128 * 128) + (uint32_t)p.bt_per_n * img_bytes;
+      for (int wi = blockIdx.x; wi < p.nwork; wi += gridDim.x) {
+        const Tc2Item item = tc2_item(p, wi);
+        const int cls = item.cls;
+        const int nk = p.ntaps[cls] * p.kchunks;
+        int b0[2], gy0[2], gx0[2];
+        for (int m = 0; m < p.MT; ++m) {
+          int tile = item.mg * p.MT + m;                            // tiles past the end: batch coordinate out of range -> zero fill
+          const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+          const int ty = tile % p.tiles_y; tile /= p.tiles_y;
+          b0[m] = tile * p.TB; gy0[m] = ty * p.TH; gx0[m] = tx * p.TW;
+        }
+        const float* wsrc = p.bt[cls] + (size_t)item.ntile * p.bt_per_n * nk * (p.bt_rows * 32);
+        int t = 0, c = 0;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(smem_u32(&empty[s]), ph ^ 1u);
+          const uint32_t fb = smem_u32(&full[s]);
+          mbar_expect_tx(fb, bytes);
+          const uint32_t st = smem_u32(smem + (size_t)s * p.stage_bytes);
+          for (int m = 0; m < p.MT; ++m) {
+            if (p.si == 1)
+              tma_load_4d(st + m * p.a_tile_bytes, &mapA, fb, c * 32, gx0[m] + p.ox[cls][t], gy0[m] + p.oy[cls][t], b0[m]);
+            else
+              tma_load_5d(st + m * p.a_tile_bytes, &mapA, fb, p.px[cls][t] * p.Ci + c * 32, gx0[m] + p.ox[cls][t], p.py[cls][t],
+                          gy0[m] + p.oy[cls][t], b0[m]);
+          }
+          for (int j = 0; j < p.bt_per_n; ++j)
+            bulk_load(st + b_off + j * img_bytes, wsrc + ((size_t)j * nk + kb) * (p.bt_rows * 32), img_bytes, fb);
+          if (++c == p.kchunks) { c = 0; ++t; }
+          if (++s == p.nstage) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    // instruction descriptor: D = f32, A = B = tf32, both K-major, N = BN, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((128u >> 4) << 24);
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    for (int wi = blockIdx.x; wi < p.nwork; wi += gridDim.x, ++it) {
+      const Tc2Item item = tc2_item(p, wi);
+      const int nk = p.ntaps[item.cls] * p.kchunks;
+      const int buf = it & 1;
+      const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(smem_u32(&acc_empty[buf]), aph ^ 1u);
+      tc_fence_after();
+      const uint32_t dbase = tmem_base + (uint32_t)(buf * p.acc_cols);
+      int kc = 0;
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait(smem_u32(&full[s]), ph);
+        tc_fence_after();
+        const int ksteps = kc == p.kchunks - 1 ? p.ksteps_last : 4;          // the last K chunk of a tap may be partial
+        if (++kc == p.kchunks) kc = 0;
+        if (elect_one()) {
+          const uint32_t st = smem_u32(smem + (size_t)s * p.stage_bytes);
+          const uint64_t bd = make_kmajor_desc(st + b_off, 32);
+          for (int m = 0; m < p.MT; ++m) {
+            const uint64_t ad = make_kmajor_desc(st + m * p.a_tile_bytes, 32);
+            for (int k = 0; k < ksteps; ++k)
+              umma_tf32(dbase + (uint32_t)(m * p.BN), ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(smem_u32(&empty[s]));
+          if (kb == nk - 1) umma_commit(smem_u32(&acc_full[buf]));
+        }
+        __syncwarp();
+        if (++s == p.nstage) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue: TMEM -> registers -> activation -> NHWC global =====================
+    switch (p.act) {
+      case ACT_RELU: tc2_epilogue<ACT_RELU>(p, out, tmem_base, acc_full, acc_empty, warp, lane); break;
+      case ACT_LRELU: tc2_epilogue<ACT_LRELU>(p, out, tmem_base, acc_full, acc_empty, warp, lane); break;
+      case ACT_TANH: tc2_epilogue<ACT_TANH>(p, out, tmem_base, acc_full, acc_empty, warp, lane); break;
+      case ACT_SIGMOID: tc2_epilogue<ACT_SIGMOID>(p, out, tmem_base, acc_full, acc_empty, warp, lane); break;
+      default: tc2_epilogue<ACT_NONE>(p, out, tmem_base, acc_full, acc_empty, warp, lane); break;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+static inline int pow2_ge2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+static inline int floordiv2_2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
+
+struct Tc2Cfg { Tc2Params p; size_t smem; int grid; double flops; };
+
+static bool tc2_cfg(const TapGeom* cls, int ncls, const float* const* bt, Tc2Cfg& c) {
+  if (!tc_encode_fn() || !tc_tapconv_multi_ok(cls, ncls) || !bt) return false;
+  const char* me = getenv("DCGANSR_TC2");
+  const int mode = me ? atoi(me) : 1;     // 0: off, 1: where it pays, 2: wherever it runs
+  if (mode == 0) return false;
+  const TapGeom& g = cls[0];
+  if (g.Ci % 32 != 0 && !(g.Ci % 8 == 0 && g.Ci >= 24)) return false;                    // 32-float K blocks (a partial last block per tap)
+  for (int i = 0; i < ncls; ++i)
+    if (!bt[i] || cls[i].ntaps < 1 || cls[i].ntaps > DSR_MAX_TAPS) return false;
+  if (g.Ci % 32 != 0) return false;                                                       // the weight images exist for whole blocks only
+  Tc2Params& p = c.p;
+  memset(&p, 0, sizeof(p));
+  p.N = g.N; p.Hg = g.Hg; p.Wg = g.Wg; p.Ho = g.Ho; p.Wo = g.Wo; p.Co = g.Co;
+  p.so = g.so; p.si = g.si; p.Ci = g.Ci; p.ncls = ncls;
+  p.kchunks = (g.Ci + 31) / 32;
+  p.ksteps_last = (g.Ci - (p.kchunks - 1) * 32) >> 3;
+  p.TW = std::min(pow2_ge2(g.Wg), 128);
+  p.TH = std::min(pow2_ge2(g.Hg), 128 / p.TW);
+  p.TB = 128 / (p.TW * p.TH);
+  p.tiles_x = (g.Wg + p.TW - 1) / p.TW;
+  p.tiles_y = (g.Hg + p.TH - 1) / p.TH;
+  p.ntiles_m = ((g.N + p.TB - 1) / p.TB) * p.tiles_y * p.tiles_x;
+  p.bt_rows = tc_bt_rows(g.Co);
+  if (p.bt_rows < 64 || p.bt_rows > 128 || p.bt_rows % 16) return false;
+  const int n_img = (g.Co + p.bt_rows - 1) / p.bt_rows;
+  if (n_img >= 2 && n_img % 2 == 0 && p.bt_rows == 128) { p.BN = 256; p.bt_per_n = 2; p.MT = 1; }
+  else { p.BN = p.bt_rows; p.bt_per_n = 1; p.MT = 2; }
+  if (const char* e = getenv("DCGANSR_TC2_SHAPE")) {                   // experiments: "1x128" one pixel tile x one image (the old tile)
+    if (!strcmp(e, "1x128")) { p.BN = p.bt_rows; p.bt_per_n = 1; p.MT = 1; }
+    if (!strcmp(e, "2x128")) { p.BN = p.bt_rows; p.bt_per_n = 1; p.MT = 2; }
+  }
+  p.ntiles_n = n_img / p.bt_per_n;
+  p.ngroups_m = (p.ntiles_m + p.MT - 1) / p.MT;
+  p.nwork = ncls * p.ntiles_n * p.ngroups_m;
+  p.n_fast = getenv("DCGANSR_TC2_NFAST") ? 1 : 0;
+  p.a_tile_bytes = 128 * 128;
+  p.stage_bytes = p.MT * p.a_tile_bytes + p.BN * 128;
+  p.nstage = std::max(2, std::min(8, (200 * 1024) / p.stage_bytes));
+  p.acc_cols = p.MT * p.BN;
+  p.tmem_cols = std::max(32, pow2_ge2(2 * p.acc_cols));
+  if (p.tmem_cols > 512) return false;
+  // one CTA per SM walks ceil(nwork / 148) items: take the layer only when that wave count wastes little and the grid fills the
+  // machine (small grids stay on the one-tile kernel with its split-K)
+  c.grid = std::min(p.nwork, NSM);
+  if (mode == 1) {
+    int nk_same = cls[0].ntaps;
+    for (int i = 1; i < ncls; ++i) if (cls[i].ntaps != nk_same) nk_same = -1;
+    const int waves = (p.nwork + NSM - 1) / NSM;
+    if (p.nwork < NSM || (double)p.nwork / ((double)waves * NSM) < 0.8 || nk_same < 0) return false;
+  }
+  c.flops = 0;
+  for (int i = 0; i < ncls; ++i) {
+    p.bt[i] = bt[i];
+    p.oy0[i] = cls[i].oy0; p.ox0[i] = cls[i].ox0; p.ntaps[i] = cls[i].ntaps;
+    for (int t = 0; t < cls[i].ntaps; ++t) {
+      if (g.si == 1) { p.oy[i][t] = (short)cls[i].dy[t]; p.ox[i][t] = (short)cls[i].dx[t]; }
+      else {
+        const int fy = floordiv2_2(cls[i].dy[t]), fx = floordiv2_2(cls[i].dx[t]);
+        p.oy[i][t] = (short)fy; p.ox[i][t] = (short)fx; p.py[i][t] = (short)(cls[i].dy[t] - 2 * fy); p.px[i][t] = (short)(cls[i].dx[t] - 2 * fx);
+      }
+    }
+    c.flops += 2.0 * g.N * g.Hg * g.Wg * cls[i].ntaps * g.Ci * g.Co;
+  }
+  c.smem = 1024 + (size_t)p.nstage * p.stage_bytes + (2 * p.nstage + 4) * sizeof(uint64_t) + 16;
+  return c.smem <= 227 * 1024;
+}
+
+bool tc2_tapconv_supported(const TapGeom* cls, int ncls, const float* const* bt) {
+  Tc2Cfg c;
+  return tc2_cfg(cls, ncls, bt, c);
+}
+
+bool k_tapconv_tc2(St st, const TapGeom* cls, int ncls, const float* const* bt, const float* in, float* out, int act, float negval,
+                   std::string* err) {
+  Tc2Cfg c;
+  if (!tc2_cfg(cls, ncls, bt, c)) { if (err) *err = "geometry not taken by the wide-tile tcgen05 kernel"; return false; }
+  Tc2Params& p = c.p;
+  p.act = act; p.neg = negval;
+  const TapGeom& g = cls[0];
+  CUtensorMap mapA;
+  const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  CUresult r;
+  if (g.si == 1) {
+    cuuint64_t dims[4] = {(cuuint64_t)g.Ci, (cuuint64_t)g.Wi, (cuuint64_t)g.Hi, (cuuint64_t)g.N};
+    cuuint64_t strides[3] = {(cuuint64_t)g.Ci * 4, (cuuint64_t)g.Wi * g.Ci * 4, (cuuint64_t)g.Hi * g.Wi * g.Ci * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TB};
+    r = tc_encode_fn()(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)in, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[5] = {(cuuint64_t)2 * g.Ci, (cuuint64_t)g.Wi / 2, 2, (cuuint64_t)g.Hi / 2, (cuuint64_t)g.N};
+    cuuint64_t strides[4] = {(cuuint64_t)2 * g.Ci * 4, (cuuint64_t)g.Wi * g.Ci * 4, (cuuint64_t)2 * g.Wi * g.Ci * 4,
+                             (cuuint64_t)g.Hi * g.Wi * g.Ci * 4};
+    cuuint32_t box[5] = {32, (cuuint32_t)p.TW, 1, (cuuint32_t)p.TH, (cuuint32_t)p.TB};
+    r = tc_encode_fn()(&mapA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)in, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled(A) failed: " + std::to_string((int)r); return false; }
+  static bool configured = false;
+  if (!configured) {
+    if (cudaFuncSetAttribute(tapconv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+      if (err) *err = "cudaFuncSetAttribute(smem) failed";
+      return false;
+    }
+    configured = true;
+  }
+  tapconv_tc2_kernel<<<c.grid, TC2_THREADS, c.smem, st.s>>>(mapA, p, out);
+  DSR_LAUNCHED(st, "tapconv_tc2", c.flops, WORK_FLOPS);
+  return true;
+}

@@ -93,3 +93,47 @@ def test_per_tap_kernel_clusters(ctx_fast, shape, cluster, monkeypatch):
     assert rel_err(dx, ref) <= FAST_TOL, ("dgrad", rel_err(dx, ref))
     for i in range(0, n, 7):
         assert rel_err(dx[i], ref[i]) <= 2 * FAST_TOL, ("dgrad image", i)
+
+
+# the persistent wide-tile per-tap kernel (kernels_tc2.cu): 256 x 128 and 128 x 256 work items, several items per CTA (stage ring
+# and TMEM double-buffer wrap), odd tile counts (a pixel group whose second tile is past the end), stride-1 and stride-2 gathers
+WIDE_SHAPES = [
+    ("conv", 75, 64, 64, 64, 128, 4, 2, 1),     # D layer 2 (train.lua:124): 2 pixel tiles x 128 couts, 300 items; dgrad 4 classes x 64 couts
+    ("conv", 37, 128, 32, 32, 256, 4, 2, 1),    # D layer 3: 128 pixels x 256 couts, odd tile counts; dgrad 2 x 128
+    ("conv", 36, 256, 16, 16, 512, 4, 2, 1),    # D layer 4: two 256-cout tiles per pixel tile; dgrad 128 x 256
+    ("full", 19, 128, 32, 32, 64, 4, 2, 1),     # C1b G layer 3 shape class (FC 128->64): 64-cout images; dgrad 16 taps, stride-2 gather
+    ("conv", 11, 64, 30, 30, 128, 3, 1, 0),     # C1b patch-D layer 2 (train-gray-patch.lua:97): 9 taps, 28 x 28 output (partial tiles)
+]
+
+
+@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("shape", WIDE_SHAPES)
+def test_wide_tile_kernel(ctx_fast, shape, mode, monkeypatch):
+    monkeypatch.setenv("DCGANSR_TC2", mode)            # 2: every geometry the kernel can run, 1: the production policy
+    kind, n, cin, h, w, cout, k, s, p = shape
+    full = kind == "full"
+    r = rng(hash(shape[1:]) % 2**31)
+    x = r.standard_normal((n, cin, h, w)).astype(np.float32)
+    wt = (0.1 * r.standard_normal((cin, cout, k, k) if full else (cout, cin, k, k))).astype(np.float32)
+    ho, wo = ((h - 1) * s - 2 * p + k, (w - 1) * s - 2 * p + k) if full else ((h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1)
+    dy = r.standard_normal((n, cout, ho, wo)).astype(np.float32)
+    lib, hc = ctx_fast.lib, ctx_fast.h
+    pre = "dcgansr_fullconv2d_" if full else "dcgansr_conv2d_"
+    args = (n, cin, h, w, cout, k, s, p)
+    X, W, DY = t64(x), t64(wt), t64(dy)
+    ctx_fast.profile_begin()
+    y = np.empty((n, cout, ho, wo), np.float32)
+    L.check(getattr(lib, pre + "fwd")(hc, ptr(x), ptr(wt), ptr(y), *args), hc)
+    dx = np.empty_like(x)
+    L.check(getattr(lib, pre + "dgrad")(hc, ptr(dy), ptr(wt), ptr(dx), *args), hc)
+    names = [k_["name"] for k_ in ctx_fast.profile_end()]
+    if mode == "2":
+        assert "tapconv_tc2" in names and "tapconv_tc" not in names, names
+    ref = (ops.fullconv2d_fwd(X, W, s, p) if full else ops.conv2d_fwd(X, W, s, p)).numpy()
+    assert rel_err(y, ref) <= FAST_TOL, ("fwd", rel_err(y, ref))
+    for i in range(n):
+        assert rel_err(y[i], ref[i]) <= 2 * FAST_TOL, ("fwd image", i)
+    ref = (ops.fullconv2d_dgrad(DY, W, s, p) if full else ops.conv2d_dgrad(DY, W, x.shape, s, p)).numpy()
+    assert rel_err(dx, ref) <= FAST_TOL, ("dgrad", rel_err(dx, ref))
+    for i in range(n):
+        assert rel_err(dx[i], ref[i]) <= 2 * FAST_TOL, ("dgrad image", i)
