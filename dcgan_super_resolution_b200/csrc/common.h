@@ -19,7 +19,10 @@ struct Prof {
   std::vector<ProfRec> recs;
 };
 // per-context device workspace of the tensor-core kernels (split-K partial tiles + self-resetting arrival counters)
-struct TcWorkspace { float* part = nullptr; size_t part_bytes = 0; int* counters = nullptr; int ncounters = 0; };
+struct TcWorkspace {
+  float* part = nullptr; size_t part_bytes = 0; int* counters = nullptr; int ncounters = 0;
+  double* lpart = nullptr; int* lcounter = nullptr;     // criterion kernel: block partials (256 doubles) + arrival counter (both precisions)
+};
 struct St {
   cudaStream_t s;
   int64_t* launches;

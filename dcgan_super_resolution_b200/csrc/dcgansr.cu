@@ -975,6 +975,9 @@ int dcgansr_ctx_create(const dcgansr_cfg* cfg, dcgansr_ctx** out) {
     CK(ctx, cudaMalloc((void**)&ctx->tcws.counters, ctx->tcws.ncounters * sizeof(int)));
     CK(ctx, cudaMemset(ctx->tcws.counters, 0, ctx->tcws.ncounters * sizeof(int)));
   }
+  CK(ctx, cudaMalloc((void**)&ctx->tcws.lpart, 256 * sizeof(double)));
+  CK(ctx, cudaMalloc((void**)&ctx->tcws.lcounter, sizeof(int)));
+  CK(ctx, cudaMemset(ctx->tcws.lcounter, 0, sizeof(int)));
   if (ctx->cfg.world_size < 1) ctx->cfg.world_size = 1;
   CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CK(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
@@ -1006,6 +1009,8 @@ void dcgansr_ctx_destroy(dcgansr_ctx* ctx) {
   for (float* p : ctx->slots) if (p) cudaFree(p);
   if (ctx->tcws.part) cudaFree(ctx->tcws.part);
   if (ctx->tcws.counters) cudaFree(ctx->tcws.counters);
+  if (ctx->tcws.lpart) cudaFree(ctx->tcws.lpart);
+  if (ctx->tcws.lcounter) cudaFree(ctx->tcws.lcounter);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
   if (ctx->tmp) cudaFree(ctx->tmp);
   if (ctx->label_vec) cudaFree(ctx->label_vec);

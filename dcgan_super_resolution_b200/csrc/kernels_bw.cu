@@ -750,13 +750,18 @@ void k_avgpool2(St st, const float* x, float* y, int N, int H, int W, int C) {
 // criteria (count = nElement of D's output: small) -- one CTA, deterministic, evaluated in double
 // like THNN's BCECriterion (eps 1e-12) / MSECriterion with sizeAverage = true.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) loss_kernel(int kind, const float* __restrict__ x, int64_t count,
-                                                    const float* __restrict__ label_vec, int64_t per, float label_const,
-                                                    double n_total, float* __restrict__ loss_out, float* __restrict__ dx) {
-  __shared__ double red[1024];
+// Small outputs (the DCGAN-64 discriminator: B values) take one CTA; patch discriminators (B x 25 x 25 values, C1b / C4) take up to
+// one CTA per SM: block partials in double, summed in block order by the last CTA to arrive (fixed order: deterministic; the
+// arrival counter resets itself).
+__global__ void __launch_bounds__(256) loss_kernel(int kind, const float* __restrict__ x, int64_t count,
+                                                   const float* __restrict__ label_vec, int64_t per, float label_const,
+                                                   double n_total, float* __restrict__ loss_out, float* __restrict__ dx,
+                                                   double* __restrict__ part, int* __restrict__ counter) {
+  __shared__ double red[256];
+  __shared__ int s_last;
   const double eps = 1e-12;
   double acc = 0.0;
-  for (int64_t i = threadIdx.x; i < count; i += 1024) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < count; i += (int64_t)gridDim.x * 256) {
     double t = label_vec ? (double)label_vec[i / per] : (double)label_const;
     double xd = (double)x[i];
     double l, g;
@@ -773,15 +778,35 @@ __global__ void __launch_bounds__(1024) loss_kernel(int kind, const float* __res
   }
   red[threadIdx.x] = acc;
   __syncthreads();
-  for (int off = 512; off > 0; off >>= 1) {
+  for (int off = 128; off > 0; off >>= 1) {
     if ((int)threadIdx.x < off) red[threadIdx.x] += red[threadIdx.x + off];
     __syncthreads();
   }
-  if (threadIdx.x == 0) loss_out[0] = (float)(red[0] / n_total);
+  if (gridDim.x == 1) {
+    if (threadIdx.x == 0) loss_out[0] = (float)(red[0] / n_total);
+    return;
+  }
+  if (threadIdx.x == 0) {
+    part[blockIdx.x] = red[0];
+    __threadfence();
+    const int old = atomicAdd(counter, 1);
+    s_last = old == (int)gridDim.x - 1;
+    if (s_last) *counter = 0;
+  }
+  __syncthreads();
+  if (s_last && threadIdx.x == 0) {
+    __threadfence();
+    double sum = 0.0;
+    for (int b = 0; b < (int)gridDim.x; ++b) sum += __ldcg(part + b);
+    loss_out[0] = (float)(sum / n_total);
+  }
 }
 void k_loss(St st, int kind, const float* x, int64_t count, const float* label_vec, int64_t per, float label_const,
             double n_total, float* loss_out, float* dx) {
-  loss_kernel<<<1, 1024, 0, st.s>>>(kind, x, count, label_vec, per > 0 ? per : 1, label_const, n_total, loss_out, dx);
+  int nb = 1;
+  if (st.ws && st.ws->lpart && count > 4096) nb = (int)std::min<int64_t>((count + 1023) / 1024, 148);
+  loss_kernel<<<nb, 256, 0, st.s>>>(kind, x, count, label_vec, per > 0 ? per : 1, label_const, n_total, loss_out, dx,
+                                    st.ws ? st.ws->lpart : nullptr, st.ws ? st.ws->lcounter : nullptr);
   DSR_LAUNCHED(st, "criterion", 8.0 * count, WORK_BYTES);
 }
 

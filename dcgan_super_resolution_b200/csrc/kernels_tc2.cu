@@ -50,6 +50,7 @@ struct Tc2Params {
 
 __device__ __forceinline__ void tc2_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
+struct TcMapsW { CUtensorMap w[TC2_MAXCLS]; };      // pair kernel: the weight image buffers as 2-D maps of 128-byte rows
 struct Tc2Item { int cls, ntile, mg; };
 __device__ __forceinline__ Tc2Item tc2_item(const Tc2Params& p, int w) {
   Tc2Item it;
@@ -218,13 +219,238 @@ __global__ void __launch_bounds__(TC2_THREADS, 1) tapconv_tc2_kernel(const __gri
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2) for 256-cout work items: the two SMs of a TPC run ONE 256 pixel x 256 cout x 8 MMA.
+// Each CTA loads its own 128-pixel A tile and HALF of the weight tile (one 128-cout image): 32 KB per 542 tensor cycles per
+// SM = 59 B/clk instead of 88 -- the L2 -> SM path (measured: ~13.5 TB/s chip-wide, lts__t_bytes of the single-CTA kernel equals
+// its operand traffic: the L2 merges nothing) is what bounds these layers.  Protocol:
+//   * both CTAs' TMA loads complete on the LEADER's full barrier (cp.async.bulk.tensor ... .cta_group::2, barrier address with
+//     the cluster-rank bit cleared); the leader arms it with the bytes of both;
+//   * only the leader's MMA warp issues tcgen05.mma.cta_group::2; its tcgen05.commit multicasts to the empty / acc_full
+//     barriers of both CTAs, so each producer and each epilogue waits locally;
+//   * accumulator rows 0..127 live in the leader's TMEM, 128..255 in the peer's; each CTA's epilogue drains its own half and
+//     arrives on the leader's acc_empty barrier (the peer through mapa + a remote arrive).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_4d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {      // arrives on the barrier at this offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t cta) {
+  asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\tmbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(bar), "r"(cta)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+template <int ACT>
+__device__ __forceinline__ void tc2p_epilogue(const Tc2Params& p, float* __restrict__ out, uint32_t tmem_base, uint64_t* acc_full,
+                                              uint64_t* acc_empty, int warp, int lane, uint32_t crank, int pair, int npairs) {
+  const int q = warp & 3;
+  const int r = q * 32 + lane;
+  const int w = r % p.TW;
+  const int h = (r / p.TW) % p.TH;
+  const int b = r / (p.TW * p.TH);
+  const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+  int it = 0;
+  for (int wi = pair; wi < p.nwork; wi += npairs, ++it) {
+    const Tc2Item item = tc2_item(p, wi);
+    const int buf = it & 1;
+    const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+    const int n0 = item.ntile * p.BN;
+    mbar_wait(smem_u32(&acc_full[buf]), aph);
+    tc_fence_after();
+    int tile = item.mg * 2 + (int)crank;
+    if (tile < p.ntiles_m) {
+      const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+      const int ty = tile % p.tiles_y; tile /= p.tiles_y;
+      const int n = tile * p.TB + b, gy = ty * p.TH + h, gx = tx * p.TW + w;
+      const bool valid = n < p.N && gy < p.Hg && gx < p.Wg;
+      float* orow = out + ((int64_t)(n * p.Ho + gy * p.so + p.oy0[item.cls]) * p.Wo + gx * p.so + p.ox0[item.cls]) * p.Co + n0;
+      const uint32_t cbase = lane_base + (uint32_t)(buf * p.acc_cols);
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(cbase + (uint32_t)c0, v);
+        tmem_ld_wait();
+        if (valid) store_row<ACT, 32>(orow + c0, v, n0 + c0, p.Co, p.neg);
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) {
+      if (crank == 0) tc2_arrive(smem_u32(&acc_empty[buf]));
+      else mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(TC2_THREADS, 1) tapconv_tc2_pair_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                          const __grid_constant__ TcMapsW mapsW, const Tc2Params p,
+                                                                          float* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.nstage * p.stage_bytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + p.nstage;
+  uint64_t* acc_full = bars + 2 * p.nstage;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t crank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    for (int s = 0; s < p.nstage; ++s) { mbar_init(smem_u32(&full[s]), 1); mbar_init(smem_u32(&empty[s]), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(smem_u32(&acc_full[s]), 1); mbar_init(smem_u32(&acc_empty[s]), 8); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();              // both CTAs' barriers are initialised before any TMA / commit / remote arrive targets them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t b_off = (uint32_t)p.a_tile_bytes;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs; completion on the leader's barrier) =====================
+    if (elect_one()) {
+      int s = 0;
+      uint32_t ph = 0;
+      const uint32_t bytes_pair = 2u * (uint32_t)p.stage_bytes;
+      for (int wi = pair; wi < p.nwork; wi += npairs) {
+        const Tc2Item item = tc2_item(p, wi);
+        const int cls = item.cls;
+        const int nk = p.ntaps[cls] * p.kchunks;
+        int tile = item.mg * 2 + (int)crank;
+        const int tx = tile % p.tiles_x; tile /= p.tiles_x;
+        const int ty = tile % p.tiles_y; tile /= p.tiles_y;
+        const int b0 = tile * p.TB, gy0 = ty * p.TH, gx0 = tx * p.TW;
+        const int wrow0 = ((item.ntile * 2 + (int)crank) * nk) * 128;         // first row of this CTA's image sequence in the image buffer
+        int t = 0, c = 0;
+        for (int kb = 0; kb < nk; ++kb) {
+          mbar_wait(smem_u32(&empty[s]), ph ^ 1u);
+          const uint32_t fb_local = smem_u32(&full[s]);
+          const uint32_t fb = fb_local & 0xFEFFFFFFu;                          // the leader's barrier (cluster rank bit cleared)
+          if (crank == 0) mbar_expect_tx(fb_local, bytes_pair);
+          const uint32_t st = smem_u32(smem + (size_t)s * p.stage_bytes);
+          if (p.si == 1)
+            tma_load_4d_2sm(st, &mapA, fb, c * 32, gx0 + p.ox[cls][t], gy0 + p.oy[cls][t], b0);
+          else
+            tma_load_5d_2sm(st, &mapA, fb, p.px[cls][t] * p.Ci + c * 32, gx0 + p.ox[cls][t], p.py[cls][t], gy0 + p.oy[cls][t], b0);
+          tma_load_2d_2sm(st + b_off, &mapsW.w[cls], fb, 0, wrow0 + kb * 128);
+          if (++c == p.kchunks) { c = 0; ++t; }
+          if (++s == p.nstage) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1 && crank == 0) {
+    // ===================== MMA issuer (leader only) =====================
+    // instruction descriptor: D = f32, A = B = tf32, both K-major, N = 256, M = 256 (128 rows per CTA)
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((256u >> 4) << 24);
+    int s = 0, it = 0;
+    uint32_t ph = 0;
+    for (int wi = pair; wi < p.nwork; wi += npairs, ++it) {
+      const Tc2Item item = tc2_item(p, wi);
+      const int nk = p.ntaps[item.cls] * p.kchunks;
+      const int buf = it & 1;
+      const uint32_t aph = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(smem_u32(&acc_empty[buf]), aph ^ 1u);
+      tc_fence_after();
+      const uint32_t dbase = tmem_base + (uint32_t)(buf * p.acc_cols);
+      int kc = 0;
+      for (int kb = 0; kb < nk; ++kb) {
+        mbar_wait(smem_u32(&full[s]), ph);
+        tc_fence_after();
+        const int ksteps = kc == p.kchunks - 1 ? p.ksteps_last : 4;
+        if (++kc == p.kchunks) kc = 0;
+        if (elect_one()) {
+          const uint32_t st = smem_u32(smem + (size_t)s * p.stage_bytes);
+          const uint64_t ad = make_kmajor_desc(st, 32);
+          const uint64_t bd = make_kmajor_desc(st + b_off, 32);
+          for (int k = 0; k < ksteps; ++k)
+            umma_tf32_2sm(dbase, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          umma_commit_2sm(smem_u32(&empty[s]));
+          if (kb == nk - 1) umma_commit_2sm(smem_u32(&acc_full[buf]));
+        }
+        __syncwarp();
+        if (++s == p.nstage) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else if (warp >= 2) {
+    switch (p.act) {
+      case ACT_RELU: tc2p_epilogue<ACT_RELU>(p, out, tmem_base, acc_full, acc_empty, warp, lane, crank, pair, npairs); break;
+      case ACT_LRELU: tc2p_epilogue<ACT_LRELU>(p, out, tmem_base, acc_full, acc_empty, warp, lane, crank, pair, npairs); break;
+      case ACT_TANH: tc2p_epilogue<ACT_TANH>(p, out, tmem_base, acc_full, acc_empty, warp, lane, crank, pair, npairs); break;
+      case ACT_SIGMOID: tc2p_epilogue<ACT_SIGMOID>(p, out, tmem_base, acc_full, acc_empty, warp, lane, crank, pair, npairs); break;
+      default: tc2p_epilogue<ACT_NONE>(p, out, tmem_base, acc_full, acc_empty, warp, lane, crank, pair, npairs); break;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();              // no CTA frees its TMEM / leaves while the pair's MMAs, commits or remote arrives may still target it
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
 static inline int pow2_ge2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 static inline int floordiv2_2(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
 
-struct Tc2Cfg { Tc2Params p; size_t smem; int grid; double flops; };
+struct Tc2Cfg { Tc2Params p; size_t smem; int grid; double flops; bool pair; };
+
+// co-resident CTA pairs of the pair kernel at its shared-memory footprint (74 on a full B200; fewer if a TPC has a disabled SM)
+static int tc2_max_clusters() {
+  static int v = -1;
+  if (v >= 0) return v;
+  v = 0;
+  if (cudaFuncSetAttribute(tapconv_tc2_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) { cudaGetLastError(); return v; }
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3(2 * NSM); lc.blockDim = dim3(TC2_THREADS); lc.dynamicSmemBytes = 200 * 1024;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, tapconv_tc2_pair_kernel, &lc) != cudaSuccess) { cudaGetLastError(); return v; }
+  v = std::min(n, NSM / 2);
+  return v;
+}
 
 static bool tc2_cfg(const TapGeom* cls, int ncls, const float* const* bt, Tc2Cfg& c) {
   if (!tc_encode_fn() || !tc_tapconv_multi_ok(cls, ncls) || !bt) return false;
@@ -263,19 +489,31 @@ static bool tc2_cfg(const TapGeom* cls, int ncls, const float* const* bt, Tc2Cfg
   p.n_fast = getenv("DCGANSR_TC2_NFAST") ? 1 : 0;
   p.a_tile_bytes = 128 * 128;
   p.stage_bytes = p.MT * p.a_tile_bytes + p.BN * 128;
+  // CTA pairs (cta_group::2) for the 256-cout items: a pair owns two pixel tiles, each CTA stages its tile + half the weight tile.
+  // Measured (scripts/exp/tc2_pair_sweep.py): 1.2 - 1.5x over the single-CTA items from 32 pair items up (C 128->256 at C1b size
+  // 422 -> 296 us = 929 TFLOP/s; C5's FC 512->256 996 TFLOP/s = 0.91 of the 1.09 PFLOP/s TF32 pipe peak)
+  c.pair = false;
+  {
+    const char* pe = getenv("DCGANSR_TC2_PAIR");
+    const int pmode = pe ? atoi(pe) : 1;
+    const int nwork2 = ncls * p.ntiles_n * ((p.ntiles_m + 1) / 2);
+    const int maxcl = pmode ? tc2_max_clusters() : 0;
+    if (pmode && p.BN == 256 && p.bt_per_n == 2 && p.MT == 1 && maxcl >= 32 && (pmode == 2 || nwork2 >= 32)) {
+      c.pair = true;
+      p.ngroups_m = (p.ntiles_m + 1) / 2;
+      p.nwork = nwork2;
+      p.stage_bytes = p.a_tile_bytes + 128 * 128;
+    }
+  }
   p.nstage = std::max(2, std::min(8, (200 * 1024) / p.stage_bytes));
-  p.acc_cols = p.MT * p.BN;
+  p.acc_cols = c.pair ? p.BN : p.MT * p.BN;
   p.tmem_cols = std::max(32, pow2_ge2(2 * p.acc_cols));
   if (p.tmem_cols > 512) return false;
-  // one CTA per SM walks ceil(nwork / 148) items: take the layer only when that wave count wastes little and the grid fills the
-  // machine (small grids stay on the one-tile kernel with its split-K)
-  c.grid = std::min(p.nwork, NSM);
-  if (mode == 1) {
-    int nk_same = cls[0].ntaps;
-    for (int i = 1; i < ncls; ++i) if (cls[i].ntaps != nk_same) nk_same = -1;
-    const int waves = (p.nwork + NSM - 1) / NSM;
-    if (p.nwork < NSM || (double)p.nwork / ((double)waves * NSM) < 0.8 || nk_same < 0) return false;
-  }
+  // one CTA per SM walks ceil(nwork / 148) items.  Measured per layer and batch against the one-tile kernel (scripts/exp/tc2_sweep.py):
+  // 1.15 - 1.6x from ~128 items up whatever the wave count, even at 32 - 64 items, slower below (C 256->512 at 8 x 8, batch 64:
+  // 16 items, 0.72x -- the one-tile kernel's split-K fills the machine there)
+  c.grid = c.pair ? 2 * std::min(p.nwork, tc2_max_clusters()) : std::min(p.nwork, NSM);
+  if (mode == 1 && !c.pair && p.nwork < 96) return false;
   c.flops = 0;
   for (int i = 0; i < ncls; ++i) {
     p.bt[i] = bt[i];
@@ -330,6 +568,32 @@ bool k_tapconv_tc2(St st, const TapGeom* cls, int ncls, const float* const* bt, 
       return false;
     }
     configured = true;
+  }
+  if (c.pair) {
+    TcMapsW mw;
+    memset(&mw, 0, sizeof(mw));
+    for (int i = 0; i < ncls; ++i) {
+      const cuuint64_t rows = (cuuint64_t)((g.Co + 127) / 128) * cls[i].ntaps * p.kchunks * 128;
+      cuuint64_t dims[2] = {32, rows};
+      cuuint64_t strides[1] = {128};
+      cuuint32_t box[2] = {32, 128};
+      r = tc_encode_fn()(&mw.w[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)bt[i], dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled(W images) failed: " + std::to_string((int)r); return false; }
+    }
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = dim3((unsigned)c.grid); lc.blockDim = dim3(TC2_THREADS); lc.dynamicSmemBytes = c.smem; lc.stream = st.s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    if (cudaLaunchKernelEx(&lc, tapconv_tc2_pair_kernel, mapA, mw, p, out) != cudaSuccess) {
+      if (err) *err = std::string("pair-kernel launch failed: ") + cudaGetErrorString(cudaGetLastError());
+      return false;
+    }
+    DSR_LAUNCHED(st, "tapconv_tc2_pair", c.flops, WORK_FLOPS);
+    return true;
   }
   tapconv_tc2_kernel<<<c.grid, TC2_THREADS, c.smem, st.s>>>(mapA, p, out);
   DSR_LAUNCHED(st, "tapconv_tc2", c.flops, WORK_FLOPS);

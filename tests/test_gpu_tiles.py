@@ -106,10 +106,14 @@ WIDE_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("mode", ["1", "2"])
+@pytest.mark.parametrize("mode", ["1", "2", "2p"])
 @pytest.mark.parametrize("shape", WIDE_SHAPES)
 def test_wide_tile_kernel(ctx_fast, shape, mode, monkeypatch):
-    monkeypatch.setenv("DCGANSR_TC2", mode)            # 2: every geometry the kernel can run, 1: the production policy
+    # 1: the production policy, 2: every geometry the kernel can run (single-CTA items only), 2p: the same with the 256-cout
+    # items forced onto CTA pairs (cta_group::2)
+    monkeypatch.setenv("DCGANSR_TC2_PAIR", "2" if mode == "2p" else ("0" if mode == "2" else "1"))
+    mode = mode[0]
+    monkeypatch.setenv("DCGANSR_TC2", mode)
     kind, n, cin, h, w, cout, k, s, p = shape
     full = kind == "full"
     r = rng(hash(shape[1:]) % 2**31)
@@ -128,7 +132,7 @@ def test_wide_tile_kernel(ctx_fast, shape, mode, monkeypatch):
     L.check(getattr(lib, pre + "dgrad")(hc, ptr(dy), ptr(wt), ptr(dx), *args), hc)
     names = [k_["name"] for k_ in ctx_fast.profile_end()]
     if mode == "2":
-        assert "tapconv_tc2" in names and "tapconv_tc" not in names, names
+        assert ("tapconv_tc2" in names or "tapconv_tc2_pair" in names) and "tapconv_tc" not in names, names
     ref = (ops.fullconv2d_fwd(X, W, s, p) if full else ops.conv2d_fwd(X, W, s, p)).numpy()
     assert rel_err(y, ref) <= FAST_TOL, ("fwd", rel_err(y, ref))
     for i in range(n):
