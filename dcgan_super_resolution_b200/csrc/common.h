@@ -206,6 +206,10 @@ bool k_tapconv_tc_multi(St st, const TapGeom* classes, int ncls, const float* co
 bool tc2_tapconv_supported(const TapGeom* classes, int ncls, const float* const* bt);
 bool k_tapconv_tc2(St st, const TapGeom* classes, int ncls, const float* const* bt, const float* in, float* out, int act, float negval,
                    std::string* err);
+// ---- kernels_tc3.cu : halo-tile A + streamed weights on CTA pairs (class groups with <= 128 couts) ----
+bool tc3_tapconv_supported(const TapGeom* classes, int ncls, const float* const* bt);
+bool k_tapconv_tc3(St st, const TapGeom* classes, int ncls, const float* const* bt, const float* in, float* out, int act, float negval,
+                   std::string* err);
 bool tc_wgrad_supported(const WgradGeom& g);
 size_t wgrad_tc_scratch_bytes(const WgradGeom& g);
 bool k_wgrad_tc(St st, const WgradGeom& g, const float* P, const float* Q, float* grad_master, float* scratch, size_t scratch_bytes,

@@ -451,6 +451,13 @@ struct ConvPlan {
       }
       const float* bts[4];
       for (size_t i = 0; i < v.size(); ++i) bts[i] = v[i].bt;
+      if (all_tc && tc3_tapconv_supported(gs, (int)v.size(), bts)) {
+        std::string e;
+        if (k_tapconv_tc3(ctx->st(), gs, (int)v.size(), bts, in, out, act, neg, &e)) return;
+        ctx->err = "tcgen05 halo-tile pair path: " + e;
+        ctx->tc_failed = true;
+        return;
+      }
       if (all_tc && tc2_tapconv_supported(gs, (int)v.size(), bts)) {
         std::string e;
         if (k_tapconv_tc2(ctx->st(), gs, (int)v.size(), bts, in, out, act, neg, &e)) return;

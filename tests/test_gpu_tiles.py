@@ -114,6 +114,7 @@ def test_wide_tile_kernel(ctx_fast, shape, mode, monkeypatch):
     monkeypatch.setenv("DCGANSR_TC2_PAIR", "2" if mode == "2p" else ("0" if mode == "2" else "1"))
     mode = mode[0]
     monkeypatch.setenv("DCGANSR_TC2", mode)
+    monkeypatch.setenv("DCGANSR_TC3", "0")             # (the halo-tile pair kernel would take most of these shapes first)
     kind, n, cin, h, w, cout, k, s, p = shape
     full = kind == "full"
     r = rng(hash(shape[1:]) % 2**31)
@@ -133,6 +134,52 @@ def test_wide_tile_kernel(ctx_fast, shape, mode, monkeypatch):
     names = [k_["name"] for k_ in ctx_fast.profile_end()]
     if mode == "2":
         assert ("tapconv_tc2" in names or "tapconv_tc2_pair" in names) and "tapconv_tc" not in names, names
+    ref = (ops.fullconv2d_fwd(X, W, s, p) if full else ops.conv2d_fwd(X, W, s, p)).numpy()
+    assert rel_err(y, ref) <= FAST_TOL, ("fwd", rel_err(y, ref))
+    for i in range(n):
+        assert rel_err(y[i], ref[i]) <= 2 * FAST_TOL, ("fwd image", i)
+    ref = (ops.fullconv2d_dgrad(DY, W, s, p) if full else ops.conv2d_dgrad(DY, W, x.shape, s, p)).numpy()
+    assert rel_err(dx, ref) <= FAST_TOL, ("dgrad", rel_err(dx, ref))
+    for i in range(n):
+        assert rel_err(dx[i], ref[i]) <= 2 * FAST_TOL, ("dgrad image", i)
+
+
+# the halo-tile pair kernel (kernels_tc3.cu): 8 x 16 pixel tiles with a halo, every tap a shifted window, streamed weight halves,
+# cta_group::2.  Shapes: 2 x 2-tap sub-pixel classes (full-conv forward / conv dgrad), the 16-tap stride-2 gather through the four
+# parity planes (conv forward / full-conv dgrad), 3 x 3 stride-1 taps, odd tile counts, partial tiles, 64 / 128 / 256 couts
+HALO_PAIR_SHAPES = [
+    ("full", 5, 256, 32, 32, 128, 4, 2, 1),     # C1b G layer 2 shape class (FC 256->128): fwd 4 classes x 128 couts; dgrad 256 couts, 4 planes
+    ("conv", 7, 64, 64, 64, 128, 4, 2, 1),      # D layer 2 (train.lua:124): fwd through the parity planes, dgrad 4 classes x 64 couts
+    ("conv", 9, 128, 32, 48, 256, 4, 2, 1),     # D layer 3, non-square: dgrad 4 classes x 128 couts on 16 x 24 class grids
+    ("conv", 6, 64, 30, 30, 128, 3, 1, 0),      # patch-D layer 2 (train-gray-patch.lua:97): 9 taps, 28 x 28 grid (partial tiles)
+    ("full", 3, 128, 24, 40, 64, 4, 2, 1),      # 64-cout images (32-row weight halves)
+]
+
+
+@pytest.mark.parametrize("shape", HALO_PAIR_SHAPES)
+def test_halo_pair_kernel(ctx_fast, shape, monkeypatch):
+    monkeypatch.setenv("DCGANSR_TC3", "2")             # every geometry the kernel can run
+    monkeypatch.setenv("DCGANSR_NO_HALO_PER_CLASS", "1")
+    kind, n, cin, h, w, cout, k, s, p = shape
+    full = kind == "full"
+    r = rng(hash(shape[1:]) % 2**31)
+    x = r.standard_normal((n, cin, h, w)).astype(np.float32)
+    wt = (0.1 * r.standard_normal((cin, cout, k, k) if full else (cout, cin, k, k))).astype(np.float32)
+    ho, wo = ((h - 1) * s - 2 * p + k, (w - 1) * s - 2 * p + k) if full else ((h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1)
+    dy = r.standard_normal((n, cout, ho, wo)).astype(np.float32)
+    lib, hc = ctx_fast.lib, ctx_fast.h
+    pre = "dcgansr_fullconv2d_" if full else "dcgansr_conv2d_"
+    args = (n, cin, h, w, cout, k, s, p)
+    X, W, DY = t64(x), t64(wt), t64(dy)
+    ctx_fast.profile_begin()
+    y = np.empty((n, cout, ho, wo), np.float32)
+    L.check(getattr(lib, pre + "fwd")(hc, ptr(x), ptr(wt), ptr(y), *args), hc)
+    dx = np.empty_like(x)
+    L.check(getattr(lib, pre + "dgrad")(hc, ptr(dy), ptr(wt), ptr(dx), *args), hc)
+    prof = {}
+    for k_ in ctx_fast.profile_end():
+        prof[k_["name"]] = prof.get(k_["name"], 0) + k_["launches"]
+    assert prof.get("tapconv_tc3", 0) == 2 and "tapconv_tc" not in prof and "tapconv_tc2" not in prof, prof
     ref = (ops.fullconv2d_fwd(X, W, s, p) if full else ops.conv2d_fwd(X, W, s, p)).numpy()
     assert rel_err(y, ref) <= FAST_TOL, ("fwd", rel_err(y, ref))
     for i in range(n):
