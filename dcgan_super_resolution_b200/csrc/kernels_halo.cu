@@ -41,7 +41,11 @@
 #define HALO_MAXSLOT 8
 #define HALO_MAXRING 16
 
-struct HaloMaps { CUtensorMap b[HALO_MAXCLS]; };
+struct HaloMaps { CUtensorMap b[HALO_MAXCLS]; CUtensorMap bh[HALO_MAXCLS]; };      // bh: boxes of Npad / 2 rows (CTA-pair mode, single-class MMAs)
+// CTA-pair mode: the resident weights of CTA `rank` as a list of TMA boxes {class | half-box flag << 8, K coordinate, cout offset,
+// destination >> 4}: for an MMA over m classes a CTA holds rows [rank * N/2, (rank + 1) * N/2) of the m * Npad stacked weight rows
+#define HALO_MAXWL 160
+struct HaloWList { int n; uint4 e[2][HALO_MAXWL]; };
 #define HALO_MAXMMA 256
 // MMA issue table (kernel parameter = constant bank, so the issuing warp reads it through the uniform datapath):
 // one entry per tcgen05.mma of a tile {A offset >> 4, W offset >> 4, TMEM column | accumulate << 31, instruction descriptor}:
@@ -79,6 +83,8 @@ struct HaloParams {
   short st_bc0[HALO_MAXCLS], st_bpy[HALO_MAXCLS];        // box -> channel coordinate, row-parity coordinate
   double* stats;                         // != nullptr: BatchNorm statistics of the OUTPUT fused into the epilogue: row (stats_row0 + blockIdx.x) of
   int stats_row0;                        // [rows][2*Co] doubles receives this CTA's (sum y, sum y^2) per output channel (its cout slice)
+  int pair;                              // CTA pairs (cta_group::2): one MMA covers the tiles of both CTAs (M = 256), each CTA holds half of
+                                         // every weight block; loads complete on the leader's barriers, commits are multicast
   int dbg;                               // DCGANSR_HALO_DBG (timing experiments only): 1 skip MMAs, 2 skip stores, 4 skip the halo TMA loads
 };
 
@@ -102,7 +108,7 @@ __device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr, uint32_t sbo, ui
 template <int ACT>
 __device__ __forceinline__ void halo_epilogue(const HaloParams& p, float* __restrict__ out, uint32_t tmem_base, uint64_t* acc_full,
                                               uint64_t* acc_empty, int warp, int half, int lane, int n0, const CUtensorMap* mapO,
-                                              uint32_t sO, float* sred) {
+                                              uint32_t sO, float* sred, uint32_t crank) {
   const int q = warp & 3;                       // TMEM lane quarter this warp may access
   const int r = q * 32 + lane;                  // tile row = pixel
   const int w = r % HALO_TW, h = r / HALO_TW;
@@ -116,14 +122,17 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams& p, float* __rest
 #pragma unroll
   for (int j = 0; j < 16; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
   int it = 0;
-  for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+  // pair mode: the pair walks tile pairs, CTA `crank` owns the second tile of each (one past the end when ntiles is odd)
+  const int tstep = p.pair ? (int)gridDim.x : (int)gridDim.x, tfirst = p.pair ? (int)(blockIdx.x & ~1u) + (int)crank : (int)blockIdx.x;
+  const int tlimit = p.pair ? ((p.ntiles + 1) & ~1) : p.ntiles;
+  for (int tile = tfirst; tile < tlimit; tile += tstep, ++it) {
     const int buf = it % p.nacc;
     const uint32_t aph = (uint32_t)(it / p.nacc) & 1u;
     int tt = tile;
     const int tx = tt % p.tiles_x; tt /= p.tiles_x;
     const int ty = tt % p.tiles_y; tt /= p.tiles_y;
     const int n = tt, gy = ty * HALO_TH + h, gx = tx * HALO_TW + w;
-    const bool valid = gy < p.Hg && gx < p.Wg && !(p.dbg & 2);
+    const bool valid = tile < p.ntiles && gy < p.Hg && gx < p.Wg && !(p.dbg & 2);
     float* pix = out + ((int64_t)(n * p.Ho + gy * p.so) * p.Wo + gx * p.so) * p.Co + n0;
     const uint32_t cbase = lane_base + (uint32_t)(buf * p.acc_cols);
     // TMA-store mode: with two staging buffers, buffer it & 1 was the source of the store group issued two tiles ago; with
@@ -163,7 +172,7 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams& p, float* __rest
           v[j] = __float_as_uint(sum);
         }
       }
-      if (dostats && gy < p.Hg && gx < p.Wg) {
+      if (dostats && tile < p.ntiles && gy < p.Hg && gx < p.Wg) {
 #pragma unroll
         for (int j = 0; j < 16; ++j) { const float y = __uint_as_float(v[j]); s1[j] += y; s2[j] = fmaf(y, y, s2[j]); }
       }
@@ -188,11 +197,14 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams& p, float* __rest
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+    if (lane == 0) {
+      if (crank == 0) mbar_arrive(smem_u32(&acc_empty[buf]));
+      else mbar_arrive_remote(smem_u32(&acc_empty[buf]), 0);        // the leader's MMA issuers own the accumulator ring of both CTAs
+    }
     if (p.tstore) {
       fence_proxy_async_smem();
       named_bar_sync(3, 256);
-      if (leader && !(p.dbg & 2)) {
+      if (leader && tile < p.ntiles && !(p.dbg & 2)) {
         const int gy0 = ty * HALO_TH, gx0 = tx * HALO_TW;
         // so == 2: output seen as [N][Ho/2][2][Wo/2][2*Co], class (coy, cox) = row parity coy, channel offset cox*Co;
         // so == 1: the same 5-D view [N][Ho][1][Wo][Co] with a unit parity dimension
@@ -232,10 +244,14 @@ __device__ __forceinline__ void halo_epilogue(const HaloParams& p, float* __rest
   }
 }
 
+// PAIR: a separate instantiation, because a kernel that contains cta_group::2 instructions cannot be launched without a cluster
+// ("cluster misconfiguration"), whatever path it takes at run time
+template <bool PAIR>
 __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                     const __grid_constant__ HaloMaps mapsB,
                                                                     const __grid_constant__ HaloTab tab,
                                                                     const __grid_constant__ CUtensorMap mapO,
+                                                                    const __grid_constant__ HaloWList wl,
                                                                     const HaloParams p, float* __restrict__ out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -252,6 +268,8 @@ __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel
   float* sred = reinterpret_cast<float*>(tmem_slot + 4);                 // 8 warps x 32 floats (fused BatchNorm statistics)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n0 = blockIdx.y * p.Npad;
+  uint32_t crank = 0;
+  if (PAIR) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
@@ -262,36 +280,56 @@ __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel
     }
     for (int s = 0; s < 4; ++s) {
       mbar_init(smem_u32(&acc_full[s]), (uint32_t)p.ngrp);
-      mbar_init(smem_u32(&acc_empty[s]), 8);
+      mbar_init(smem_u32(&acc_empty[s]), PAIR ? 16 : 8);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {      // TMEM owner
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();      // both CTAs' barriers exist before any load / commit / remote arrive targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const int tstep = (int)gridDim.x, tfirst = PAIR ? (int)(blockIdx.x & ~1u) + (int)crank : (int)blockIdx.x;
+  const int tlimit = PAIR ? ((p.ntiles + 1) & ~1) : p.ntiles;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (elect_one()) {
       // resident weights: every (class, tap, chunk) tile of this CTA's cout slice
       const uint32_t wf = smem_u32(w_full);
-      mbar_expect_tx(wf, (uint32_t)p.w_tx);
-      for (int c = 0; c < p.ncls; ++c)
-        for (int t = 0; t < p.ntaps[c]; ++t)
-          for (int q = 0; q < p.kchunks; ++q)
-            tma_load_2d(smem_u32(sW) + (uint32_t)(p.tap_wtile[c][t] + q * p.tap_wstride[c][t]) * p.wtile_bytes, &mapsB.b[c], wf,
-                        t * p.Ci + q * p.KBw, n0);
+      if (PAIR) {
+        // this CTA's half of every weight block; both CTAs' boxes complete on the leader's barrier
+        if (crank == 0) mbar_expect_tx(wf, 2u * (uint32_t)p.w_tx);
+        const uint32_t wfl = wf & 0xFEFFFFFFu;
+        for (int i = 0; i < wl.n; ++i) {
+          const uint4 e = wl.e[crank][i];
+          const int c = (int)(e.x & 0xFFu);
+          tma_load_2d_2sm(smem_u32(sW) + (e.w << 4), (e.x >> 8) ? &mapsB.bh[c] : &mapsB.b[c], wfl, (int)e.y, n0 + (int)e.z);
+        }
+      } else {
+        mbar_expect_tx(wf, (uint32_t)p.w_tx);
+        for (int c = 0; c < p.ncls; ++c)
+          for (int t = 0; t < p.ntaps[c]; ++t)
+            for (int q = 0; q < p.kchunks; ++q)
+              tma_load_2d(smem_u32(sW) + (uint32_t)(p.tap_wtile[c][t] + q * p.tap_wstride[c][t]) * p.wtile_bytes, &mapsB.b[c], wf,
+                          t * p.Ci + q * p.KBw, n0);
+      }
       // plane ring: plane pl of the CTA's it-th tile lives in buffer (it * nplanes + pl) % nring
       int rs = 0;
       uint32_t rph = 0;
       const int pf_dist = p.nring / p.nplanes + 1;
-      for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x) {
+      for (int tile = tfirst; tile < tlimit; tile += tstep) {
         int tt = tile;
         const int tx = tt % p.tiles_x; tt /= p.tiles_x;
         const int ty = tt % p.tiles_y; tt /= p.tiles_y;
@@ -299,7 +337,7 @@ __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel
         // L2 prefetch of the halo tile `pf_dist` tiles ahead: the smem ring is only 1-2 tiles deep (the weights take
         // most of the shared memory), which alone does not keep enough DRAM reads in flight
         {
-          const int ptile = tile + pf_dist * (int)gridDim.x;
+          const int ptile = tile + pf_dist * tstep;
           if (ptile < p.ntiles) {
             int pt = ptile;
             const int ptx = pt % p.tiles_x; pt /= p.tiles_x;
@@ -315,10 +353,18 @@ __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel
         for (int pl = 0; pl < p.nplanes; ++pl) {
           mbar_wait(smem_u32(&a_empty[rs]), rph ^ 1u);
           const uint32_t fb = smem_u32(&a_full[rs]);
-          if (p.dbg & 4) mbar_arrive(fb);
+          const uint32_t dst = smem_u32(sA + (size_t)rs * p.plane_bytes);
+          if (PAIR) {
+            // a tile past the end (odd tile count): image index out of range, the box is zero-filled and still counts its bytes
+            if (crank == 0) mbar_expect_tx(fb, 2u * (uint32_t)p.plane_tx);
+            const uint32_t fbl = fb & 0xFEFFFFFFu;
+            if (p.si == 1)
+              tma_load_4d_2sm(dst, &mapA, fbl, p.pl_c[pl], gx0 + p.pl_x[pl], gy0 + p.pl_y[pl], n);
+            else
+              tma_load_5d_2sm(dst, &mapA, fbl, p.pl_c[pl], gx0 + p.pl_x[pl], p.pl_py[pl], gy0 + p.pl_y[pl], n);
+          } else if (p.dbg & 4) mbar_arrive(fb);
           else {
             mbar_expect_tx(fb, (uint32_t)p.plane_tx);
-            const uint32_t dst = smem_u32(sA + (size_t)rs * p.plane_bytes);
             if (p.si == 1)
               tma_load_4d(dst, &mapA, fb, p.pl_c[pl], gx0 + p.pl_x[pl], gy0 + p.pl_y[pl], n);
             else
@@ -328,6 +374,8 @@ __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel
         }
       }
     }
+  } else if (warp <= p.ngrp && crank != 0) {
+    // pair mode, second CTA: the leader's issuers run the MMAs of both tiles
   } else if (warp <= p.ngrp) {
     // ===================== MMA issuers =====================
     // The MMAs of these thin layers are small (N = 16..64: 8..32 tensor cycles each) while issuing one costs a single
@@ -342,7 +390,7 @@ __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel
     const uint64_t bdesc = make_desc_k(smem_u32(sW), w_sbo, wl);
     int it = 0, rs = 0;
     uint32_t rph = 0;
-    for (int tile = blockIdx.x; tile < p.ntiles; tile += gridDim.x, ++it) {
+    for (int tile = tfirst; tile < tlimit; tile += tstep, ++it) {
       const int buf = it % p.nacc;
       const uint32_t aph = (uint32_t)(it / p.nacc) & 1u;
       mbar_wait(smem_u32(&acc_empty[buf]), aph ^ 1u);
@@ -356,13 +404,23 @@ __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel
         if (elect_one()) {
           const uint64_t adesc = make_desc_k(smem_u32(sA + (size_t)rs * p.plane_bytes), (uint32_t)p.pitch_bytes, (uint64_t)p.a_layout);
           const int iend = (p.dbg & 1) ? min(i + 1, (int)p.pend[grp][pl]) : (int)p.pend[grp][pl];
+          if (PAIR) {
 #pragma unroll 4
-          for (int k = i; k < iend; ++k) {
-            const uint4 e = tab.e[k];
-            umma_tf32(dbase + (e.z & 0xFFFFu), adesc + (uint64_t)e.x, bdesc + (uint64_t)e.y, e.w, (uint32_t)((int)e.z < 0 ? 0 : 1));
+            for (int k = i; k < iend; ++k) {
+              const uint4 e = tab.e[k];
+              umma_tf32_2sm(dbase + (e.z & 0xFFFFu), adesc + (uint64_t)e.x, bdesc + (uint64_t)e.y, e.w, (uint32_t)((int)e.z < 0 ? 0 : 1));
+            }
+            umma_commit_2sm(smem_u32(&a_empty[rs]));
+            if (pl == p.nplanes - 1) umma_commit_2sm(smem_u32(&acc_full[buf]));
+          } else {
+#pragma unroll 4
+            for (int k = i; k < iend; ++k) {
+              const uint4 e = tab.e[k];
+              umma_tf32(dbase + (e.z & 0xFFFFu), adesc + (uint64_t)e.x, bdesc + (uint64_t)e.y, e.w, (uint32_t)((int)e.z < 0 ? 0 : 1));
+            }
+            umma_commit(smem_u32(&a_empty[rs]));
+            if (pl == p.nplanes - 1) umma_commit(smem_u32(&acc_full[buf]));
           }
-          umma_commit(smem_u32(&a_empty[rs]));
-          if (pl == p.nplanes - 1) umma_commit(smem_u32(&acc_full[buf]));
         }
         __syncwarp();
         i = p.pend[grp][pl];
@@ -373,18 +431,20 @@ __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel
     const int half = (warp - p.ngrp - 1) >> 2;
     // ===================== epilogue: TMEM -> registers -> activation -> NHWC global =====================
     switch (p.act) {
-      case ACT_RELU: halo_epilogue<ACT_RELU>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut), sred); break;
-      case ACT_LRELU: halo_epilogue<ACT_LRELU>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut), sred); break;
-      case ACT_TANH: halo_epilogue<ACT_TANH>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut), sred); break;
-      case ACT_SIGMOID: halo_epilogue<ACT_SIGMOID>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut), sred); break;
-      default: halo_epilogue<ACT_NONE>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut), sred); break;
+      case ACT_RELU: halo_epilogue<ACT_RELU>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut), sred, crank); break;
+      case ACT_LRELU: halo_epilogue<ACT_LRELU>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut), sred, crank); break;
+      case ACT_TANH: halo_epilogue<ACT_TANH>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut), sred, crank); break;
+      case ACT_SIGMOID: halo_epilogue<ACT_SIGMOID>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut), sred, crank); break;
+      default: halo_epilogue<ACT_NONE>(p, out, tmem_base, acc_full, acc_empty, warp, half, lane, n0, &mapO, smem_u32(sOut), sred, crank); break;
     }
   }
   tc_fence_before();
   __syncthreads();
+  if (PAIR) cluster_sync_all();      // neither CTA frees its TMEM / leaves while the pair's MMAs, commits or remote arrives may target it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
   }
 }
 
@@ -394,15 +454,42 @@ __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel
 static inline int pow2_ge_h(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 static inline int floordiv2_h(int v) { return v >= 0 ? v / 2 : -((-v + 1) / 2); }
 
-struct HaloCfg { HaloParams p; HaloTab tab; int nsplit; size_t smem; int grid_x; };
+struct HaloCfg { HaloParams p; HaloTab tab; HaloWList wl; int nsplit; size_t smem; int grid_x; };
 
 #define HALO_SMEM_MAX 232448      // 227 KB: the sm_100 per-block dynamic shared memory limit
 
+static int halo_max_clusters();
+static bool halo_cfg_mode(const TapGeom* cls, int ncls, HaloCfg& c, bool pair);
+
+// CTA pairs first (DCGANSR_HALO_PAIR: 0 never, 1 where the geometry allows, default), the single-CTA form otherwise.  The choice
+// depends on the geometry only, never on the batch: the plan-time decisions of dcgansr.cu (halo_mode, weight packs) and the
+// run-time configuration must agree.
 static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
+  // Measured per layer (C2 / C3b / C4, scripts/bench_layers.py with DCGANSR_HALO_PAIR=2): a cta_group::2 MMA with N <= 128 costs
+  // ~110 tensor cycles against 64 for the single-CTA M = 128 one, so pairs do not cut the tensor time of these thin layers
+  // (FC 48->24 forward 1258 -> 1374 us, C2 FC 64->32 dgrad 143 -> 210 us).  What they do is CAPACITY: each CTA holds half of every
+  // weight block, so a class group whose weights do not fit one CTA runs as ONE launch with merged classes (FC 96->48 forward,
+  // 295 KB: four per-class launches 1056 us -> 679 us) and a cout-split layer whose plane ring is starved by its weights reads
+  // its input once (FC 96->48 dgrad 958 -> 681 us).  DCGANSR_HALO_PAIR: 0 never, 1 that policy (default), 2 wherever possible.
+  const char* e = getenv("DCGANSR_HALO_PAIR");
+  const int pm = e ? atoi(e) : 1;
+  const bool can_pair = pm && halo_max_clusters() >= 32;
+  if (pm == 2 && can_pair && halo_cfg_mode(cls, ncls, c, true)) return true;
+  const bool single = halo_cfg_mode(cls, ncls, c, false);
+  // (single-CTA form kept when it runs in one or two cout slices with a plane ring of at least one whole tile)
+  if (!can_pair || (single && (c.nsplit == 1 || (c.nsplit == 2 && c.p.nring >= c.p.nplanes)))) return single;
+  HaloCfg c2;
+  if (halo_cfg_mode(cls, ncls, c2, true) && (!single || c2.nsplit < c.nsplit)) { c = c2; return true; }
+  return single;
+}
+
+static bool halo_cfg_mode(const TapGeom* cls, int ncls, HaloCfg& c, bool pair) {
   if (!tc_encode_fn() || ncls < 1 || ncls > HALO_MAXCLS) return false;
   HaloParams& p = c.p;
   memset(&p, 0, sizeof(p));
   memset(&c.tab, 0, sizeof(c.tab));
+  c.wl.n = 0;
+  p.pair = pair ? 1 : 0;
   const TapGeom& g0 = cls[0];
   const int Ci = g0.Ci;
   // channel counts: multiples of 32 or 16 map exactly; for si == 1 any multiple of 4 (the reference's ngf = 12 gives 48 / 24 / 12)
@@ -521,7 +608,7 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
   auto set_npad = [&](int npad) {
     p.Npad = npad;
     p.wtile_bytes = npad * p.KBw * 4;            // a multiple of 1024 (npad % 16 == 0, KBw >= 16)
-    p.w_bytes = ttot * p.kchunks * p.wtile_bytes;
+    p.w_bytes = ttot * p.kchunks * p.wtile_bytes / (pair ? 2 : 1);       // pair mode: each CTA holds half of every weight block
     p.w_tx = p.w_bytes;
     p.acc_cols = (try_merge ? 5 : (ncls > 1 ? ncls : std::min(HALO_MAXGRP, cls[0].ntaps))) * npad;
   };
@@ -652,21 +739,39 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
     // one entry per MMA, then a stable sort by (issuer group, plane): the issuers consume the plane ring in plane order
     struct Ent { int grp, plane; uint4 e; };
     std::vector<Ent> ents;
-    int i = 0, wt = 0;       // wt: running weight-tile index
+    int i = 0, wt = 0;       // wt: running weight-tile index (pair mode: in half tiles of Npad / 2 rows)
+    const uint32_t hb = (uint32_t)p.wtile_bytes / 2;
     for (auto& o : ops) {
       int grp = 0;
       while (grp + 1 < p.ngrp && i >= p.gbeg[grp + 1]) ++grp;
       for (int j = 0; j < o.m; ++j) { p.tap_wtile[o.cl[j]][o.tp[j]] = (unsigned short)(wt + j); p.tap_wstride[o.cl[j]][o.tp[j]] = (unsigned short)o.m; }
+      if (pair) {
+        // rows [rank * N/2, (rank + 1) * N/2) of the o.m stacked class tiles: m = 1 half a tile, m = 2 one class each, m = 4 two each
+        if (o.m == 3) return false;
+        for (int q = 0; q < p.kchunks; ++q)
+          for (int rank = 0; rank < 2; ++rank) {
+            const uint32_t dst = (uint32_t)(wt + q * o.m) * hb;
+            const int nl = o.m == 4 ? 2 : 1;
+            for (int l = 0; l < nl; ++l) {
+              const int j = o.m == 1 ? 0 : (o.m == 2 ? rank : 2 * rank + l);
+              const int idx = c.wl.n + (rank == 0 ? l : l);      // both ranks fill the same slots
+              if (idx >= HALO_MAXWL) return false;
+              c.wl.e[rank][idx] = make_uint4((uint32_t)o.cl[j] | (o.m == 1 ? 0x100u : 0u), (uint32_t)(o.tp[j] * Ci + q * p.KBw),
+                                            o.m == 1 ? (uint32_t)(rank * (p.Npad / 2)) : 0u, (dst + (uint32_t)l * p.wtile_bytes) >> 4);
+            }
+            if (rank == 1) c.wl.n += nl;
+          }
+      }
       for (int q = 0; q < p.kchunks; ++q)
         for (int k = 0; k < ks_of(q); ++k, ++i) {
           // si == 1: plane = K chunk.  si == 2: the tap's K step sits f floats into the wide pixel row -> plane f / 32
           const int f = tap_kb[o.tp[0]] + q * p.KBw + k * 8;
           const int plane = p.si == 1 ? o.a_plane + q : o.a_plane + f / 32;
           const uint32_t aoff = p.si == 1 ? (uint32_t)o.a_off + k * 32 : (uint32_t)o.a_off + (f % 32) * 4;
-          const uint32_t woff = (uint32_t)(wt + q * o.m) * p.wtile_bytes + k * 32;
+          const uint32_t woff = pair ? (uint32_t)(wt + q * o.m) * hb + k * 32 : (uint32_t)(wt + q * o.m) * p.wtile_bytes + k * 32;
           const uint32_t accum = (o.init && q == 0 && k == 0) ? 0u : 1u;
-          // D = f32, A = B = tf32, K-major, M = 128, N = m * Npad
-          const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((o.m * p.Npad) >> 3) << 17) | ((128u >> 4) << 24);
+          // D = f32, A = B = tf32, K-major, M = 128 (pair mode: 256, 128 rows per CTA), N = m * Npad
+          const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((o.m * p.Npad) >> 3) << 17) | (((pair ? 256u : 128u) >> 4) << 24);
           if (plane < 0 || plane >= p.nplanes) return false;
           ents.push_back(Ent{grp, plane, make_uint4(aoff >> 4, woff >> 4, (uint32_t)(o.slot0 * p.Npad) | (accum ? 0u : 0x80000000u), idesc)});
         }
@@ -748,7 +853,31 @@ static bool halo_cfg(const TapGeom* cls, int ncls, HaloCfg& c) {
   c.smem = fixed + (size_t)p.w_bytes + (size_t)p.nring * p.plane_bytes + (size_t)p.st_nbuf * p.st_bytes;
   // one persistent CTA per SM (13 warps x ~100 registers; the 8 epilogue warps provide the memory-level parallelism)
   c.grid_x = std::max(1, std::min(p.ntiles, (NSM + c.nsplit - 1) / c.nsplit));
+  if (pair) {
+    if ((p.Npad / 2) % 8) return false;                                  // N / 2 rows per CTA, whole 8-row groups
+    const int pairs = std::max(1, std::min((p.ntiles + 1) / 2, std::min(halo_max_clusters(), NSM / 2) / c.nsplit));
+    c.grid_x = 2 * pairs;
+  }
   return true;
+}
+
+// co-resident CTA pairs of the halo kernel at its shared-memory footprint (74 on a full B200)
+static int halo_max_clusters() {
+  static int v = -1;
+  if (v >= 0) return v;
+  v = 0;
+  if (cudaFuncSetAttribute(tapconv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) { cudaGetLastError(); return v; }
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3(2 * NSM); lc.blockDim = dim3(32 * (9 + HALO_MAXGRP)); lc.dynamicSmemBytes = 220 * 1024;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, tapconv_halo_kernel<true>, &lc) != cudaSuccess) { cudaGetLastError(); return v; }
+  v = std::min(n, NSM / 2);
+  return v;
 }
 
 // Supported AND expected to beat the per-tap kernel: the activations are read once only if the cout slices are few, and
@@ -810,6 +939,12 @@ bool k_tapconv_halo(St st, const TapGeom* classes, int ncls, const float* const*
     r = enc(&maps.b[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)bp[i], dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, wswz,
             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled(B, halo) failed: " + std::to_string((int)r); return false; }
+    if (p.pair) {
+      cuuint32_t boxh[2] = {(cuuint32_t)p.KBw, (cuuint32_t)(p.Npad / 2)};
+      r = enc(&maps.bh[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)bp[i], dims, strides, boxh, ones, CU_TENSOR_MAP_INTERLEAVE_NONE, wswz,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled(B half, halo) failed: " + std::to_string((int)r); return false; }
+    }
   }
   CUtensorMap mapO;
   memset(&mapO, 0, sizeof(mapO));
@@ -826,14 +961,28 @@ bool k_tapconv_halo(St st, const TapGeom* classes, int ncls, const float* const*
   }
   static bool configured = false;
   if (!configured) {
-    if (cudaFuncSetAttribute(tapconv_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
+    if (cudaFuncSetAttribute(tapconv_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+        cudaFuncSetAttribute(tapconv_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) {
       if (err) *err = "cudaFuncSetAttribute(smem, halo) failed";
       return false;
     }
     configured = true;
   }
   dim3 grid((unsigned)c.grid_x, (unsigned)c.nsplit);
-  tapconv_halo_kernel<<<grid, 32 * (9 + p.ngrp), c.smem, st.s>>>(mapA, maps, c.tab, mapO, p, out);
+  if (p.pair) {
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.gridDim = grid; lc.blockDim = dim3(32 * (9 + p.ngrp)); lc.dynamicSmemBytes = c.smem; lc.stream = st.s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = 1;
+    if (cudaLaunchKernelEx(&lc, tapconv_halo_kernel<true>, mapA, maps, c.tab, mapO, c.wl, p, out) != cudaSuccess) {
+      if (err) *err = std::string("halo pair launch failed: ") + cudaGetErrorString(cudaGetLastError());
+      return false;
+    }
+  } else
+    tapconv_halo_kernel<false><<<grid, 32 * (9 + p.ngrp), c.smem, st.s>>>(mapA, maps, c.tab, mapO, c.wl, p, out);
   // HBM-bound by construction (input and output once, weights resident): the roofline work of a launch is its
   // algorithmic bytes = input + output + weights (fp32)
   double wbytes = 0;
