@@ -210,6 +210,11 @@ bool k_tapconv_tc2(St st, const TapGeom* classes, int ncls, const float* const* 
 bool tc3_tapconv_supported(const TapGeom* classes, int ncls, const float* const* bt);
 bool k_tapconv_tc3(St st, const TapGeom* classes, int ncls, const float* const* bt, const float* in, float* out, int act, float negval,
                    std::string* err);
+// wgrad on CTA pairs (kernels_tc2.cu): Cp >= 256, 256 cp x up to 256 cq per MMA
+bool wgrad_tc_pair_supported(const WgradGeom& g);
+size_t wgrad_tc_pair_scratch_bytes(const WgradGeom& g);
+bool k_wgrad_tc_pair(St st, const WgradGeom& g, const float* P, const float* Q, float* grad_master, float* scratch, size_t scratch_bytes,
+                     std::string* err);
 bool tc_wgrad_supported(const WgradGeom& g);
 size_t wgrad_tc_scratch_bytes(const WgradGeom& g);
 bool k_wgrad_tc(St st, const WgradGeom& g, const float* P, const float* Q, float* grad_master, float* scratch, size_t scratch_bytes,

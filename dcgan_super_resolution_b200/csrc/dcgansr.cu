@@ -498,6 +498,7 @@ struct ConvPlan {
     size_t b = wgrad_simt_scratch_bytes(g);
     b = std::max(b, thin_wgrad_scratch_bytes(g));
     if (fast && tc_wgrad_supported(g)) b = std::max(b, wgrad_tc_scratch_bytes(g));
+    if (fast) b = std::max(b, wgrad_tc_pair_scratch_bytes(g));
     if (fast) b = std::max(b, wgrad_halo_scratch_bytes(g));
     return b;
   }
@@ -512,6 +513,13 @@ struct ConvPlan {
       std::string e;
       if (k_wgrad_halo(ctx->st(), g, Pp, Qp, grad_master, scratch, scratch_bytes, &e)) return;
       ctx->err = "tcgen05 halo wgrad: " + e;
+      ctx->tc_failed = true;
+      return;
+    }
+    if (fast && wgrad_tc_pair_supported(g)) {
+      std::string e;
+      if (k_wgrad_tc_pair(ctx->st(), g, Pp, Qp, grad_master, scratch, scratch_bytes, &e)) return;
+      ctx->err = "tcgen05 pair wgrad: " + e;
       ctx->tc_failed = true;
       return;
     }

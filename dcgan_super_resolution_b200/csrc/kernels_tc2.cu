@@ -564,3 +564,318 @@ bool k_tapconv_tc2(St st, const TapGeom* cls, int ncls, const float* const* bt, 
   DSR_LAUNCHED(st, "tapconv_tc2", c.flops, WORK_FLOPS);
   return true;
 }
+
+// ==========================================================================================
+// wgrad on CTA pairs (cta_group::2):  acc[t][cp][cq] = sum_pix P[pix][cp] * Q[shift_t(pix)][cq]
+//
+// The per-tap formulation of kernels_tc.cu:wgrad_tc_kernel (both operands MN-major as the TMA boxes of the NHWC tensors land,
+// one TMEM accumulator per tap of the CTA's tap group, split-K over pixel tiles, partials -> scratch -> k_wgrad_reduce) with
+// M = 256: the pair owns 256 consecutive cp channels (each CTA stages the P tile of its 128) and every shifted Q tile is
+// staged half by each CTA (n_mma / 2 channels).  Per tap and 64-pixel tile a CTA moves 32 KB / TG + n_mma * 128 B instead of
+// 32 KB / TG + n_mma * 256 B, and an N = 256 MMA runs at the full tensor rate (an M = 128, N = 128 one is bound by its A read).
+// ==========================================================================================
+struct WgpParams {
+  int Cp, Cq, ntaps, s;
+  int TW, TH, TB, tiles_x, tiles_y, ntiles, tiles_per_split;
+  int n_mma, atoms_q_half, TG, tmem_cols, tap_groups, q_tiles, mpairs, S;
+  int q_stage_bytes, nq_stage;
+  long long split_stride;
+  short oy[DSR_MAX_TAPS], ox[DSR_MAX_TAPS], py[DSR_MAX_TAPS], px[DSR_MAX_TAPS];
+};
+
+__device__ __forceinline__ uint64_t wgp_desc_mn(uint32_t saddr, uint32_t lbo) {      // MN-major SWIZZLE_128B_BASE32B (see kernels_tc.cu)
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFFu) << 16;
+  d |= (uint64_t)(512u >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+
+#define WGP_KPIX 64
+#define WGP_P_STAGE (4 * WGP_KPIX * 32 * 4)      // 128 channels x 64 pixels x 4 B = 32 KB
+__global__ void __launch_bounds__(TC2_THREADS, 1) wgrad_tc_pair_kernel(const __grid_constant__ CUtensorMap mapP,
+                                                                       const __grid_constant__ CUtensorMap mapQ, const WgpParams p,
+                                                                       float* __restrict__ scratch) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sP = smem;                                        // 2 stages
+  uint8_t* sQ = smem + 2 * WGP_P_STAGE;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sQ + (size_t)p.nq_stage * p.q_stage_bytes);
+  uint64_t* p_full = bars;           // [2]
+  uint64_t* p_empty = bars + 2;      // [2]
+  uint64_t* q_full = bars + 4;       // [8]
+  uint64_t* q_empty = bars + 12;     // [8]
+  uint64_t* tmem_full = bars + 20;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint32_t crank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+  // item = (split, tap group, cp pair, cq tile)
+  int item = blockIdx.x >> 1;
+  const int qtile = item % p.q_tiles; item /= p.q_tiles;
+  const int mpair = item % p.mpairs; item /= p.mpairs;
+  const int tgi = item % p.tap_groups; item /= p.tap_groups;
+  const int split = item;
+  const int t0 = tgi * p.TG;
+  const int tg_n = min(p.TG, p.ntaps - t0);
+  const int m0 = mpair * 256 + (int)crank * 128, q0 = qtile * p.n_mma + (int)crank * (p.n_mma / 2);
+  const int tile_beg = split * p.tiles_per_split;
+  const int tile_end = min(p.ntiles, tile_beg + p.tiles_per_split);
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapP) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapQ) : "memory");
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&p_full[i]), 1); mbar_init(smem_u32(&p_empty[i]), 1); }
+    for (int i = 0; i < p.nq_stage; ++i) { mbar_init(smem_u32(&q_full[i]), 1); mbar_init(smem_u32(&q_empty[i]), 1); }
+    mbar_init(smem_u32(tmem_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)p.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t atom = (uint32_t)(WGP_KPIX * 32 * 4);        // 32 channels x 64 pixels
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int ps = 0, qs = 0;
+      uint32_t pph = 0, qph = 0;
+      for (int tile = tile_beg; tile < tile_end; ++tile) {
+        int tt = tile;
+        const int tx = tt % p.tiles_x; tt /= p.tiles_x;
+        const int ty = tt % p.tiles_y; tt /= p.tiles_y;
+        const int b0 = tt * p.TB, gy0 = ty * p.TH, gx0 = tx * p.TW;
+        mbar_wait(smem_u32(&p_empty[ps]), pph ^ 1u);
+        const uint32_t pf_local = smem_u32(&p_full[ps]);
+        const uint32_t pf = pf_local & 0xFEFFFFFFu;
+        if (crank == 0) mbar_expect_tx(pf_local, 2u * 4u * atom);
+        for (int a = 0; a < 4; ++a)
+          tma_load_4d_2sm(smem_u32(sP + (size_t)ps * WGP_P_STAGE) + a * atom, &mapP, pf, m0 + a * 32, gx0, gy0, b0);
+        if (++ps == 2) { ps = 0; pph ^= 1u; }
+        for (int tg = 0; tg < tg_n; ++tg) {
+          const int t = t0 + tg;
+          mbar_wait(smem_u32(&q_empty[qs]), qph ^ 1u);
+          const uint32_t qf_local = smem_u32(&q_full[qs]);
+          const uint32_t qf = qf_local & 0xFEFFFFFFu;
+          if (crank == 0) mbar_expect_tx(qf_local, 2u * (uint32_t)p.atoms_q_half * atom);
+          const uint32_t dq = smem_u32(sQ + (size_t)qs * p.q_stage_bytes);
+          for (int a = 0; a < p.atoms_q_half; ++a) {
+            if (p.s == 1)
+              tma_load_4d_2sm(dq + a * atom, &mapQ, qf, q0 + a * 32, gx0 + p.ox[t], gy0 + p.oy[t], b0);
+            else
+              tma_load_5d_2sm(dq + a * atom, &mapQ, qf, p.px[t] * p.Cq + q0 + a * 32, gx0 + p.ox[t], p.py[t], gy0 + p.oy[t], b0);
+          }
+          if (++qs == p.nq_stage) { qs = 0; qph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1 && crank == 0) {
+    // D = f32, A = B = tf32, both MN-major (bits 15, 16), N = n_mma, M = 256
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(p.n_mma >> 3) << 17) | ((256u >> 4) << 24);
+    int ps = 0, qs = 0;
+    uint32_t pph = 0, qph = 0;
+    const uint32_t kstep = 8u * 32u * 4u;                     // 8 pixels of a 32-channel atom
+    for (int tile = tile_beg; tile < tile_end; ++tile) {
+      mbar_wait(smem_u32(&p_full[ps]), pph);
+      const uint32_t pa = smem_u32(sP + (size_t)ps * WGP_P_STAGE);
+      for (int tg = 0; tg < tg_n; ++tg) {
+        mbar_wait(smem_u32(&q_full[qs]), qph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t qa = smem_u32(sQ + (size_t)qs * p.q_stage_bytes);
+#pragma unroll
+          for (int k = 0; k < WGP_KPIX / 8; ++k)
+            umma_tf32_2sm(tmem_base + (uint32_t)(tg * p.n_mma), wgp_desc_mn(pa + k * kstep, atom), wgp_desc_mn(qa + k * kstep, atom), idesc,
+                          (tile > tile_beg || k > 0) ? 1u : 0u);
+          umma_commit_2sm(smem_u32(&q_empty[qs]));
+          if (tg == tg_n - 1) {
+            umma_commit_2sm(smem_u32(&p_empty[ps]));
+            if (tile == tile_end - 1) umma_commit_2sm(smem_u32(tmem_full));
+          }
+        }
+        __syncwarp();
+        if (++qs == p.nq_stage) { qs = 0; qph ^= 1u; }
+      }
+      if (++ps == 2) { ps = 0; pph ^= 1u; }
+    }
+  } else if (warp >= 2 && tile_end > tile_beg) {
+    const int q = warp & 3;
+    const int cp = m0 + q * 32 + lane;
+    const int cq0 = qtile * p.n_mma;                          // the accumulator columns are the whole n_mma slice (both CTAs' halves)
+    mbar_wait(smem_u32(tmem_full), 0);
+    tc_fence_after();
+    const int Ntot = p.ntaps * p.Cq;
+    float* drow = scratch + (long long)split * p.split_stride + (long long)cp * Ntot;
+    for (int tg = 0; tg < tg_n; ++tg) {
+      for (int c0 = 0; c0 < p.n_mma; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(tg * p.n_mma + c0), v);
+        tmem_ld_wait();
+        if (cp < p.Cp) {
+          const int cq = cq0 + c0;
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            if (cq + j + 3 < p.Cq) {
+              *reinterpret_cast<float4*>(drow + (t0 + tg) * p.Cq + cq + j) =
+                  make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                if (cq + j + e < p.Cq) drow[(t0 + tg) * p.Cq + cq + j + e] = __uint_as_float(v[j + e]);
+            }
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+static int wgp_max_clusters() {
+  static int v = -1;
+  if (v >= 0) return v;
+  v = 0;
+  if (cudaFuncSetAttribute(wgrad_tc_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess) { cudaGetLastError(); return v; }
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3(2 * NSM); lc.blockDim = dim3(TC2_THREADS); lc.dynamicSmemBytes = 200 * 1024;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, wgrad_tc_pair_kernel, &lc) != cudaSuccess) { cudaGetLastError(); return v; }
+  v = std::min(n, NSM / 2);
+  return v;
+}
+
+struct WgpCfg { WgpParams p; size_t smem; int grid; };
+
+static bool wgp_cfg(const WgradGeom& g, WgpCfg& c) {
+  if (!tc_encode_fn()) return false;
+  const char* e = getenv("DCGANSR_WGRAD_PAIR");
+  const int mode = e ? atoi(e) : 1;        // 0 off, 1 where it pays, 2 wherever it runs
+  if (mode == 0) return false;
+  WgpParams& p = c.p;
+  memset(&p, 0, sizeof(p));
+  if (g.Cp % 32 || g.Cq % 32 || g.Cp < 256 || g.Cq < 64 || g.ntaps < 1 || g.ntaps > DSR_MAX_TAPS) return false;
+  if (g.s != 1 && g.s != 2) return false;
+  if (g.s == 2 && (g.Hq % 2 || g.Wq % 2)) return false;
+  const int maxcl = wgp_max_clusters();
+  if (maxcl < 32) return false;
+  p.Cp = g.Cp; p.Cq = g.Cq; p.ntaps = g.ntaps; p.s = g.s;
+  p.TW = std::min(pow2_ge2(g.Wp), WGP_KPIX);
+  p.TH = std::min(pow2_ge2(g.Hp), WGP_KPIX / p.TW);
+  p.TB = WGP_KPIX / (p.TW * p.TH);
+  p.tiles_x = (g.Wp + p.TW - 1) / p.TW;
+  p.tiles_y = (g.Hp + p.TH - 1) / p.TH;
+  p.ntiles = ((g.N + p.TB - 1) / p.TB) * p.tiles_y * p.tiles_x;
+  // cq slice per item: 256 columns when the layer has them (an N = 256 pair MMA runs at the full tensor rate), else 128 / 64
+  p.n_mma = g.Cq >= 256 ? 256 : (g.Cq >= 128 ? 128 : 64);
+  p.q_tiles = (g.Cq + p.n_mma - 1) / p.n_mma;
+  p.atoms_q_half = p.n_mma / 64;
+  p.TG = std::max(1, std::min(g.ntaps, 512 / p.n_mma));
+  p.tap_groups = (g.ntaps + p.TG - 1) / p.TG;
+  p.mpairs = (g.Cp + 255) / 256;
+  p.tmem_cols = std::max(32, pow2_ge2(p.TG * p.n_mma));
+  p.q_stage_bytes = p.atoms_q_half * WGP_KPIX * 32 * 4;
+  p.nq_stage = std::max(2, std::min(8, (200 * 1024 - 2 * WGP_P_STAGE) / p.q_stage_bytes));
+  // pixel splits: every item accumulates over its own range of pixel tiles.  The items run in waves of `maxcl` pairs, so S is
+  // chosen to fill whole waves (19 splits of 4 tap groups = 76 items on 74 pairs would run two half-empty waves: measured 0.91x)
+  const int other = p.tap_groups * p.mpairs * p.q_tiles;
+  int best_s = 1;
+  double best_eff = 0.0;
+  for (int S = 1; S <= p.ntiles && S * other <= 4 * maxcl; ++S) {
+    const int tps = (p.ntiles + S - 1) / S;
+    const int s_eff = (p.ntiles + tps - 1) / tps;              // splits that actually hold tiles
+    const long long items = (long long)s_eff * other;
+    const long long waves = (items + maxcl - 1) / maxcl;
+    const double eff = (double)items / (double)(waves * maxcl);
+    if (eff > best_eff + 0.03) { best_eff = eff; best_s = S; }   // a later (larger) S must be clearly better: more partials to reduce
+  }
+  p.tiles_per_split = (p.ntiles + best_s - 1) / best_s;
+  p.S = (p.ntiles + p.tiles_per_split - 1) / p.tiles_per_split;
+  p.split_stride = (long long)g.Cp * g.ntaps * g.Cq;
+  for (int t = 0; t < g.ntaps; ++t) {
+    if (g.s == 1) { p.oy[t] = (short)g.dy[t]; p.ox[t] = (short)g.dx[t]; }
+    else {
+      const int fy = floordiv2_2(g.dy[t]), fx = floordiv2_2(g.dx[t]);
+      p.oy[t] = (short)fy; p.ox[t] = (short)fx; p.py[t] = (short)(g.dy[t] - 2 * fy); p.px[t] = (short)(g.dx[t] - 2 * fx);
+    }
+  }
+  c.grid = 2 * p.S * other;
+  c.smem = 1024 + 2 * WGP_P_STAGE + (size_t)p.nq_stage * p.q_stage_bytes + 24 * sizeof(uint64_t);
+  // measured (scripts/exp/wgrad_pair_sweep.py): 1.27 - 1.63x over wgrad_tc from 256 pixel tiles up (C1b FC 256->128 566 -> 352 us,
+  // C5 FC 512->256 1811 -> 1111 us = 990 TFLOP/s), 0.91 - 0.95x on the small discriminator layers at batch 128 (128 tiles)
+  if (mode == 1 && (p.ntiles < 256 || p.tiles_per_split < 4)) return false;
+  return c.smem <= 227 * 1024;
+}
+
+bool wgrad_tc_pair_supported(const WgradGeom& g) { WgpCfg c; return wgp_cfg(g, c); }
+size_t wgrad_tc_pair_scratch_bytes(const WgradGeom& g) {
+  WgpCfg c;
+  if (!wgp_cfg(g, c)) return 0;
+  return (size_t)c.p.S * g.Cp * g.ntaps * g.Cq * sizeof(float);
+}
+
+bool k_wgrad_tc_pair(St st, const WgradGeom& g, const float* P, const float* Q, float* grad_master, float* scratch, size_t scratch_bytes,
+                     std::string* err) {
+  WgpCfg c;
+  if (!wgp_cfg(g, c)) { if (err) *err = "wgrad geometry not taken by the pair kernel"; return false; }
+  const WgpParams& p = c.p;
+  if ((size_t)p.S * g.Cp * g.ntaps * g.Cq * sizeof(float) > scratch_bytes) { if (err) *err = "wgrad scratch too small"; return false; }
+  CUtensorMap mapP, mapQ;
+  const cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  CUresult r;
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)g.Cp, (cuuint64_t)g.Wp, (cuuint64_t)g.Hp, (cuuint64_t)g.N};
+    cuuint64_t strides[3] = {(cuuint64_t)g.Cp * 4, (cuuint64_t)g.Wp * g.Cp * 4, (cuuint64_t)g.Hp * g.Wp * g.Cp * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TB};
+    r = tc_encode_fn()(&mapP, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)P, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled(P) failed: " + std::to_string((int)r); return false; }
+  if (g.s == 1) {
+    cuuint64_t dims[4] = {(cuuint64_t)g.Cq, (cuuint64_t)g.Wq, (cuuint64_t)g.Hq, (cuuint64_t)g.N};
+    cuuint64_t strides[3] = {(cuuint64_t)g.Cq * 4, (cuuint64_t)g.Wq * g.Cq * 4, (cuuint64_t)g.Hq * g.Wq * g.Cq * 4};
+    cuuint32_t box[4] = {32, (cuuint32_t)p.TW, (cuuint32_t)p.TH, (cuuint32_t)p.TB};
+    r = tc_encode_fn()(&mapQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)Q, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  } else {
+    cuuint64_t dims[5] = {(cuuint64_t)2 * g.Cq, (cuuint64_t)g.Wq / 2, 2, (cuuint64_t)g.Hq / 2, (cuuint64_t)g.N};
+    cuuint64_t strides[4] = {(cuuint64_t)2 * g.Cq * 4, (cuuint64_t)g.Wq * g.Cq * 4, (cuuint64_t)2 * g.Wq * g.Cq * 4,
+                             (cuuint64_t)g.Hq * g.Wq * g.Cq * 4};
+    cuuint32_t box[5] = {32, (cuuint32_t)p.TW, 1, (cuuint32_t)p.TH, (cuuint32_t)p.TB};
+    r = tc_encode_fn()(&mapQ, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)Q, dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  }
+  if (r != CUDA_SUCCESS) { if (err) *err = "cuTensorMapEncodeTiled(Q) failed: " + std::to_string((int)r); return false; }
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.gridDim = dim3((unsigned)c.grid); lc.blockDim = dim3(TC2_THREADS); lc.dynamicSmemBytes = c.smem; lc.stream = st.s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  lc.attrs = at; lc.numAttrs = 1;
+  if (cudaLaunchKernelEx(&lc, wgrad_tc_pair_kernel, mapP, mapQ, p, scratch) != cudaSuccess) {
+    if (err) *err = std::string("wgrad pair launch failed: ") + cudaGetErrorString(cudaGetLastError());
+    return false;
+  }
+  DSR_LAUNCHED(st, "wgrad_tc_pair", 2.0 * g.N * g.Hp * g.Wp * g.Cp * g.Cq * g.ntaps, WORK_FLOPS);
+  k_wgrad_reduce(st, scratch, p.S, g.Cp, g.Cq, g.ntaps, grad_master);
+  return true;
+}

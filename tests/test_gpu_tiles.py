@@ -188,3 +188,37 @@ def test_halo_pair_kernel(ctx_fast, shape, monkeypatch):
     assert rel_err(dx, ref) <= FAST_TOL, ("dgrad", rel_err(dx, ref))
     for i in range(n):
         assert rel_err(dx[i], ref[i]) <= 2 * FAST_TOL, ("dgrad image", i)
+
+
+# accGradParameters on CTA pairs (kernels_tc2.cu:wgrad_tc_pair_kernel): 256 cp per MMA, cq slices of 64 / 128 / 256, tap groups,
+# stride-1 and stride-2 shifted tensors, several pixel splits
+WGRAD_PAIR_SHAPES = [
+    ("conv", 12, 128, 32, 32, 256, 4, 2, 1),    # D layer 3 (train.lua:127): P = dy (256), Q = x (128), 16 taps in groups of 4
+    ("conv", 10, 256, 16, 16, 512, 4, 2, 1),    # D layer 4: two cp pairs, 256-column cq slice, groups of 2 taps
+    ("full", 6, 256, 24, 24, 128, 4, 2, 1),     # C1b G layer 2 shape class (FC 256->128): P = x (256), Q = dy (128) at twice the size
+    ("conv", 9, 128, 28, 28, 256, 3, 1, 0),     # patch-D layer 3 (train-gray-patch.lua:100): 9 taps, stride 1
+    ("full", 5, 384, 16, 16, 64, 4, 2, 1),      # cp not a multiple of 256 (second pair half empty), 64-column cq slice
+]
+
+
+@pytest.mark.parametrize("shape", WGRAD_PAIR_SHAPES)
+def test_wgrad_pair_kernel(ctx_fast, shape, monkeypatch):
+    monkeypatch.setenv("DCGANSR_WGRAD_PAIR", "2")
+    monkeypatch.setenv("DCGANSR_NO_WGRAD_HALO", "1")
+    kind, n, cin, h, w, cout, k, s, p = shape
+    full = kind == "full"
+    r = rng(hash(shape[1:]) % 2**31)
+    x = r.standard_normal((n, cin, h, w)).astype(np.float32)
+    wshape = (cin, cout, k, k) if full else (cout, cin, k, k)
+    ho, wo = ((h - 1) * s - 2 * p + k, (w - 1) * s - 2 * p + k) if full else ((h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1)
+    dy = r.standard_normal((n, cout, ho, wo)).astype(np.float32)
+    lib, hc = ctx_fast.lib, ctx_fast.h
+    pre = "dcgansr_fullconv2d_" if full else "dcgansr_conv2d_"
+    dw = np.empty(wshape, np.float32)
+    ctx_fast.profile_begin()
+    L.check(getattr(lib, pre + "wgrad")(hc, ptr(x), ptr(dy), ptr(dw), n, cin, h, w, cout, k, s, p), hc)
+    names = [k_["name"] for k_ in ctx_fast.profile_end()]
+    assert "wgrad_tc_pair" in names and "wgrad_tc" not in names, names
+    X, DY = t64(x), t64(dy)
+    ref = (ops.fullconv2d_wgrad(X, DY, wshape, s, p) if full else ops.conv2d_wgrad(X, DY, wshape, s, p)).numpy()
+    assert rel_err(dw, ref) <= FAST_TOL, ("wgrad", rel_err(dw, ref))
