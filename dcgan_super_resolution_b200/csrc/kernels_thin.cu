@@ -83,9 +83,9 @@ static bool thin_wg_cfg(const WgradGeom& g, ThinWg& w) {
   w.seg = w.Wa; w.nseg = 1;
   // (giving the slots of one warp segments of the SAME row, for L1 locality of the thin loads, was slower still: the per-item
   //  setup of up to 16 pair pointers is paid per segment)
-  // block reduction buffer: (pairs per group <= 16 / Ct ... 16) * Ct * V float4 <= 40 KB
+  // block reduction buffer: (pairs per group <= 16 / Ct ... 16) * Ct * V float4 <= 48 KB (the static shared-memory limit)
   const int grp = w.Ct == 1 ? 16 : (w.Ct == 2 ? 8 : 4);
-  if ((size_t)grp * w.Ct * w.V * 4 * sizeof(float) > 40 * 1024) return false;
+  if ((size_t)grp * w.Ct * w.V * 4 * sizeof(float) > 48 * 1024) return false;      // (FC 3->1024 of the C5 generator: exactly 48 KB)
   return true;
 }
 
@@ -114,7 +114,7 @@ size_t thin_wgrad_scratch_bytes(const WgradGeom& g) {
 template <int CT, int MAXP, int UNR>
 __global__ void __launch_bounds__(256, THIN_WG_MINB(CT, MAXP, UNR)) thin_wgrad_kernel(const ThinWg w, const float* __restrict__ fat,
                                                           const float* __restrict__ thin, float* __restrict__ scratch) {
-  __shared__ __align__(16) float4 red4[MAXP * CT * 256 > 2560 ? 2560 : MAXP * CT * 256];   // <= 40 KB: [pair][ct][V lanes]
+  __shared__ __align__(16) float4 red4[MAXP * CT * 256 > 3072 ? 3072 : MAXP * CT * 256];   // <= 48 KB: [pair][ct][V lanes]
   const int cls = blockIdx.y;
   const int j0 = blockIdx.z * MAXP;                       // this block's group of (tap, thin pixel) pairs
   const int np = min(MAXP, w.npairs[cls] - j0);

@@ -73,6 +73,7 @@ FULL_SHAPES = [
     (2, 64, 16, 16, 32, 4, 2, 1),      # C2 G layer 3, spatial reduced
     (2, 8, 5, 5, 4, 3, 1, 1),          # stride 1 full conv
     (1, 4, 4, 4, 5, 5, 2, 2),          # k5 s2 (uneven taps per class), Co = 5
+    (2, 3, 6, 6, 1024, 4, 2, 1),       # C5 G layer 1 (FC 3->1024): the thin wgrad's block reduction at its 48 KB limit
 ]
 
 
