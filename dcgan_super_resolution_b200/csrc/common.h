@@ -182,7 +182,9 @@ void k_pack_taps_tc(St st, const float* master, float* bp, int ntaps, const int*
 bool k_tapconv_tc(St st, const TapGeom& g, const float* in, const float* bp, float* out, int act, float negval,
                   std::string* err);
 // ---- kernels_halo.cu : weights-resident halo-tile kernel (all sub-pixel classes of a module in one launch) ----
-bool halo_tapconv_supported(const TapGeom* classes, int ncls);
+// allow_pair = false: only the single-CTA form counts (per-class launches of a class group are not worth a CTA pair: the
+// halo-tile pair kernel of kernels_tc3.cu runs those layers faster -- C1b FC 256->128 forward 0.43 ms against 4 x 0.17 ms)
+bool halo_tapconv_supported(const TapGeom* classes, int ncls, bool allow_pair = true);
 // stats != nullptr (and halo_stats_rows(...) > 0): the epilogue also writes per-CTA BatchNorm partial sums of the output,
 // rows [stats_row0, stats_row0 + halo_stats_rows) of a [rows][2*Co] double matrix (sum y | sum y^2)
 int halo_stats_rows(const TapGeom* classes, int ncls);

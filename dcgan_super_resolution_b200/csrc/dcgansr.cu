@@ -291,7 +291,7 @@ struct ConvPlan {
     for (int i = 0; i < n; ++i) {
       if (gs[i].Hg <= 0 || gs[i].Wg <= 0) continue;
       if ((int64_t)gs[i].Hg * gs[i].Wg < 16 * 128 && !getenv("DCGANSR_HALO_ALL")) return 0;
-      if (!halo_tapconv_supported(gs + i, 1)) return 0;
+      if (!halo_tapconv_supported(gs + i, 1, false)) return 0;
     }
     return 1;
   }

@@ -882,9 +882,10 @@ static int halo_max_clusters() {
 
 // Supported AND expected to beat the per-tap kernel: the activations are read once only if the cout slices are few, and
 // TMA / MMA overlap needs the double-buffered halo tile.  DCGANSR_HALO_ALL=1 (tests) takes every supported geometry.
-bool halo_tapconv_supported(const TapGeom* classes, int ncls) {
+bool halo_tapconv_supported(const TapGeom* classes, int ncls, bool allow_pair) {
   HaloCfg c;
   if (!halo_cfg(classes, ncls, c)) return false;
+  if (!allow_pair && c.p.pair) return false;
   if (getenv("DCGANSR_HALO_ALL")) return true;
   // few cout slices (the input is read once per slice), and either the full two-tile ring or a spatially large layer (a short
   // ring leans on the L2 prefetch, which needs many tiles per CTA to pay off)
