@@ -475,6 +475,9 @@ def dp_check(env):
         b = run(env.world, prec, False, no_overlap=True)
         c = run(env.world, prec, False, graph=True)
         res[f"bucket_bit_identical_{prec}"] = bool(np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]))
+        # (bit identity holds at N = 2, where a sum of two terms has one order; from N = 4 up NCCL may pick another algorithm --
+        #  another summation order -- for the bucket-sized messages than for the whole gradient vector: report the size of it)
+        res[f"bucket_max_rel_diff_{prec}"] = float(max(np.max(np.abs(a[0] - b[0])) / np.max(np.abs(b[0])), np.max(np.abs(a[1] - b[1])) / np.max(np.abs(b[1]))))
         res[f"graph_replay_identical_{prec}"] = bool(np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1]))
     a = run(env.world, "strict", True)
     if env.rank == 0:
