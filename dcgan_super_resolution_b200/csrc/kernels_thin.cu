@@ -31,6 +31,7 @@ struct ThinWg {
   int V, PS;                  // float4 lanes per pixel (pow2 >= Cf/4), pixel slots per block
   int seg, nseg;              // a work item = `seg` class pixels of one fat row (rows are split when there are few of them)
   int T, Cp, Cq, fat_is_p;
+  int nzg;                    // pair groups per class (set by the launcher)
   int npairs[THIN_MAXCLS];
   short cy[THIN_MAXCLS], cx[THIN_MAXCLS];
   short oy[THIN_MAXCLS][THIN_MAXP], ox[THIN_MAXCLS][THIN_MAXP], tap[THIN_MAXCLS][THIN_MAXP];
@@ -115,8 +116,13 @@ template <int CT, int MAXP, int UNR>
 __global__ void __launch_bounds__(256, THIN_WG_MINB(CT, MAXP, UNR)) thin_wgrad_kernel(const ThinWg w, const float* __restrict__ fat,
                                                           const float* __restrict__ thin, float* __restrict__ scratch) {
   __shared__ __align__(16) float4 red4[MAXP * CT * 256 > 3072 ? 3072 : MAXP * CT * 256];   // <= 48 KB: [pair][ct][V lanes]
+  // blockIdx.x = block * nzg + pair group: the groups of one block index walk the SAME fat rows, so they are neighbours in the
+  // launch order and run at the same time -- the fat tensor comes from HBM once and from L2 for the other groups (as blockIdx.z
+  // the groups ran one after the other: D conv 3->64 wgrad at C3b read its 268 MB four times, 412 us)
   const int cls = blockIdx.y;
-  const int j0 = blockIdx.z * MAXP;                       // this block's group of (tap, thin pixel) pairs
+  const int nzg = w.nzg;                                   // pair groups folded into blockIdx.x
+  const int bx = blockIdx.x / nzg, nbx = gridDim.x / nzg;
+  const int j0 = (int)(blockIdx.x % nzg) * MAXP;           // this block's group of (tap, thin pixel) pairs
   const int np = min(MAXP, w.npairs[cls] - j0);
   if (np <= 0) return;
   const int lane4 = threadIdx.x % w.V;            // float4 lane along the fat channels
@@ -134,7 +140,7 @@ __global__ void __launch_bounds__(256, THIN_WG_MINB(CT, MAXP, UNR)) thin_wgrad_k
   const int items = w.N * w.Ha * w.nseg;          // < 2^31 (checked by thin_wg_cfg): 32-bit index arithmetic per item
   auto run = [&](auto tsc) {
   constexpr int TS = decltype(tsc)::value;        // thin pixels per class pixel along x (1 or 2), compile time: immediate offsets
-  for (int item = blockIdx.x * w.PS + slot; item < items; item += gridDim.x * w.PS) {
+  for (int item = bx * w.PS + slot; item < items; item += nbx * w.PS) {
     const int row = item / w.nseg;
     const int bbeg = (item - row * w.nseg) * w.seg, bend = min(nb, bbeg + w.seg);
     const int n = row / w.Ha, a = row - n * w.Ha;
@@ -241,7 +247,7 @@ __global__ void __launch_bounds__(256, THIN_WG_MINB(CT, MAXP, UNR)) thin_wgrad_k
   }
   // scratch[block][cp][t*Cq + cq]
   const float* red = reinterpret_cast<const float*>(red4);
-  float* dst = scratch + (int64_t)blockIdx.x * w.Cp * w.T * w.Cq;
+  float* dst = scratch + (int64_t)bx * w.Cp * w.T * w.Cq;
   const int total = np * CT * w.Cf;
   for (int i = threadIdx.x; i < total; i += 256) {
     const int cf = i % w.Cf;
@@ -264,10 +270,11 @@ bool k_wgrad_thin(St st, const WgradGeom& g, const float* P, const float* Q, flo
   const float* thin = w.fat_is_p ? Q : P;
   int maxp = 0;
   for (int c = 0; c < w.ncls; ++c) maxp = std::max(maxp, w.npairs[c]);
-  // accumulators: MAXP * CT float4 per thread, kept <= 16 (64 registers); more pairs -> pair groups on blockIdx.z
+  // accumulators: MAXP * CT float4 per thread, kept <= 16 (64 registers); more pairs -> pair groups folded into blockIdx.x
 #define THIN_LAUNCH(CT, MP, UNR)                                                    \
   do {                                                                              \
-    dim3 grid(nb, w.ncls, (maxp + (MP) - 1) / (MP));                                \
+    w.nzg = (maxp + (MP) - 1) / (MP);                                               \
+    dim3 grid(nb * w.nzg, w.ncls, 1);                                               \
     thin_wgrad_kernel<CT, MP, UNR><<<grid, 256, 0, st.s>>>(w, fat, thin, scratch);  \
   } while (0)
   switch (w.Ct) {
