@@ -105,14 +105,24 @@ bool thin_wgrad_supported(const WgradGeom& g) { ThinWg w; return thin_wg_cfg(g, 
 size_t thin_wgrad_scratch_bytes(const WgradGeom& g) {
   ThinWg w;
   if (!thin_wg_cfg(g, w)) return 0;
-  return (size_t)thin_wg_blocks(w) * g.Cp * g.Cq * g.ntaps * sizeof(float);
+  // + the 3-channel thin tensor padded to 4 channels (one 16-byte load per thin pixel instead of three 4-byte ones)
+  const size_t part = ((size_t)thin_wg_blocks(w) * g.Cp * g.Cq * g.ntaps * sizeof(float) + 255) / 256 * 256;
+  return part + (w.Ct == 3 ? (size_t)w.N * w.Ht * w.Wt * 4 * sizeof(float) : 0);
+}
+
+// 3 -> 4 channel padding of a small NHWC tensor (the RGB side of a thin wgrad)
+__global__ void __launch_bounds__(256) pad34_kernel(const float* __restrict__ in, float4* __restrict__ out, int64_t npix) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < npix; i += (int64_t)gridDim.x * 256)
+    out[i] = make_float4(__ldg(in + 3 * i), __ldg(in + 3 * i + 1), __ldg(in + 3 * i + 2), 0.f);
 }
 
 // 3 resident blocks per SM for the 4-accumulator variant (80 registers, no spills): occupancy is what hides the HBM latency
 // of the fat-tensor stream; the bigger variants would spill under that cap.
 #define THIN_WG_MINB(CT, MAXP, UNR) ((CT) * (MAXP) <= 4 ? ((UNR) <= 4 ? 3 : 2) : ((CT) * (MAXP) <= 12 ? 2 : 1))
 // UNR = fat pixels loaded per thread before they are used
-template <int CT, int MAXP, int UNR>
+// CTS = floats between thin pixels in memory: CT, or 4 for the padded 3-channel tensor (vector loads: the kernel is bound by the
+// L1's sector rate -- 82 % l1tex throughput on C 12->3 wgrad -- and the three 4-byte loads per thin pixel were 86 % of its sectors)
+template <int CT, int MAXP, int UNR, int CTS>
 __global__ void __launch_bounds__(256, THIN_WG_MINB(CT, MAXP, UNR)) thin_wgrad_kernel(const ThinWg w, const float* __restrict__ fat,
                                                           const float* __restrict__ thin, float* __restrict__ scratch) {
   __shared__ __align__(16) float4 red4[MAXP * CT * 256 > 3072 ? 3072 : MAXP * CT * 256];   // <= 48 KB: [pair][ct][V lanes]
@@ -161,7 +171,7 @@ __global__ void __launch_bounds__(256, THIN_WG_MINB(CT, MAXP, UNR)) thin_wgrad_k
         const int ty = a * w.ts + w.oy[cls][j0 + j];
         tx0[j] = w.ox[cls][j0 + j];
         if (ty >= 0 && ty < w.Ht) {
-          trow[j] = thin + ((int64_t)(n * w.Ht + ty) * w.Wt) * CT;
+          trow[j] = thin + ((int64_t)(n * w.Ht + ty) * w.Wt) * CTS;
           bi0 = max(bi0, tx0[j] < 0 ? (-tx0[j] + TS - 1) / TS : 0);
           bi1 = min(bi1, w.Wt - 1 - tx0[j] >= 0 ? (w.Wt - 1 - tx0[j]) / TS + 1 : 0);
         }
@@ -175,12 +185,20 @@ __global__ void __launch_bounds__(256, THIN_WG_MINB(CT, MAXP, UNR)) thin_wgrad_k
 #pragma unroll
         for (int j = 0; j < MAXP; ++j) {
           if (j < np && trow[j]) {
-            const float* tp = trow[j] + (b0 * TS + tx0[j]) * CT;
+            const float* tp = trow[j] + (b0 * TS + tx0[j]) * CTS;
 #pragma unroll
             for (int u = 0; u < UNR; ++u) {
+              float tvv[4];
+              if (CTS == 4) {
+                const float4 t4 = __ldg(reinterpret_cast<const float4*>(tp + u * TS * 4));
+                tvv[0] = t4.x; tvv[1] = t4.y; tvv[2] = t4.z; tvv[3] = t4.w;
+              } else {
+#pragma unroll
+                for (int c = 0; c < CT; ++c) tvv[c] = __ldg(tp + u * TS * CT + c);
+              }
 #pragma unroll
               for (int c = 0; c < CT; ++c) {
-                const float tv = __ldg(tp + u * TS * CT + c);
+                const float tv = tvv[c];
                 acc[j][c].x = fmaf(tv, f[u].x, acc[j][c].x); acc[j][c].y = fmaf(tv, f[u].y, acc[j][c].y);
                 acc[j][c].z = fmaf(tv, f[u].z, acc[j][c].z); acc[j][c].w = fmaf(tv, f[u].w, acc[j][c].w);
               }
@@ -201,7 +219,7 @@ __global__ void __launch_bounds__(256, THIN_WG_MINB(CT, MAXP, UNR)) thin_wgrad_k
             if (tx >= 0 && tx < w.Wt) {
 #pragma unroll
               for (int c = 0; c < CT; ++c) {
-                const float tv = __ldg(trow[j] + tx * CT + c);
+                const float tv = __ldg(trow[j] + tx * CTS + c);
                 acc[j][c].x = fmaf(tv, f[u].x, acc[j][c].x); acc[j][c].y = fmaf(tv, f[u].y, acc[j][c].y);
                 acc[j][c].z = fmaf(tv, f[u].z, acc[j][c].z); acc[j][c].w = fmaf(tv, f[u].w, acc[j][c].w);
               }
@@ -265,9 +283,20 @@ bool k_wgrad_thin(St st, const WgradGeom& g, const float* P, const float* Q, flo
   ThinWg w;
   if (!thin_wg_cfg(g, w)) return false;
   const int nb = thin_wg_blocks(w);
-  if ((size_t)nb * g.Cp * g.Cq * g.ntaps * sizeof(float) > scratch_bytes) return false;
+  const size_t part = ((size_t)nb * g.Cp * g.Cq * g.ntaps * sizeof(float) + 255) / 256 * 256;
+  const char* pe = getenv("DCGANSR_THIN_PAD34");
+  // measured in one process (scripts/exp/thin_ab.py): C 12->3 wgrad 460 -> 225 us, FC 3->96 wgrad 303 -> 299 us (fat = the shifted
+  // tensor), but D conv 3->64 wgrad 382 -> 439 us (fat = the grid tensor, 16 pairs in 4 groups): padded only in the first form
+  const size_t padb = (w.Ct == 3 && !w.fat_is_p && !(pe && atoi(pe) == 0)) ? (size_t)w.N * w.Ht * w.Wt * 4 * sizeof(float) : 0;
+  if (part + padb > scratch_bytes) return false;
   const float* fat = w.fat_is_p ? P : Q;
   const float* thin = w.fat_is_p ? Q : P;
+  if (padb) {
+    float4* tp4 = reinterpret_cast<float4*>(reinterpret_cast<char*>(scratch) + part);
+    const int64_t npix = (int64_t)w.N * w.Ht * w.Wt;
+    pad34_kernel<<<(unsigned)std::min<int64_t>((npix + 255) / 256, NSM * 8), 256, 0, st.s>>>(thin, tp4, npix);
+    thin = reinterpret_cast<const float*>(tp4);
+  }
   int maxp = 0;
   for (int c = 0; c < w.ncls; ++c) maxp = std::max(maxp, w.npairs[c]);
   // accumulators: MAXP * CT float4 per thread, kept <= 16 (64 registers); more pairs -> pair groups folded into blockIdx.x
@@ -275,7 +304,8 @@ bool k_wgrad_thin(St st, const WgradGeom& g, const float* P, const float* Q, flo
   do {                                                                              \
     w.nzg = (maxp + (MP) - 1) / (MP);                                               \
     dim3 grid(nb * w.nzg, w.ncls, 1);                                               \
-    thin_wgrad_kernel<CT, MP, UNR><<<grid, 256, 0, st.s>>>(w, fat, thin, scratch);  \
+    if (padb) thin_wgrad_kernel<CT, MP, UNR, 4><<<grid, 256, 0, st.s>>>(w, fat, thin, scratch);  \
+    else thin_wgrad_kernel<CT, MP, UNR, CT><<<grid, 256, 0, st.s>>>(w, fat, thin, scratch);      \
   } while (0)
   switch (w.Ct) {
     case 1: THIN_LAUNCH(1, 4, 4); break;        // (deeper load batches, UNR 8 / 16, measured on the 16-channel layer: no change)
@@ -433,7 +463,7 @@ __global__ void __launch_bounds__(256) thin_in_kernel(const ThinIn p, const floa
 // lane, where thin_in_kernel spends one 512-byte shared-memory read per 4 FMAs per lane (it is shared-memory bound at CI = 3:
 // D conv 3->64 615 us for 318 MB at C3b).  Lanes are consecutive pixels of a row: coalesced 12 B-strided input reads through L1,
 // 4*CH-byte output segments.
-template <int CI, int CH>
+template <int CI, int CH, int PX>
 __global__ void __launch_bounds__(256) thin_in_px_kernel(const ThinIn p, const float* __restrict__ in, float* __restrict__ out) {
   extern __shared__ __align__(16) float sw[];                  // [t][ci][CH] of this (class, cout chunk)
   const int nchunk = p.Co / CH;
@@ -444,36 +474,54 @@ __global__ void __launch_bounds__(256) thin_in_px_kernel(const ThinIn p, const f
     sw[i] = c.wp[(int64_t)tc * p.Co + chunk * CH + j];
   }
   __syncthreads();
-  const int64_t npix = (int64_t)p.N * c.Hg * c.Wg;
+  // PX = 2: a thread owns two horizontally adjacent output pixels (every broadcast weight read feeds 2 x 4 FMAs); the class
+  // grid's row is walked in pixel pairs (Wg even, checked by the launcher)
+  const int Wp = c.Wg / PX;
+  const int64_t npix = (int64_t)p.N * c.Hg * Wp;
   auto run = [&](auto actc) {
   constexpr int A = decltype(actc)::value;
   for (int64_t pix = (int64_t)blockIdx.x * 256 + threadIdx.x; pix < npix; pix += (int64_t)gridDim.x * 256) {
     int64_t q = pix;
-    const int gx = (int)(q % c.Wg); q /= c.Wg;
+    const int gx = (int)(q % Wp) * PX; q /= Wp;
     const int gy = (int)(q % c.Hg);
     const int n = (int)(q / c.Hg);
-    float4 acc[CH / 4];
+    float4 acc[PX][CH / 4];
 #pragma unroll
-    for (int j = 0; j < CH / 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u = 0; u < PX; ++u)
+#pragma unroll
+      for (int j = 0; j < CH / 4; ++j) acc[u][j] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int t = 0; t < c.ntaps; ++t) {
-      const int iy = gy * p.si + c.dy[t], ix = gx * p.si + c.dx[t];
-      if (iy < 0 || iy >= p.Hi || ix < 0 || ix >= p.Wi) continue;
-      const float* ip = in + ((int64_t)(n * p.Hi + iy) * p.Wi + ix) * CI;
+      const int iy = gy * p.si + c.dy[t];
+      if (iy < 0 || iy >= p.Hi) continue;
+      const float* irow = in + ((int64_t)(n * p.Hi + iy) * p.Wi) * CI;
       const float4* w = reinterpret_cast<const float4*>(sw + t * CI * CH);
+      float x[PX][CI];
+#pragma unroll
+      for (int u = 0; u < PX; ++u) {
+        const int ix = (gx + u) * p.si + c.dx[t];
+        const bool ok = ix >= 0 && ix < p.Wi;
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci) x[u][ci] = ok ? __ldg(irow + ix * CI + ci) : 0.f;
+      }
 #pragma unroll
       for (int ci = 0; ci < CI; ++ci) {
-        const float x = __ldg(ip + ci);
 #pragma unroll
         for (int j = 0; j < CH / 4; ++j) {
           const float4 wv = w[ci * (CH / 4) + j];
-          acc[j].x = fmaf(x, wv.x, acc[j].x); acc[j].y = fmaf(x, wv.y, acc[j].y);
-          acc[j].z = fmaf(x, wv.z, acc[j].z); acc[j].w = fmaf(x, wv.w, acc[j].w);
+#pragma unroll
+          for (int u = 0; u < PX; ++u) {
+            acc[u][j].x = fmaf(x[u][ci], wv.x, acc[u][j].x); acc[u][j].y = fmaf(x[u][ci], wv.y, acc[u][j].y);
+            acc[u][j].z = fmaf(x[u][ci], wv.z, acc[u][j].z); acc[u][j].w = fmaf(x[u][ci], wv.w, acc[u][j].w);
+          }
         }
       }
     }
-    float* o = out + ((int64_t)(n * p.Ho + gy * p.so + c.oy0) * p.Wo + gx * p.so + c.ox0) * p.Co + chunk * CH;
 #pragma unroll
-    for (int j = 0; j < CH / 4; ++j) *reinterpret_cast<float4*>(o + 4 * j) = thin_act4<A>(acc[j], p.act, p.neg);
+    for (int u = 0; u < PX; ++u) {
+      float* o = out + ((int64_t)(n * p.Ho + gy * p.so + c.oy0) * p.Wo + (gx + u) * p.so + c.ox0) * p.Co + chunk * CH;
+#pragma unroll
+      for (int j = 0; j < CH / 4; ++j) *reinterpret_cast<float4*>(o + 4 * j) = thin_act4<A>(acc[u][j], p.act, p.neg);
+    }
   }
   };
   if (p.act == ACT_NONE) run(ActC<ACT_NONE>{});
@@ -534,9 +582,21 @@ bool k_tapconv_thin_in(St st, const TapGeom* cls, int ncls, const float* const* 
       int64_t maxpix = 0;
       int maxt2 = 1;
       for (int i = 0; i < ncls; ++i) { maxpix = std::max<int64_t>(maxpix, (int64_t)g.N * cls[i].Hg * cls[i].Wg); maxt2 = std::max(maxt2, cls[i].ntaps); }
-      dim3 grid2((unsigned)std::min<int64_t>((maxpix + 255) / 256, NSM * 8), (unsigned)(ncls * (g.Co / CH)));
+      // two pixels per thread for the stride-2 gathers when every class grid has an even width (measured: D conv 3->64 forward
+      // 323 -> 300 us, D conv 1->64 29 -> 25 us; not for the stride-1 classes: C 12->3 dgrad 309 -> 407 us).  Also measured and
+      // dropped: the cout chunks of a pixel on consecutive threads instead of on different blocks (whole-row writes, but four
+      // distinct weight addresses per warp: 304 -> 765 us)
+      bool even = true;
+      for (int i = 0; i < ncls; ++i) even = even && cls[i].Wg % 2 == 0;
+      const char* e2 = getenv("DCGANSR_THIN_PX2");
+      const int PXv = (even && g.si == 2 && !(e2 && atoi(e2) == 0)) ? 2 : 1;
+      dim3 grid2((unsigned)std::min<int64_t>((maxpix / PXv + 255) / 256, NSM * 8), (unsigned)(ncls * (g.Co / CH)));
       const size_t smem2 = (size_t)maxt2 * g.Ci * CH * sizeof(float);
-#define THIN_PX_LAUNCH(CI_, CH_) thin_in_px_kernel<CI_, CH_><<<grid2, 256, smem2, st.s>>>(p, in, out)
+#define THIN_PX_LAUNCH(CI_, CH_)                                                                       \
+      do {                                                                                             \
+        if (PXv == 2) thin_in_px_kernel<CI_, CH_, 2><<<grid2, 256, smem2, st.s>>>(p, in, out);         \
+        else thin_in_px_kernel<CI_, CH_, 1><<<grid2, 256, smem2, st.s>>>(p, in, out);                  \
+      } while (0)
 #define THIN_PX_CH(CI_)                                         \
       do {                                                      \
         if (CH == 16) THIN_PX_LAUNCH(CI_, 16);                  \
