@@ -22,7 +22,6 @@ struct Prof {
 struct TcWorkspace {
   float* part = nullptr; size_t part_bytes = 0; int* counters = nullptr; int ncounters = 0;
   double* lpart = nullptr; int* lcounter = nullptr;     // criterion kernel: block partials (256 doubles) + arrival counter (both precisions)
-  float* pad = nullptr; size_t pad_bytes = 0;           // 3 -> 4 channel padded copy of an RGB convolution input (kernels_thin.cu); sized at net creation
 };
 struct St {
   cudaStream_t s;

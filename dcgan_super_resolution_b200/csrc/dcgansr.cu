@@ -100,18 +100,6 @@ static void graphs_invalidate(dcgansr_ctx* ctx, const void* net) {
   ctx->graphs.resize(k);
 }
 
-static int fail(dcgansr_ctx* ctx, int code, const std::string& msg);
-// grows the context's padded-input scratch (never inside a step: nets and layer-level ops size it before they launch)
-static int ensure_pad(dcgansr_ctx* ctx, size_t bytes) {
-  if (bytes <= ctx->tcws.pad_bytes) return 0;
-  cudaStreamSynchronize(ctx->stream);
-  graphs_invalidate(ctx, nullptr);          // captured steps hold the old pointer
-  if (ctx->tcws.pad) cudaFree(ctx->tcws.pad);
-  ctx->tcws.pad = nullptr; ctx->tcws.pad_bytes = 0;
-  if (cudaMalloc((void**)&ctx->tcws.pad, bytes) != cudaSuccess) { cudaGetLastError(); return 0; }     // without it the kernels read the 3-channel tensor
-  ctx->tcws.pad_bytes = bytes;
-  return 0;
-}
 static int fail(dcgansr_ctx* ctx, int code, const std::string& msg) {
   t_err = msg;
   if (ctx) ctx->err = msg;
@@ -503,13 +491,6 @@ struct ConvPlan {
     run_classes(ctx, fwd, hmode_fwd, in, out, N, act, neg, stats, stats_rows);
   }
   void dgrad_run(dcgansr_ctx* ctx, const float* dy, float* dx, int N) { run_classes(ctx, dgrad, hmode_dgrad, dy, dx, N, ACT_NONE, 0.f); }
-  // bytes of the 4-channel padded copy a 3-channel input of this module's forward / dgrad classes takes (kernels_thin.cu)
-  size_t pad_bytes(int N) const {
-    size_t b = 0;
-    for (auto* v : {&fwd, &dgrad})
-      if (!v->empty() && (*v)[0].g.Ci == 3) b = std::max(b, (size_t)N * (*v)[0].g.Hi * (*v)[0].g.Wi * 4 * sizeof(float));
-    return b;
-  }
   bool fast = false;       // FAST_TF32: tensor-core wgrad when the geometry allows
   size_t wscratch_bytes(int N) const {
     WgradGeom g = wg;
@@ -1043,7 +1024,6 @@ void dcgansr_ctx_destroy(dcgansr_ctx* ctx) {
   for (float* p : ctx->slots) if (p) cudaFree(p);
   if (ctx->tcws.part) cudaFree(ctx->tcws.part);
   if (ctx->tcws.counters) cudaFree(ctx->tcws.counters);
-  if (ctx->tcws.pad) cudaFree(ctx->tcws.pad);
   if (ctx->tcws.lpart) cudaFree(ctx->tcws.lpart);
   if (ctx->tcws.lcounter) cudaFree(ctx->tcws.lcounter);
   if (ctx->flush_buf) cudaFree(ctx->flush_buf);
@@ -1296,7 +1276,7 @@ int dcgansr_net_create(dcgansr_ctx* ctx, const dcgansr_layer* layers, int n_laye
   int64_t gmax = B * in_c * in_h * in_w;
   int maxC = 1;
   int64_t maxP = 1;
-  size_t wsc = 0, padb = 0;
+  size_t wsc = 0;
   for (auto& m : net->mods) {
     int64_t oe = B * m.cout * m.hout * m.wout;
     gmax = std::max(gmax, std::max(oe, B * m.cin * m.hin * m.win));
@@ -1312,10 +1292,8 @@ int dcgansr_net_create(dcgansr_ctx* ctx, const dcgansr_layer* layers, int n_laye
     if (m.conv) {
       if (e == cudaSuccess && m.conv->alloc_device(ctx) != 0) e = cudaErrorMemoryAllocation;
       wsc = std::max(wsc, m.conv->wscratch_bytes((int)B));
-      padb = std::max(padb, m.conv->pad_bytes((int)B));
     }
   }
-  ensure_pad(ctx, padb);
   // aliases for fused ACT / VIEW modules
   for (size_t i = 0; i < net->mods.size(); ++i) {
     Mod& m = net->mods[i];
@@ -1831,7 +1809,6 @@ static int conv_op(dcgansr_ctx* ctx, bool full, int what, const float* a, const 
   if (!err.empty()) return fail(ctx, DCGANSR_ERR_INVALID, err);
   struct Guard { ConvPlan& p; ~Guard() { p.free_device(); } } guard{plan};
   if (int rc = plan.alloc_device(ctx)) return rc;
-  ensure_pad(ctx, plan.pad_bytes(n));
   Arena ar;
   int64_t xin = (int64_t)n * cin * h * wd, yout = (int64_t)n * cout * plan.Hout * plan.Wout, wn = plan.weight_count();
   float* dX = ar.f(xin);
@@ -1893,7 +1870,6 @@ int dcgansr_bench_conv(dcgansr_ctx* ctx, int full, int what, int n, int cin, int
   if (!err.empty()) return fail(ctx, DCGANSR_ERR_INVALID, err);
   struct Guard { ConvPlan& p; ~Guard() { p.free_device(); } } guard{plan};
   if (int rc = plan.alloc_device(ctx)) return rc;
-  ensure_pad(ctx, plan.pad_bytes(n));
   Arena ar;
   int64_t xin = (int64_t)n * cin * h * wd, yout = (int64_t)n * cout * plan.Hout * plan.Wout, wn = plan.weight_count();
   float *dX = ar.f(xin), *dY = ar.f(yout), *dW = ar.f(wn);

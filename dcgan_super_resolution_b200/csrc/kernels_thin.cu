@@ -463,9 +463,7 @@ __global__ void __launch_bounds__(256) thin_in_kernel(const ThinIn p, const floa
 // lane, where thin_in_kernel spends one 512-byte shared-memory read per 4 FMAs per lane (it is shared-memory bound at CI = 3:
 // D conv 3->64 615 us for 318 MB at C3b).  Lanes are consecutive pixels of a row: coalesced 12 B-strided input reads through L1,
 // 4*CH-byte output segments.
-// CS = floats between input pixels in memory: CI, or 4 for a 3-channel input padded to 4 (one 16-byte load per pixel: the kernel is
-// bound by the L1's sector rate, 83 % l1tex throughput, and the three 4-byte loads per input pixel are most of its sectors)
-template <int CI, int CH, int PX, int CS>
+template <int CI, int CH, int PX>
 __global__ void __launch_bounds__(256) thin_in_px_kernel(const ThinIn p, const float* __restrict__ in, float* __restrict__ out) {
   extern __shared__ __align__(16) float sw[];                  // [t][ci][CH] of this (class, cout chunk)
   const int nchunk = p.Co / CH;
@@ -495,20 +493,15 @@ __global__ void __launch_bounds__(256) thin_in_px_kernel(const ThinIn p, const f
     for (int t = 0; t < c.ntaps; ++t) {
       const int iy = gy * p.si + c.dy[t];
       if (iy < 0 || iy >= p.Hi) continue;
-      const float* irow = in + ((int64_t)(n * p.Hi + iy) * p.Wi) * CS;
+      const float* irow = in + ((int64_t)(n * p.Hi + iy) * p.Wi) * CI;
       const float4* w = reinterpret_cast<const float4*>(sw + t * CI * CH);
       float x[PX][CI];
 #pragma unroll
       for (int u = 0; u < PX; ++u) {
         const int ix = (gx + u) * p.si + c.dx[t];
         const bool ok = ix >= 0 && ix < p.Wi;
-        if (CS == 4 && CI == 3) {
-          const float4 v = ok ? __ldg(reinterpret_cast<const float4*>(irow + ix * 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          x[u][0] = v.x; x[u][1] = v.y; x[u][CI - 1] = v.z;
-        } else {
 #pragma unroll
-          for (int ci = 0; ci < CI; ++ci) x[u][ci] = ok ? __ldg(irow + ix * CI + ci) : 0.f;
-        }
+        for (int ci = 0; ci < CI; ++ci) x[u][ci] = ok ? __ldg(irow + ix * CI + ci) : 0.f;
       }
 #pragma unroll
       for (int ci = 0; ci < CI; ++ci) {
@@ -592,33 +585,18 @@ bool k_tapconv_thin_in(St st, const TapGeom* cls, int ncls, const float* const* 
       // two pixels per thread for the stride-2 gathers when every class grid has an even width (measured: D conv 3->64 forward
       // 323 -> 300 us, D conv 1->64 29 -> 25 us; not for the stride-1 classes: C 12->3 dgrad 309 -> 407 us).  Also measured and
       // dropped: the cout chunks of a pixel on consecutive threads instead of on different blocks (whole-row writes, but four
-      // distinct weight addresses per warp: 304 -> 765 us)
+      // distinct weight addresses per warp: 304 -> 765 us); a 4-channel padded copy of the 3-channel input for 16-byte loads (what
+      // doubled the thin wgrad): D conv 3->64 forward 302 -> 341 us, C 12->3 dgrad 304 -> 319 us
       bool even = true;
       for (int i = 0; i < ncls; ++i) even = even && cls[i].Wg % 2 == 0;
       const char* e2 = getenv("DCGANSR_THIN_PX2");
       const int PXv = (even && g.si == 2 && !(e2 && atoi(e2) == 0)) ? 2 : 1;
       dim3 grid2((unsigned)std::min<int64_t>((maxpix / PXv + 255) / 256, NSM * 8), (unsigned)(ncls * (g.Co / CH)));
       const size_t smem2 = (size_t)maxt2 * g.Ci * CH * sizeof(float);
-      // 3-channel input: padded to 4 channels in the context's scratch (sized at net creation) for 16-byte loads
-      const float* src = in;
-      bool padded = false;
-      {
-        const size_t need = (size_t)g.N * g.Hi * g.Wi * 4 * sizeof(float);
-        const char* e4 = getenv("DCGANSR_THIN_PAD34");
-        if (g.Ci == 3 && st.ws && st.ws->pad && st.ws->pad_bytes >= need && !(e4 && atoi(e4) == 0)) {
-          const int64_t np = (int64_t)g.N * g.Hi * g.Wi;
-          pad34_kernel<<<(unsigned)std::min<int64_t>((np + 255) / 256, NSM * 8), 256, 0, st.s>>>(in, reinterpret_cast<float4*>(st.ws->pad), np);
-          src = st.ws->pad;
-          padded = true;
-        }
-      }
-#define THIN_PX_LAUNCH(CI_, CH_)                                                                                        \
-      do {                                                                                                              \
-        if (padded && (CI_) == 3) {                                                                                     \
-          if (PXv == 2) thin_in_px_kernel<CI_, CH_, 2, 4><<<grid2, 256, smem2, st.s>>>(p, src, out);                    \
-          else thin_in_px_kernel<CI_, CH_, 1, 4><<<grid2, 256, smem2, st.s>>>(p, src, out);                             \
-        } else if (PXv == 2) thin_in_px_kernel<CI_, CH_, 2, CI_><<<grid2, 256, smem2, st.s>>>(p, in, out);              \
-        else thin_in_px_kernel<CI_, CH_, 1, CI_><<<grid2, 256, smem2, st.s>>>(p, in, out);                              \
+#define THIN_PX_LAUNCH(CI_, CH_)                                                                       \
+      do {                                                                                             \
+        if (PXv == 2) thin_in_px_kernel<CI_, CH_, 2><<<grid2, 256, smem2, st.s>>>(p, in, out);         \
+        else thin_in_px_kernel<CI_, CH_, 1><<<grid2, 256, smem2, st.s>>>(p, in, out);                  \
       } while (0)
 #define THIN_PX_CH(CI_)                                         \
       do {                                                      \
