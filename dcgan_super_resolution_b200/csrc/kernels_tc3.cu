@@ -363,6 +363,8 @@ static bool tc3_cfg(const TapGeom* cls, int ncls, const float* const* bt, Tc3Cfg
   p.na_stage = std::min(8, (budget - p.nb_stage * p.b_stage_bytes) / p.plane_bytes);
   if (p.na_stage < 2) return false;
   p.nb_stage = std::min(32, (budget - p.na_stage * p.plane_bytes) / p.b_stage_bytes);
+  if (const char* e = getenv("DCGANSR_TC3_NA")) p.na_stage = std::max(2, std::min(p.na_stage, atoi(e)));      // ring-depth experiments
+  if (const char* e = getenv("DCGANSR_TC3_NB")) p.nb_stage = std::max(2, std::min(p.nb_stage, atoi(e)));
   p.acc_cols = p.BN;
   p.tmem_cols = std::max(32, pow2_ge3(2 * p.acc_cols));
   const int maxcl = tc3_max_clusters();
