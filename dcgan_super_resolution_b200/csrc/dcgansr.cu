@@ -575,6 +575,12 @@ struct dcgansr_net {
   int64_t gelems = 0;
   double *bn_partials = nullptr, *bn_sums = nullptr, *bn_sums_total = nullptr;
   double *mb_fsum = nullptr, *mb_bsum = nullptr;       // micro-batched execution: whole-batch BN sums (forward / backward), 2 x nbn each
+  // micro-batched execution: the output of ONE convolution kept for every micro-batch of the step (ck_B samples), so that the
+  // re-forwards of the later BatchNorm passes start behind it instead of at the net input (mb_ensure_ckpt picks the module)
+  int ck_mod = -1, ck_B = 0;
+  float *ck_buf = nullptr, *ck_home = nullptr;         // ck_home: the module's own (micro-batch sized) output buffer
+  int64_t ck_elems = 0;                                // floats per micro-batch
+  bool ck_valid = false;
   float* bn_fmeans = nullptr;                         // (float)(sum / n) of the BN backward reductions, 2 groups x 2C
   float* wscratch = nullptr;
   size_t wscratch_bytes = 0;
@@ -602,6 +608,9 @@ static void net_release_device(dcgansr_net* net) {
   cudaStreamSynchronize(c->stream);
   graphs_invalidate(c, net);          // a re-created net often gets the same heap / device addresses: no stale replay
   c->nets.erase(std::remove(c->nets.begin(), c->nets.end(), net), c->nets.end());
+  if (net->ck_mod >= 0 && net->ck_buf) net->mods[net->ck_mod].out = net->ck_home;       // micro-batch checkpoint: back to the module's own buffer
+  if (net->ck_buf) cudaFree(net->ck_buf);
+  net->ck_buf = nullptr; net->ck_mod = -1; net->ck_B = 0; net->ck_valid = false;
   for (auto& m : net->mods) {
     if (m.conv) m.conv->free_device();
     if (m.owns_out && m.out) cudaFree(m.out);
@@ -648,13 +657,14 @@ static void net_pack_all(dcgansr_net* net) {
 // bn_frozen: BatchNorm modules normalise with the statistics already in save_mean / save_invstd (whole-batch statistics of a
 // micro-batched step) and leave the running statistics alone.
 static int net_forward_dev(dcgansr_net* net, const float* in, int B, int groups = 1, int stop = -1, bool bn_frozen = false,
-                           const float** stop_in = nullptr) {
+                           const float** stop_in = nullptr, int start = 0) {
   dcgansr_ctx* ctx = net->ctx;
   St st = ctx->st();
-  const float* cur = in;
+  // start > 0: module start - 1 already holds its output for this batch (micro-batch checkpoint)
+  const float* cur = start > 0 ? net->mods[start - 1].out : in;
   const bool sync = ctx->cfg.sync_bn && ctx->world() > 1;
   const int NB = B * groups;
-  for (size_t mi = 0; mi < net->mods.size(); ++mi) {
+  for (size_t mi = (size_t)start; mi < net->mods.size(); ++mi) {
     Mod& m = net->mods[mi];
     if ((int)mi == stop) { if (stop_in) *stop_in = cur; CKLAST(ctx); return 0; }
     switch (m.kind) {
@@ -885,30 +895,85 @@ static int net_backward_dev(dcgansr_net* net, const float* in, const float* dy, 
 //             accumulating the parameter gradients.
 // Cost: about (J + 1) forward and backward passes for J BatchNorms; result = the single-batch step up to summation order.
 // ------------------------------------------------------------------------------------------
+// Points the checkpointed module's output (and the fused modules that alias it) at micro-batch mi's slice, or back home (mi < 0)
+static void mb_select(dcgansr_net* net, int mi) {
+  if (net->ck_mod < 0 || !net->ck_buf) return;
+  net->mods[net->ck_mod].out = mi < 0 ? net->ck_home : net->ck_buf + (int64_t)mi * net->ck_elems;
+  for (size_t i = net->ck_mod + 1; i < net->mods.size() && !net->mods[i].owns_out; ++i) net->mods[i].out = net->mods[i - 1].out;
+}
+
+// Chooses and allocates the checkpoint for a step of B samples (never inside a capture: called by step_run before it).  A
+// checkpoint at convolution i serves every pass that runs past i: the candidate with the largest (flops up to i) x (BatchNorms
+// behind i + 1) whose B-sample output fits the free memory is taken.  C5: FC 1024->512's output (64 GiB) -- the re-forwards of
+// the BN3 / BN4 / final passes and of three of the five backward passes start behind the two first layers.
+static void mb_ensure_ckpt(dcgansr_ctx* ctx, dcgansr_net* net, int B) {
+  if (net->ck_B == B || B <= net->max_batch) return;
+  cudaStreamSynchronize(ctx->stream);
+  graphs_invalidate(ctx, net);
+  mb_select(net, -1);
+  if (net->ck_buf) cudaFree(net->ck_buf);
+  net->ck_buf = nullptr; net->ck_mod = -1; net->ck_B = B; net->ck_valid = false;
+  if (getenv("DCGANSR_NO_MB_CKPT")) return;
+  size_t free_b = 0, total_b = 0;
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) { cudaGetLastError(); return; }
+  const size_t margin = (size_t)4 << 30;
+  double prefix = 0.0, best = 0.0;
+  int best_i = -1;
+  for (size_t i = 0; i + 1 < net->mods.size(); ++i) {
+    Mod& m = net->mods[i];
+    if (!m.conv) continue;
+    prefix += 2.0 * m.cin * m.cout * m.L.kh * m.L.kw * (m.kind == DCGANSR_FULLCONV ? (double)m.hin * m.win : (double)m.hout * m.wout);
+    int bn_after = 0;
+    for (size_t j = i + 1; j < net->mods.size(); ++j) bn_after += net->mods[j].kind == DCGANSR_BN;
+    if (!m.owns_out || bn_after == 0) continue;
+    const size_t bytes = (size_t)B * m.cout * m.hout * m.wout * sizeof(float);
+    if (bytes + margin > free_b) continue;
+    const double score = prefix * (bn_after + 1);
+    if (score > best) { best = score; best_i = (int)i; }
+  }
+  if (best_i < 0) return;
+  Mod& m = net->mods[best_i];
+  net->ck_elems = (int64_t)net->max_batch * m.cout * m.hout * m.wout;
+  if (cudaMalloc((void**)&net->ck_buf, (size_t)B * m.cout * m.hout * m.wout * sizeof(float)) != cudaSuccess) { cudaGetLastError(); net->ck_buf = nullptr; return; }
+  net->ck_mod = best_i;
+  net->ck_home = m.out;
+  if (getenv("DCGANSR_MB_DEBUG"))
+    fprintf(stderr, "[dcgansr] micro-batch checkpoint: module %d (%d -> %d channels, %d x %d), %.1f GiB for %d samples, %.1f GiB were free\n", best_i,
+            m.cin, m.cout, m.hout, m.wout, (double)B * m.cout * m.hout * m.wout * 4 / (1 << 30), B, (double)free_b / (1 << 30));
+}
+
 static int net_forward_mb(dcgansr_net* net, const float* in_all, int B, float* out_all) {
   dcgansr_ctx* ctx = net->ctx;
   St st = ctx->st();
   const int b = net->max_batch, k = B / b;
   const int64_t ie = (int64_t)b * net->in_c * net->in_h * net->in_w, oe = (int64_t)b * net->out_c * net->out_h * net->out_w;
   if (net->nbn > 0) CK(ctx, cudaMemsetAsync(net->mb_fsum, 0, 2 * net->nbn * sizeof(double), ctx->stream));
+  const bool ck = net->ck_buf && net->ck_B == B;
+  net->ck_valid = false;            // the parameters changed since the last step
   for (size_t j = 0; j < net->mods.size(); ++j) {
     Mod& m = net->mods[j];
     if (m.kind != DCGANSR_BN) continue;
     const int C = m.cin;
     const int64_t P = (int64_t)b * m.hin * m.win;
+    const bool from_ck = ck && net->ck_valid && (int)j > net->ck_mod;
     for (int mi = 0; mi < k; ++mi) {
       const float* x = nullptr;
-      if (int rc = net_forward_dev(net, in_all + mi * ie, b, 1, (int)j, true, &x)) return rc;
+      if (ck) mb_select(net, mi);
+      if (int rc = net_forward_dev(net, in_all + mi * ie, b, 1, (int)j, true, &x, from_ck ? net->ck_mod + 1 : 0)) return rc;
       k_bn_stats(st, x, P, C, net->bn_partials, net->bn_sums);
       k_dacc(st, net->mb_fsum + 2 * m.bn_off, net->bn_sums, 2 * C);
     }
+    // this pass ran the checkpointed convolution with the final statistics of every BatchNorm before it: its slices are final
+    if (ck && (int)j > net->ck_mod) net->ck_valid = true;
     k_bn_finalize(st, net->mb_fsum + 2 * m.bn_off, C, (double)P * k, m.L.eps, m.L.momentum, m.save_mean, m.save_invstd,
                   net->bn_rmean + m.bn_off, net->bn_rvar + m.bn_off);
   }
   for (int mi = 0; mi < k; ++mi) {
-    if (int rc = net_forward_dev(net, in_all + mi * ie, b, 1, -1, true)) return rc;
+    if (ck) mb_select(net, mi);
+    if (int rc = net_forward_dev(net, in_all + mi * ie, b, 1, -1, true, nullptr, (ck && net->ck_valid) ? net->ck_mod + 1 : 0)) return rc;
     CK(ctx, cudaMemcpyAsync(out_all + mi * oe, net->last_out, oe * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
   }
+  if (ck) { net->ck_valid = true; mb_select(net, -1); }
   net->last_out = nullptr;           // the cached activations are those of the LAST micro-batch only
   net->last_batch = 0;
   CKLAST(ctx);
@@ -924,18 +989,24 @@ static int net_backward_mb(dcgansr_net* net, const float* in_all, const float* d
   for (int j = (int)net->mods.size() - 1; j >= 0; --j) {
     if (net->mods[j].kind != DCGANSR_BN) continue;
     MbWalk w{B, j, false};
+    // the walk of this pass stops at BatchNorm j: it needs the activations from module j - 1 on; behind the checkpoint they are
+    // rebuilt from it (the forward pass of this step left every slice final)
+    const bool from_ck = net->ck_buf && net->ck_B == B && net->ck_valid && j > net->ck_mod;
     for (int mi = 0; mi < k; ++mi) {
-      if (int rc = net_forward_dev(net, in_all + mi * ie, b, 1, -1, true)) return rc;
+      if (net->ck_buf && net->ck_B == B) mb_select(net, mi);
+      if (int rc = net_forward_dev(net, in_all + mi * ie, b, 1, -1, true, nullptr, from_ck ? net->ck_mod + 1 : 0)) return rc;
       CK(ctx, cudaMemcpyAsync(net->gbuf[0], dy_all + mi * oe, oe * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
       if (int rc = net_backward_dev(net, in_all + mi * ie, net->gbuf[0], b, false, false, &dxd, 1, 0, false, &w)) return rc;
     }
   }
   for (int mi = 0; mi < k; ++mi) {
     MbWalk w{B, -1, mi == 0};
+    if (net->ck_buf && net->ck_B == B) mb_select(net, mi);
     if (int rc = net_forward_dev(net, in_all + mi * ie, b, 1, -1, true)) return rc;
     CK(ctx, cudaMemcpyAsync(net->gbuf[0], dy_all + mi * oe, oe * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
     if (int rc = net_backward_dev(net, in_all + mi * ie, net->gbuf[0], b, true, false, &dxd, 1, 0, reduce_buckets && mi == k - 1, &w)) return rc;
   }
+  mb_select(net, -1);
   CKLAST(ctx);
   return 0;
 }
@@ -1607,8 +1678,10 @@ static int step_run(dcgansr_ctx* ctx, dcgansr_net* G, dcgansr_net* D, const dcga
   size_t lr_bytes = (size_t)B * G->in_c * G->in_h * G->in_w * sizeof(float);
   if (int rc = ensure(ctx, &ctx->lr_buf, &ctx->lr_cap, std::max<size_t>(lr_bytes, 16))) return rc;
   if (int rc = ensure(ctx, &ctx->label_vec, &ctx->label_cap, std::max<size_t>((size_t)B * sizeof(float), 16))) return rc;
-  if (B > G->max_batch)
+  if (B > G->max_batch) {
     if (int rc = ensure(ctx, &ctx->fake_buf, &ctx->fake_cap, (size_t)B * D->in_c * D->in_h * D->in_w * sizeof(float))) return rc;
+    mb_ensure_ckpt(ctx, G, B);
+  }
   if (ctx->cfg.use_graph && !ctx->prof.on) {       // the per-launch event profiler needs eager launches
     GraphEntry* ge = nullptr;
     for (auto& g : ctx->graphs)
