@@ -903,8 +903,8 @@ static void mb_select(dcgansr_net* net, int mi) {
 }
 
 // Chooses and allocates the checkpoint for a step of B samples (never inside a capture: called by step_run before it).  A
-// checkpoint at convolution i serves every pass that runs past i: the candidate with the largest (flops up to i) x (BatchNorms
-// behind i + 1) whose B-sample output fits the free memory is taken.  C5: FC 1024->512's output (64 GiB) -- the re-forwards of
+// checkpoint at convolution i serves every pass that runs past i: the candidate with the largest (flops up to i) x 2 x (BatchNorms
+// behind i) whose B-sample output fits the free memory is taken.  C5: FC 1024->512's output (64 GiB) -- the re-forwards of
 // the BN3 / BN4 / final passes and of three of the five backward passes start behind the two first layers.
 static void mb_ensure_ckpt(dcgansr_ctx* ctx, dcgansr_net* net, int B) {
   if (net->ck_B == B || B <= net->max_batch) return;
@@ -928,7 +928,7 @@ static void mb_ensure_ckpt(dcgansr_ctx* ctx, dcgansr_net* net, int B) {
     if (!m.owns_out || bn_after == 0) continue;
     const size_t bytes = (size_t)B * m.cout * m.hout * m.wout * sizeof(float);
     if (bytes + margin > free_b) continue;
-    const double score = prefix * (bn_after + 1);
+    const double score = prefix * 2.0 * bn_after;      // bn_after forward passes (the later statistics passes + the final one) and as many backward passes start behind it
     if (score > best) { best = score; best_i = (int)i; }
   }
   if (best_i < 0) return;
