@@ -311,7 +311,9 @@ def roofline_of(top, peaks, precision):
             "kernel": t["kernel"], "share_of_step": t["share"], "avg_launch_ms": t["avg_ms"], "work_per_launch": t["work_per_launch"],
             "launches_per_step": t["launches_per_step"],
             "peak_source": peaks["source"] + (" (copy bandwidth)" if t["bound"] == "hbm" else
-                                              " (burst bf16 GEMM / 2: kind::tf32 runs at half the bf16 rate)" if precision == "tf32"
+                                              " (burst bf16 GEMM / 2: kind::tf32 runs at half the bf16 rate; the cta_group::2 kernels exceed what cuBLAS "
+                                              "reached -- the pipe's own TF32 ceiling is 1.09-1.16 PFLOP/s at 1.8-1.96 GHz, see sm__pipe_tensor_cycles_active "
+                                              "in profiles/r2_ncu_full.csv)" if precision == "tf32"
                                               else " (burst bf16 GEMM; strict mode computes in fp32 FFMA)"),
             "traffic_note": "dram__bytes_read+write of the heaviest launch of this kernel in profiles/ (ncu --set full); null when that "
                             "capture was taken on another workload's shapes"}
