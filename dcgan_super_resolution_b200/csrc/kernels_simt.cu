@@ -282,13 +282,18 @@ void k_tapconv_simt(St st, const TapGeom& g, const float* in, const float* wp, f
 // wgrad.  CTA tile 64 (cp) x 64 (flattened (t,cq)), 16 pixels per K step, thread tile 4x4.
 // grid = (ceil(T*Cq/64), ceil(Cp/64), S); split s handles pixels [s*chunk, (s+1)*chunk).
 // ------------------------------------------------------------------------------------------
-struct WgCfg { int S; int64_t chunk; int tiles_n, tiles_m; };
+struct WgCfg { int S; int64_t chunk; int tiles_n, tiles_m, bm, bn; };
 
 static WgCfg wg_cfg(const WgradGeom& g) {
   WgCfg c;
   int64_t npix = (int64_t)g.N * g.Hp * g.Wp;
-  c.tiles_n = (g.ntaps * g.Cq + 63) / 64;
-  c.tiles_m = (g.Cp + 63) / 64;
+  // CTA tile (cp x (t,cq)): 64 x 64, or the narrow variants for few grid-tensor channels (DCGANSR_SIMT_NARROW=0 disables them)
+  static const bool narrow = !(getenv("DCGANSR_SIMT_NARROW") && atoi(getenv("DCGANSR_SIMT_NARROW")) == 0);
+  c.bm = 64; c.bn = 64;
+  if (narrow && g.Cp <= 16) { c.bm = 16; c.bn = 256; }
+  else if (narrow && g.Cp <= 32) { c.bm = 32; c.bn = 128; }
+  c.tiles_n = (g.ntaps * g.Cq + c.bn - 1) / c.bn;
+  c.tiles_m = (g.Cp + c.bm - 1) / c.bm;
   int64_t tiles = (int64_t)c.tiles_n * c.tiles_m;
   int64_t want = (NSM * 4 + tiles - 1) / tiles;          // aim at ~4 CTAs per SM
   int64_t max_s = (npix + 255) / 256;                   // at least 256 pixels per split
@@ -418,6 +423,119 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradGeom g, const floa
   }
 }
 
+// Narrow-M variant for few grid-tensor channels (Cp <= 32: the generator's last layers, e.g. C 24->12 with P = dy of 12 channels):
+// CTA tile BM (cp) x BN ((t,cq)) with BM * BN = 4096 -- 16 x 256 or 32 x 128 -- instead of 64 x 64, which ran that layer with 19 %
+// of its rows in use (22 ms, 3.5 TFLOP/s at C3b).  Same thread tile (4 x 4), K step (16 pixels) and partial layout.
+template <int BM, int BN, bool VECQ>
+__global__ void __launch_bounds__(256) wgrad_simt_narrow_kernel(WgradGeom g, const float* __restrict__ P, const float* __restrict__ Q,
+                                                                float* __restrict__ scratch, int64_t chunk) {
+  static_assert(BM * BN == 4096 && BM % 4 == 0 && BN % 64 == 0, "256 threads x (4 x 4)");
+  constexpr int NB = BN / 64;                  // B float4 slots per thread and K step
+  __shared__ __align__(16) float As[16][BM];   // [pixel][cp]
+  __shared__ __align__(16) float Bs[16][BN];   // [pixel][(t,cq)]
+  const int tid = threadIdx.x;
+  const int Ntot = g.ntaps * g.Cq;
+  const int n0 = blockIdx.x * BN, mbase = blockIdx.y * BM;
+  const int64_t npix = (int64_t)g.N * g.Hp * g.Wp;
+  const int64_t pbeg = (int64_t)blockIdx.z * chunk;
+  const int64_t pend = pbeg + chunk < npix ? pbeg + chunk : npix;
+  // A: threads 0 .. 16 * BM / 4 - 1 load one float4 each
+  const int lkA = tid / (BM / 4), lvA = tid % (BM / 4);
+  const bool a_loader = tid < 16 * (BM / 4);
+  // B: slot = tid + j * 256 -> pixel slot / (BN / 4), column group slot % (BN / 4); the (t, cq) of its 4 columns are fixed
+  int lkB[NB], lvB[NB], bt[NB][4], bc[NB][4];
+  bool bval[NB][4];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    const int slot = tid + j * 256;
+    lkB[j] = slot / (BN / 4); lvB[j] = slot % (BN / 4);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int n = n0 + lvB[j] * 4 + e;
+      bval[j][e] = n < Ntot;
+      bt[j][e] = bval[j][e] ? n / g.Cq : 0;
+      bc[j][e] = n - bt[j][e] * g.Cq;
+    }
+  }
+  const int tx = tid % (BN / 4), ty = tid / (BN / 4);
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int64_t p0 = pbeg; p0 < pend; p0 += 16) {
+    if (a_loader) {
+      const int64_t p = p0 + lkA;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int cp = mbase + lvA * 4;
+      if (p < pend) {
+        const float* src = P + p * g.Cp + cp;
+        if (g.Cp % 4 == 0) { if (cp < g.Cp) v = __ldg(reinterpret_cast<const float4*>(src)); }
+        else {
+          if (cp + 0 < g.Cp) v.x = __ldg(src + 0);
+          if (cp + 1 < g.Cp) v.y = __ldg(src + 1);
+          if (cp + 2 < g.Cp) v.z = __ldg(src + 2);
+          if (cp + 3 < g.Cp) v.w = __ldg(src + 3);
+        }
+      }
+      *reinterpret_cast<float4*>(&As[lkA][lvA * 4]) = v;
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      const int64_t p = p0 + lkB[j];
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p < pend) {
+        const int gx = (int)(p % g.Wp);
+        const int64_t q = p / g.Wp;
+        const int gy = (int)(q % g.Hp), n = (int)(q / g.Hp);
+        if (VECQ) {
+          if (bval[j][0]) {
+            const int qy = gy * g.s + g.dy[bt[j][0]], qx = gx * g.s + g.dx[bt[j][0]];
+            if (qy >= 0 && qy < g.Hq && qx >= 0 && qx < g.Wq)
+              v = __ldg(reinterpret_cast<const float4*>(Q + ((int64_t)(n * g.Hq + qy) * g.Wq + qx) * g.Cq + bc[j][0]));
+          }
+        } else {
+          float e4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            if (bval[j][e]) {
+              const int qy = gy * g.s + g.dy[bt[j][e]], qx = gx * g.s + g.dx[bt[j][e]];
+              if (qy >= 0 && qy < g.Hq && qx >= 0 && qx < g.Wq)
+                e4[e] = __ldg(Q + ((int64_t)(n * g.Hq + qy) * g.Wq + qx) * g.Cq + bc[j][e]);
+            }
+          }
+          v = make_float4(e4[0], e4[1], e4[2], e4[3]);
+        }
+      }
+      *reinterpret_cast<float4*>(&Bs[lkB[j]][lvB[j] * 4]) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+  float* dst = scratch + (int64_t)blockIdx.z * g.Cp * Ntot;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int cp = mbase + ty * 4 + i;
+    if (cp >= g.Cp) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < Ntot) dst[(int64_t)cp * Ntot + n] = acc[i][j];
+    }
+  }
+}
+
 // grad_master[cp*(Cq*T) + cq*T + t] += sum_s scratch[s][cp][t*Cq + cq]          (fixed order: deterministic)
 // A block owns one cp and a chunk of its T*Cq row.  The S partials are summed by 4 split groups (s = g, g+4, ...) over 64
 // element lanes, combined through shared memory in fixed order, and the (t,cq) -> (cq,t) transposition to the Torch7
@@ -488,7 +606,13 @@ void k_wgrad_simt(St st, const WgradGeom& g, const float* P, const float* Q, flo
   WgCfg c = wg_cfg(g);
   dim3 grid(c.tiles_n, c.tiles_m, c.S);
   bool vp = g.Cp % 4 == 0, vq = g.Cq % 4 == 0;
-  if (vp && vq) wgrad_simt_kernel<true, true><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
+  if (c.bm == 16) {
+    if (vq) wgrad_simt_narrow_kernel<16, 256, true><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
+    else wgrad_simt_narrow_kernel<16, 256, false><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
+  } else if (c.bm == 32) {
+    if (vq) wgrad_simt_narrow_kernel<32, 128, true><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
+    else wgrad_simt_narrow_kernel<32, 128, false><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
+  } else if (vp && vq) wgrad_simt_kernel<true, true><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
   else if (vp) wgrad_simt_kernel<true, false><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
   else if (vq) wgrad_simt_kernel<false, true><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
   else wgrad_simt_kernel<false, false><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
