@@ -290,8 +290,11 @@ static WgCfg wg_cfg(const WgradGeom& g) {
   // CTA tile (cp x (t,cq)): 64 x 64, or the narrow variants for few grid-tensor channels (DCGANSR_SIMT_NARROW=0 disables them)
   static const bool narrow = !(getenv("DCGANSR_SIMT_NARROW") && atoi(getenv("DCGANSR_SIMT_NARROW")) == 0);
   c.bm = 64; c.bn = 64;
+  // (measured at C3b: Cp = 12: 22.0 ms at 64 rows, 14.1 at 32, 8.5 at 16; but Cp = 48 / 96 lose with narrower tiles -- 22.3 -> 28.3 ->
+  //  40.5 ms -- their operand loads are shared by fewer FMAs: narrow tiles only where a 64-row tile would be more than half empty)
   if (narrow && g.Cp <= 16) { c.bm = 16; c.bn = 256; }
   else if (narrow && g.Cp <= 32) { c.bm = 32; c.bn = 128; }
+  if (const char* e = getenv("DCGANSR_SIMT_BM")) { const int v = atoi(e); if (v == 16 || v == 32 || v == 64) { c.bm = v; c.bn = 4096 / v; } }
   c.tiles_n = (g.ntaps * g.Cq + c.bn - 1) / c.bn;
   c.tiles_m = (g.Cp + c.bm - 1) / c.bm;
   int64_t tiles = (int64_t)c.tiles_n * c.tiles_m;
