@@ -295,6 +295,8 @@ static WgCfg wg_cfg(const WgradGeom& g) {
   if (narrow && g.Cp <= 16) { c.bm = 16; c.bn = 256; }
   else if (narrow && g.Cp <= 32) { c.bm = 32; c.bn = 128; }
   if (const char* e = getenv("DCGANSR_SIMT_BM")) { const int v = atoi(e); if (v == 16 || v == 32 || v == 64) { c.bm = v; c.bn = 4096 / v; } }
+  // 64 x 128 tile with 8 x 4 thread tiles (twice the FMAs per shared-memory read) for the wide layers
+  if (c.bm == 64 && c.bn == 64 && g.ntaps * g.Cq >= 128 && !(getenv("DCGANSR_SIMT_BIG") && atoi(getenv("DCGANSR_SIMT_BIG")) == 0)) c.bn = 128;
   c.tiles_n = (g.ntaps * g.Cq + c.bn - 1) / c.bn;
   c.tiles_m = (g.Cp + c.bm - 1) / c.bm;
   int64_t tiles = (int64_t)c.tiles_n * c.tiles_m;
@@ -429,11 +431,12 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradGeom g, const floa
 // Narrow-M variant for few grid-tensor channels (Cp <= 32: the generator's last layers, e.g. C 24->12 with P = dy of 12 channels):
 // CTA tile BM (cp) x BN ((t,cq)) with BM * BN = 4096 -- 16 x 256 or 32 x 128 -- instead of 64 x 64, which ran that layer with 19 %
 // of its rows in use (22 ms, 3.5 TFLOP/s at C3b).  Same thread tile (4 x 4), K step (16 pixels) and partial layout.
-template <int BM, int BN, bool VECQ>
+template <int BM, int BN, int TM, bool VECQ>
 __global__ void __launch_bounds__(256) wgrad_simt_narrow_kernel(WgradGeom g, const float* __restrict__ P, const float* __restrict__ Q,
                                                                 float* __restrict__ scratch, int64_t chunk) {
-  static_assert(BM * BN == 4096 && BM % 4 == 0 && BN % 64 == 0, "256 threads x (4 x 4)");
-  constexpr int NB = BN / 64;                  // B float4 slots per thread and K step
+  static_assert(BM * BN == 1024 * TM && BM % 4 == 0 && BN % 64 == 0 && TM % 4 == 0, "256 threads x (TM x 4)");
+  constexpr int NB = BN / 64;                                   // B float4 slots per thread and K step
+  constexpr int NA = (16 * (BM / 4) + 255) / 256;               // A float4 slots per thread and K step
   __shared__ __align__(16) float As[16][BM];   // [pixel][cp]
   __shared__ __align__(16) float Bs[16][BN];   // [pixel][(t,cq)]
   const int tid = threadIdx.x;
@@ -442,9 +445,6 @@ __global__ void __launch_bounds__(256) wgrad_simt_narrow_kernel(WgradGeom g, con
   const int64_t npix = (int64_t)g.N * g.Hp * g.Wp;
   const int64_t pbeg = (int64_t)blockIdx.z * chunk;
   const int64_t pend = pbeg + chunk < npix ? pbeg + chunk : npix;
-  // A: threads 0 .. 16 * BM / 4 - 1 load one float4 each
-  const int lkA = tid / (BM / 4), lvA = tid % (BM / 4);
-  const bool a_loader = tid < 16 * (BM / 4);
   // B: slot = tid + j * 256 -> pixel slot / (BN / 4), column group slot % (BN / 4); the (t, cq) of its 4 columns are fixed
   int lkB[NB], lvB[NB], bt[NB][4], bc[NB][4];
   bool bval[NB][4];
@@ -461,28 +461,33 @@ __global__ void __launch_bounds__(256) wgrad_simt_narrow_kernel(WgradGeom g, con
     }
   }
   const int tx = tid % (BN / 4), ty = tid / (BN / 4);
-  float acc[4][4];
+  float acc[TM][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   for (int64_t p0 = pbeg; p0 < pend; p0 += 16) {
-    if (a_loader) {
-      const int64_t p = p0 + lkA;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      const int cp = mbase + lvA * 4;
-      if (p < pend) {
-        const float* src = P + p * g.Cp + cp;
-        if (g.Cp % 4 == 0) { if (cp < g.Cp) v = __ldg(reinterpret_cast<const float4*>(src)); }
-        else {
-          if (cp + 0 < g.Cp) v.x = __ldg(src + 0);
-          if (cp + 1 < g.Cp) v.y = __ldg(src + 1);
-          if (cp + 2 < g.Cp) v.z = __ldg(src + 2);
-          if (cp + 3 < g.Cp) v.w = __ldg(src + 3);
+#pragma unroll
+    for (int j = 0; j < NA; ++j) {
+      const int slot = tid + j * 256;
+      if (slot < 16 * (BM / 4)) {
+        const int lkA = slot / (BM / 4), lvA = slot % (BM / 4);
+        const int64_t p = p0 + lkA;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int cp = mbase + lvA * 4;
+        if (p < pend) {
+          const float* src = P + p * g.Cp + cp;
+          if (g.Cp % 4 == 0) { if (cp < g.Cp) v = __ldg(reinterpret_cast<const float4*>(src)); }
+          else {
+            if (cp + 0 < g.Cp) v.x = __ldg(src + 0);
+            if (cp + 1 < g.Cp) v.y = __ldg(src + 1);
+            if (cp + 2 < g.Cp) v.z = __ldg(src + 2);
+            if (cp + 3 < g.Cp) v.w = __ldg(src + 3);
+          }
         }
+        *reinterpret_cast<float4*>(&As[lkA][lvA * 4]) = v;
       }
-      *reinterpret_cast<float4*>(&As[lkA][lvA * 4]) = v;
     }
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
@@ -516,11 +521,16 @@ __global__ void __launch_bounds__(256) wgrad_simt_narrow_kernel(WgradGeom g, con
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < 16; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+      float av[TM];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < TM; i += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * TM + i]);
+        av[i] = a.x; av[i + 1] = a.y; av[i + 2] = a.z; av[i + 3] = a.w;
+      }
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
@@ -528,8 +538,8 @@ __global__ void __launch_bounds__(256) wgrad_simt_narrow_kernel(WgradGeom g, con
   }
   float* dst = scratch + (int64_t)blockIdx.z * g.Cp * Ntot;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int cp = mbase + ty * 4 + i;
+  for (int i = 0; i < TM; ++i) {
+    const int cp = mbase + ty * TM + i;
     if (cp >= g.Cp) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -610,11 +620,14 @@ void k_wgrad_simt(St st, const WgradGeom& g, const float* P, const float* Q, flo
   dim3 grid(c.tiles_n, c.tiles_m, c.S);
   bool vp = g.Cp % 4 == 0, vq = g.Cq % 4 == 0;
   if (c.bm == 16) {
-    if (vq) wgrad_simt_narrow_kernel<16, 256, true><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
-    else wgrad_simt_narrow_kernel<16, 256, false><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
+    if (vq) wgrad_simt_narrow_kernel<16, 256, 4, true><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
+    else wgrad_simt_narrow_kernel<16, 256, 4, false><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
   } else if (c.bm == 32) {
-    if (vq) wgrad_simt_narrow_kernel<32, 128, true><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
-    else wgrad_simt_narrow_kernel<32, 128, false><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
+    if (vq) wgrad_simt_narrow_kernel<32, 128, 4, true><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
+    else wgrad_simt_narrow_kernel<32, 128, 4, false><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
+  } else if (c.bn == 128) {
+    if (vq) wgrad_simt_narrow_kernel<64, 128, 8, true><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
+    else wgrad_simt_narrow_kernel<64, 128, 8, false><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
   } else if (vp && vq) wgrad_simt_kernel<true, true><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
   else if (vp) wgrad_simt_kernel<true, false><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
   else if (vq) wgrad_simt_kernel<false, true><<<grid, 256, 0, st.s>>>(g, P, Q, scratch, c.chunk);
