@@ -200,3 +200,15 @@ def test_lua_hosts_use_only_the_shim_surface(host):
                 kinds += [lua_kind[k] for k in re.findall(r"(?:nn\.)?\b(SpatialFullConvolution|SpatialConvolution|SpatialBatchNormalization|"
                                                           r"SpatialUpSamplingNearest|LeakyReLU|ReLU|Tanh|Sigmoid|View)\(", ln)]
         assert kinds == [s["kind"] for s in specs], (host, var, kinds)
+
+
+def test_build_compiles_every_cuda_source():
+    """Every .cu under csrc/ is in the build list (a kernel file left out would only show up as an unresolved symbol at link time,
+    or -- with a weak fallback -- not at all)."""
+    import os
+
+    from dcgan_super_resolution_b200 import build as b
+    here = os.path.dirname(os.path.abspath(b.__file__))
+    on_disk = sorted(f for f in os.listdir(os.path.join(here, "csrc")) if f.endswith(".cu"))
+    assert sorted(b.SOURCES) == on_disk, (sorted(b.SOURCES), on_disk)
+    assert "arch=compute_100a,code=sm_100a" in " ".join(b.NVCC_FLAGS) and "-lineinfo" in b.NVCC_FLAGS
