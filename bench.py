@@ -437,6 +437,22 @@ def run_workload(env, ctx, workload, B, steps, warmup, precision, legs=("staged"
     return res
 
 
+def sync_bn_timing(env, workload="C4", B=64, steps=20):
+    """ms per sync_bn=1 step of a BatchNorm-heavy small-step workload, statistics through the peer-memory kernel vs ncclAllReduce."""
+    out = {"workload": f"{workload} at {B} per GPU, sync_bn=1, CUDA graph, {steps} steps"}
+    for name, peer in (("nccl", False), ("peer", True), ("nccl_again", False), ("peer_again", True)):
+        if not peer:
+            os.environ["DCGANSR_PEER_AR"] = "0"
+        try:
+            ctx = env.new_ctx("tf32", graph=True, sync_bn=True)
+            r = run_workload(env, ctx, workload, B, steps, 3, "tf32", legs=("staged",))
+            ctx.close()
+            out[name] = r["ms_per_step"]
+        finally:
+            os.environ.pop("DCGANSR_PEER_AR", None)
+    return out
+
+
 def dp_check(env):
     """The 2-GPU checks of scripts/dp_check.py at whatever N the run has (the driver's pytest box has one GPU)."""
     import numpy as np
@@ -450,11 +466,15 @@ def dp_check(env):
     rng = np.random.Generator(np.random.Philox(99))
     full = [rng.uniform(-1, 1, (env.world * B, 1, 64, 64)).astype(np.float32) for _ in range(3)]
 
-    def run(world, precision, sync_bn, no_overlap=False, batch=B, shard=True, graph=False):
+    def run(world, precision, sync_bn, no_overlap=False, batch=B, shard=True, graph=False, peer=True, info=None):
         if no_overlap:
             os.environ["DCGANSR_NO_OVERLAP"] = "1"
+        if not peer:
+            os.environ["DCGANSR_PEER_AR"] = "0"
         try:
             ctx = env.new_ctx(precision, graph=graph, sync_bn=sync_bn, world=world)
+            if info is not None:
+                info["peer"] = ctx.comm_peer_enabled()
             G = dsr.Sequential.from_specs(specsG).cuda(ctx, (1, 32, 32), batch)
             D = dsr.Sequential.from_specs(specsD).cuda(ctx, (1, 64, 64), 2 * batch)
             G.set_params(init.weights_init(specsG, 4321))
@@ -470,6 +490,7 @@ def dp_check(env):
             return out
         finally:
             os.environ.pop("DCGANSR_NO_OVERLAP", None)
+            os.environ.pop("DCGANSR_PEER_AR", None)
 
     res = {"world": env.world, "batch_per_rank": B}
     for prec in ("strict", "tf32"):
@@ -481,7 +502,18 @@ def dp_check(env):
         #  another summation order -- for the bucket-sized messages than for the whole gradient vector: report the size of it)
         res[f"bucket_max_rel_diff_{prec}"] = float(max(np.max(np.abs(a[0] - b[0])) / np.max(np.abs(b[0])), np.max(np.abs(a[1] - b[1])) / np.max(np.abs(b[1]))))
         res[f"graph_replay_identical_{prec}"] = bool(np.array_equal(a[0], c[0]) and np.array_equal(a[1], c[1]))
-    a = run(env.world, "strict", True)
+    info = {}
+    a = run(env.world, "strict", True, info=info)
+    # sync_bn statistics: one-shot NVLink peer-memory all-reduce fused into the BatchNorm statistics tail (kernels_peer.cu) against
+    # ncclAllReduce of the same sums (DCGANSR_PEER_AR=0), eager and under graph replay (the call counter lives on the device)
+    res["sync_bn_peer_allreduce"] = bool(info.get("peer"))
+    if info.get("peer"):
+        n = run(env.world, "strict", True, peer=False)
+        g = run(env.world, "strict", True, graph=True)
+        res["sync_bn_peer_vs_nccl_max_rel_diff"] = float(max(np.max(np.abs(a[0] - n[0])) / np.max(np.abs(n[0])),
+                                                             np.max(np.abs(a[1] - n[1])) / np.max(np.abs(n[1]))))
+        res["sync_bn_peer_graph_replay_identical"] = bool(np.array_equal(a[0], g[0]) and np.array_equal(a[1], g[1]))
+        res["sync_bn_step_ms"] = sync_bn_timing(env)
     if env.rank == 0:
         ref = run(1, "strict", False, batch=env.world * B, shard=False)
         eG = float(np.max(np.abs(a[0] - ref[0])) / np.max(np.abs(ref[0])))

@@ -57,6 +57,7 @@ _SIGS = {
     "dcgansr_profile_end": (C.c_int, [_P, C.c_char_p, _I64]),
     "dcgansr_comm_get_unique_id": (C.c_int, [_P, _P]),
     "dcgansr_comm_init": (C.c_int, [_P, _P]),
+    "dcgansr_comm_peer_enabled": (C.c_int, [_P]),
     "dcgansr_net_create": (C.c_int, [_P, C.POINTER(Layer), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "dcgansr_net_destroy": (None, [_P]),
     "dcgansr_net_out_shape": (C.c_int, [_P, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdcgansr.so")
-SOURCES = ["dcgansr.cu", "kernels_bw.cu", "kernels_simt.cu", "kernels_thin.cu", "kernels_tc.cu", "kernels_tc2.cu", "kernels_tc3.cu", "kernels_halo.cu", "kernels_wgrad_halo.cu"]
+SOURCES = ["dcgansr.cu", "kernels_bw.cu", "kernels_simt.cu", "kernels_thin.cu", "kernels_tc.cu", "kernels_tc2.cu", "kernels_tc3.cu", "kernels_halo.cu", "kernels_wgrad_halo.cu", "kernels_peer.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "-Xcompiler", "-Wall",

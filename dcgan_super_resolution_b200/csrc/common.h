@@ -137,6 +137,20 @@ void k_fill(St st, float* p, int64_t count, float v);
 void k_scale(St st, float* p, int64_t count, float s);
 void k_flush(St st, float* buf, int64_t count);
 
+// ---- kernels_peer.cu : one-shot all-reduce over NVLink peer memory (sync_bn statistics) ------
+#define PEER_MAXW 8       // ranks of one NVSwitch domain
+#define PEER_SLOTS 4
+struct PeerAR {
+  double* data[PEER_MAXW];               // rank r's receive area [PEER_SLOTS][PEER_MAXW][nmax] (own: local pointer, peers: cudaIpc mappings)
+  unsigned long long* flags[PEER_MAXW];  // rank r's flags [PEER_SLOTS][PEER_MAXW]
+  unsigned long long* seq;               // calls completed by this rank (device memory: advanced by the kernels, graph-replayable)
+  int* err;                              // host-mapped: set when a peer did not arrive within the time-out
+  int rank, world, nmax;
+};
+void k_peer_allreduce(St st, const PeerAR& p, const double* in, double* out, int n);
+void k_bn_finalize_peer(St st, const PeerAR& p, double* sums, int C, double n_total, float eps, float momentum, float* save_mean,
+                        float* save_invstd, float* running_mean, float* running_var);
+
 // ---- kernels_simt.cu : strict fp32 FFMA convolutions -----------------------------------------
 // Packed weights for the tap-list kernels: Wp[t][a][b] = master[a*sa + b*sb + tapidx[t]]
 void k_pack_taps(St st, const float* master, float* wp, int ntaps, const int* tapidx_dev, int A, int B,

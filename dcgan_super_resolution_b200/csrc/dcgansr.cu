@@ -82,6 +82,12 @@ struct dcgansr_ctx {
   Prof prof;
   TcWorkspace tcws;
   std::vector<dcgansr_net*> nets;          // live nets created on this ctx (dcgansr_ctx_destroy detaches them)
+  // one-shot all-reduce over NVLink peer memory (kernels_peer.cu): set up by dcgansr_comm_init when every rank can map every peer
+  PeerAR peer{};
+  bool peer_ok = false;
+  void* peer_base = nullptr;
+  std::vector<void*> peer_maps;
+  int* peer_err_h = nullptr;
   St st() { return St{stream, &launches, &prof, &tcws}; }
   int world() const { return cfg.world_size > 1 && comm ? cfg.world_size : 1; }
 };
@@ -716,11 +722,16 @@ static int net_forward_dev(dcgansr_net* net, const float* in, int B, int groups 
           float* sinv = m.save_invstd + (int64_t)g * 2 * net->nbn;
           k_bn_stats(st, xg, P, C, net->bn_partials, net->bn_sums);
           double n_total = (double)P;
-          if (sync) {
-            if (int rc = nccl_allreduce(ctx, net->bn_sums, 2 * C, ncclDouble, ctx->stream)) return rc;
-            n_total *= ctx->world();
+          if (sync) n_total *= ctx->world();
+          if (sync && ctx->peer_ok && 2 * C <= ctx->peer.nmax) {
+            // the statistics tail does the cross-rank exchange itself (pushes over NVLink, kernels_peer.cu)
+            k_bn_finalize_peer(st, ctx->peer, net->bn_sums, C, n_total, m.L.eps, m.L.momentum, smean, sinv, net->bn_rmean + m.bn_off,
+                               net->bn_rvar + m.bn_off);
+          } else {
+            if (sync)
+              if (int rc = nccl_allreduce(ctx, net->bn_sums, 2 * C, ncclDouble, ctx->stream)) return rc;
+            k_bn_finalize(st, net->bn_sums, C, n_total, m.L.eps, m.L.momentum, smean, sinv, net->bn_rmean + m.bn_off, net->bn_rvar + m.bn_off);
           }
-          k_bn_finalize(st, net->bn_sums, C, n_total, m.L.eps, m.L.momentum, smean, sinv, net->bn_rmean + m.bn_off, net->bn_rvar + m.bn_off);
           k_bn_apply_act(st, xg, m.out + (int64_t)g * P * C, P, C, net->params + m.p_off, net->params + m.p_off + C, smean, sinv,
                          m.fused_act, m.fused_neg);
         }
@@ -857,8 +868,12 @@ static int net_backward_dev(dcgansr_net* net, const float* in, const float* dy, 
           const double* tot = net->bn_sums;
           double n_total = (double)P;
           if (sync) {
-            CK(ctx, cudaMemcpyAsync(net->bn_sums_total, net->bn_sums, 2 * C * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-            if (int rc = nccl_allreduce(ctx, net->bn_sums_total, 2 * C, ncclDouble, ctx->stream)) return rc;
+            if (ctx->peer_ok && 2 * C <= ctx->peer.nmax) {
+              k_peer_allreduce(st, ctx->peer, net->bn_sums, net->bn_sums_total, 2 * C);
+            } else {
+              CK(ctx, cudaMemcpyAsync(net->bn_sums_total, net->bn_sums, 2 * C * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+              if (int rc = nccl_allreduce(ctx, net->bn_sums_total, 2 * C, ncclDouble, ctx->stream)) return rc;
+            }
             tot = net->bn_sums_total;
             n_total *= ctx->world();
           }
@@ -1078,6 +1093,81 @@ int dcgansr_ctx_create(const dcgansr_cfg* cfg, dcgansr_ctx** out) {
   return 0;
 }
 
+// ---- peer-memory exchange area of the one-shot all-reduce (kernels_peer.cu) ------------------
+static void peer_teardown(dcgansr_ctx* ctx) {
+  for (void* m : ctx->peer_maps) if (m) cudaIpcCloseMemHandle(m);
+  ctx->peer_maps.clear();
+  if (ctx->peer_base) cudaFree(ctx->peer_base);
+  ctx->peer_base = nullptr;
+  if (ctx->peer_err_h) cudaFreeHost(ctx->peer_err_h);
+  ctx->peer_err_h = nullptr;
+  ctx->peer_ok = false;
+}
+// Every rank allocates its receive area, the cudaIpc handles travel through one NCCL all-reduce (a sum over zero-filled slots is
+// a gather), every rank maps every peer, and a second all-reduce makes the outcome unanimous: either all ranks use the peer
+// path or all stay on ncclAllReduce (different nodes, no peer access, DCGANSR_PEER_AR=0).
+static int peer_setup(dcgansr_ctx* ctx) {
+  const char* e = getenv("DCGANSR_PEER_AR");
+  const int W = ctx->cfg.world_size, me = ctx->cfg.rank;
+  const bool want = !(e && atoi(e) == 0) && W <= PEER_MAXW;
+  const int nmax = 4096;
+  const size_t data_bytes = (size_t)PEER_SLOTS * PEER_MAXW * nmax * sizeof(double);
+  const size_t flag_bytes = (size_t)PEER_SLOTS * PEER_MAXW * sizeof(unsigned long long);
+  struct Rec { cudaIpcMemHandle_t h; unsigned char ok; unsigned char pad[63]; };
+  static_assert(sizeof(Rec) == 128, "one record per rank");
+  Rec mine;
+  memset(&mine, 0, sizeof(mine));
+  if (want && cudaMalloc(&ctx->peer_base, data_bytes + flag_bytes + 256) == cudaSuccess) {
+    CK(ctx, cudaMemsetAsync(ctx->peer_base, 0, data_bytes + flag_bytes + 256, ctx->stream));
+    if (cudaIpcGetMemHandle(&mine.h, ctx->peer_base) == cudaSuccess) mine.ok = 1;
+  }
+  cudaGetLastError();
+  unsigned char* d_rec = nullptr;
+  CK(ctx, cudaMalloc((void**)&d_rec, (size_t)W * sizeof(Rec)));
+  std::vector<Rec> all((size_t)W);
+  auto gather = [&]() -> int {
+    CK(ctx, cudaMemsetAsync(d_rec, 0, (size_t)W * sizeof(Rec), ctx->stream));
+    CK(ctx, cudaMemcpyAsync(d_rec + (size_t)me * sizeof(Rec), &mine, sizeof(Rec), cudaMemcpyHostToDevice, ctx->stream));
+    CKN(ctx, ctx->nccl.AllReduce(d_rec, d_rec, (size_t)W * sizeof(Rec), ncclUint8, ncclSum, ctx->comm, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(all.data(), d_rec, (size_t)W * sizeof(Rec), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return 0;
+  };
+  int rc = gather();
+  bool ok = rc == 0;
+  for (int r = 0; ok && r < W; ++r) ok = all[r].ok == 1;
+  std::vector<void*> base((size_t)W, nullptr);
+  if (ok) {
+    for (int r = 0; r < W; ++r) {
+      if (r == me) { base[r] = ctx->peer_base; continue; }
+      void* ptr = nullptr;
+      if (cudaIpcOpenMemHandle(&ptr, all[r].h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+      ctx->peer_maps.push_back(ptr);
+      base[r] = ptr;
+    }
+  }
+  if (ok && cudaHostAlloc((void**)&ctx->peer_err_h, sizeof(int), cudaHostAllocMapped) != cudaSuccess) { cudaGetLastError(); ok = false; }
+  // unanimity (also the barrier behind which every rank's flags are known to be zeroed)
+  mine.ok = ok ? 1 : 0;
+  if (rc == 0) rc = gather();
+  for (int r = 0; ok && r < W; ++r) ok = all[r].ok == 1;
+  cudaFree(d_rec);
+  if (rc != 0 || !ok) { peer_teardown(ctx); return rc; }
+  *ctx->peer_err_h = 0;
+  PeerAR& p = ctx->peer;
+  for (int r = 0; r < W; ++r) {
+    p.data[r] = (double*)base[r];
+    p.flags[r] = (unsigned long long*)((char*)base[r] + data_bytes);
+  }
+  p.seq = (unsigned long long*)((char*)ctx->peer_base + data_bytes + flag_bytes);
+  int* derr = nullptr;
+  CK(ctx, cudaHostGetDevicePointer((void**)&derr, ctx->peer_err_h, 0));
+  p.err = derr;
+  p.rank = me; p.world = W; p.nmax = nmax;
+  ctx->peer_ok = true;
+  return 0;
+}
+
 void dcgansr_ctx_destroy(dcgansr_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->cfg.device);
@@ -1091,6 +1181,7 @@ void dcgansr_ctx_destroy(dcgansr_ctx* ctx) {
     live.swap(ctx->nets);
     for (dcgansr_net* n : live) net_release_device(n);
   }
+  peer_teardown(ctx);
   if (ctx->comm && ctx->nccl.CommDestroy) ctx->nccl.CommDestroy(ctx->comm);
   for (float* p : ctx->slots) if (p) cudaFree(p);
   if (ctx->tcws.part) cudaFree(ctx->tcws.part);
@@ -1120,6 +1211,8 @@ int dcgansr_synchronize(dcgansr_ctx* ctx) {
   if (!ctx) return fail(nullptr, DCGANSR_ERR_INVALID, "null ctx");
   CK(ctx, cudaStreamSynchronize(ctx->stream));
   CKLAST(ctx);
+  if (ctx->peer_err_h && *(volatile int*)ctx->peer_err_h)
+    return fail(ctx, DCGANSR_ERR_NCCL, "peer-memory all-reduce: a rank did not arrive within the time-out");
   return 0;
 }
 int dcgansr_timer_begin(dcgansr_ctx* ctx) {
@@ -1234,8 +1327,10 @@ int dcgansr_comm_init(dcgansr_ctx* ctx, const void* unique_id_128) {
   ncclUniqueId id;
   memcpy(&id, unique_id_128, 128);
   CKN(ctx, ctx->nccl.CommInitRank(&ctx->comm, ctx->cfg.world_size, id, ctx->cfg.rank));
-  return 0;
+  return peer_setup(ctx);
 }
+
+int dcgansr_comm_peer_enabled(dcgansr_ctx* ctx) { return ctx && ctx->peer_ok ? 1 : 0; }
 
 // ---- net description --------------------------------------------------------------------------
 void dcgansr_net_destroy(dcgansr_net* net) {
@@ -1667,6 +1762,8 @@ static int check_step_args(dcgansr_ctx* ctx, dcgansr_net* G, dcgansr_net* D, con
   if (G->out_c != D->in_c || G->out_h != D->in_h || G->out_w != D->in_w)
     return fail(ctx, DCGANSR_ERR_INVALID, "G output shape must equal D input shape");
   if (cfg->loss != DCGANSR_LOSS_BCE && cfg->loss != DCGANSR_LOSS_MSE) return fail(ctx, DCGANSR_ERR_INVALID, "bad loss kind");
+  if (ctx->peer_err_h && *(volatile int*)ctx->peer_err_h)
+    return fail(ctx, DCGANSR_ERR_NCCL, "peer-memory all-reduce: a rank did not arrive within the time-out (earlier step)");
   if (ctx->cfg.world_size > 1 && !ctx->comm)
     return fail(ctx, DCGANSR_ERR_NCCL, "world_size > 1 but dcgansr_comm_init was never called: the ranks would train unsynchronised replicas");
   return 0;

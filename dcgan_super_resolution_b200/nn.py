@@ -80,6 +80,10 @@ class Context:
         buf = C.create_string_buffer(bytes(unique_id), 128)
         L.check(self.lib.dcgansr_comm_init(self.h, buf), self.h)
 
+    def comm_peer_enabled(self) -> bool:
+        """True when the sync_bn statistics go through the one-shot NVLink peer-memory all-reduce (kernels_peer.cu)."""
+        return bool(self.lib.dcgansr_comm_peer_enabled(self.h))
+
 
 # ---- module descriptors: constructor signatures of torch/nn ------------------------------------
 class Module:

@@ -124,6 +124,10 @@ int dcgansr_profile_end(dcgansr_ctx* ctx, char* json_out, int64_t cap);
  * dcgansr_comm_get_unique_id and distributed by the host (torch.distributed / MPI / file). */
 int dcgansr_comm_get_unique_id(dcgansr_ctx* ctx, void* unique_id_128);
 int dcgansr_comm_init(dcgansr_ctx* ctx, const void* unique_id_128);
+/* 1 when dcgansr_comm_init mapped every rank's exchange area into every peer (cudaIpc over NVLink / NVSwitch, one node,
+ * <= 8 ranks): the sync_bn statistics are then all-reduced by a one-shot push kernel fused into the BatchNorm statistics tail
+ * instead of ncclAllReduce.  0: single rank, peers not mappable, or DCGANSR_PEER_AR=0 -- every rank takes the same answer. */
+int dcgansr_comm_peer_enabled(dcgansr_ctx* ctx);
 
 /* ---- net description: nn.Sequential():add(...) (train.lua:97-136) ------------------------ */
 /* ctx may be NULL: a plan-only net (shape inference, parameter counts; no device memory, every
