@@ -440,7 +440,8 @@ def run_workload(env, ctx, workload, B, steps, warmup, precision, legs=("staged"
 def sync_bn_timing(env, workload="C4", B=64, steps=20):
     """ms per sync_bn=1 step of a BatchNorm-heavy small-step workload, statistics through the peer-memory kernel vs ncclAllReduce."""
     out = {"workload": f"{workload} at {B} per GPU, sync_bn=1, CUDA graph, {steps} steps"}
-    for name, peer in (("nccl", False), ("peer", True), ("nccl_again", False), ("peer_again", True)):
+    for name, peer in (("nccl", False), ("peer", True)) * 2:
+        name = name + ("_again" if name in out else "")
         if not peer:
             os.environ["DCGANSR_PEER_AR"] = "0"
         try:
@@ -453,8 +454,9 @@ def sync_bn_timing(env, workload="C4", B=64, steps=20):
     return out
 
 
-def dp_check(env):
-    """The 2-GPU checks of scripts/dp_check.py at whatever N the run has (the driver's pytest box has one GPU)."""
+def dp_check(env, quick=False):
+    """The 2-GPU checks of scripts/dp_check.py at whatever N the run has (the driver's pytest box has one GPU).
+    quick: only the sync_bn / peer-memory all-reduce part."""
     import numpy as np
 
     import dcgan_super_resolution_b200 as dsr
@@ -493,7 +495,7 @@ def dp_check(env):
             os.environ.pop("DCGANSR_PEER_AR", None)
 
     res = {"world": env.world, "batch_per_rank": B}
-    for prec in ("strict", "tf32"):
+    for prec in (() if quick else ("strict", "tf32")):
         a = run(env.world, prec, False)
         b = run(env.world, prec, False, no_overlap=True)
         c = run(env.world, prec, False, graph=True)

@@ -9,7 +9,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import bench  # noqa: E402
 
 env = bench.Env()
-res = bench.dp_check(env)
+res = bench.dp_check(env, quick="--quick" in sys.argv)
 env.close()
 if env.rank == 0:
     print(json.dumps(res))
