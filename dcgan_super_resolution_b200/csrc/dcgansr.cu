@@ -17,6 +17,7 @@
 
 #include <dlfcn.h>
 #include <nccl.h>
+#include <mutex>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1094,10 +1095,30 @@ int dcgansr_ctx_create(const dcgansr_cfg* cfg, dcgansr_ctx** out) {
 }
 
 // ---- peer-memory exchange area of the one-shot all-reduce (kernels_peer.cu) ------------------
+// The exchange areas are pooled per process and device and never freed: freeing memory a peer still has mapped is undefined
+// behaviour, and a barrier inside a destructor could hang behind a lost rank.  A context takes a free area of its device (1 MB
+// each) and hands it back; every dcgansr_comm_init zeroes it again behind the ranks' rendezvous.
+struct PeerArea { int device; void* ptr; bool in_use; };
+static std::mutex g_peer_mu;
+static std::vector<PeerArea> g_peer_pool;
+static void* peer_area_acquire(int device, size_t bytes) {
+  std::lock_guard<std::mutex> lk(g_peer_mu);
+  for (auto& a : g_peer_pool)
+    if (a.device == device && !a.in_use) { a.in_use = true; return a.ptr; }
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  g_peer_pool.push_back(PeerArea{device, p, true});
+  return p;
+}
+static void peer_area_release(void* ptr) {
+  std::lock_guard<std::mutex> lk(g_peer_mu);
+  for (auto& a : g_peer_pool)
+    if (a.ptr == ptr) a.in_use = false;
+}
 static void peer_teardown(dcgansr_ctx* ctx) {
   for (void* m : ctx->peer_maps) if (m) cudaIpcCloseMemHandle(m);
   ctx->peer_maps.clear();
-  if (ctx->peer_base) cudaFree(ctx->peer_base);
+  if (ctx->peer_base) peer_area_release(ctx->peer_base);
   ctx->peer_base = nullptr;
   if (ctx->peer_err_h) cudaFreeHost(ctx->peer_err_h);
   ctx->peer_err_h = nullptr;
@@ -1117,7 +1138,8 @@ static int peer_setup(dcgansr_ctx* ctx) {
   static_assert(sizeof(Rec) == 128, "one record per rank");
   Rec mine;
   memset(&mine, 0, sizeof(mine));
-  if (want && cudaMalloc(&ctx->peer_base, data_bytes + flag_bytes + 256) == cudaSuccess) {
+  peer_teardown(ctx);
+  if (want && (ctx->peer_base = peer_area_acquire(ctx->cfg.device, data_bytes + flag_bytes + 256)) != nullptr) {
     CK(ctx, cudaMemsetAsync(ctx->peer_base, 0, data_bytes + flag_bytes + 256, ctx->stream));
     if (cudaIpcGetMemHandle(&mine.h, ctx->peer_base) == cudaSuccess) mine.ok = 1;
   }
