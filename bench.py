@@ -583,8 +583,47 @@ def main():
         sctx = env.new_ctx("strict", graph=bool(args.graph), sync_bn=bool(args.sync_bn))
         strict = run_workload(env, sctx, args.workload, B, max(2, min(args.steps, 5)), 3, "strict", legs=("staged", "profile"), profile_steps=1)
         sctx.close()
+
+    def make_line(dpc, cpu):
+        return {
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+            "config": make_config(args.workload, cfg, B, world),
+            "run": {"precision": args.precision, "cuda_graph": bool(args.graph), "graph_prime_steps": head.get("graph_prime_steps"),
+                    "sync_bn": bool(args.sync_bn), "generator_microbatch": head.get("generator_microbatch"), "control_plane": "gloo (the only NCCL communicators are libdcgansr's)" if world > 1 else "single process",
+                    "l2": f"no flush: per-step working set (conv outputs {head['conv_out_mb_per_rank']:.0f} MB fp32 per rank, rotating staged input "
+                          "batches) exceeds the 126 MB L2",
+                    "algorithmic_gflop_per_step_per_gpu": head["algorithmic_gflop_per_step_per_gpu"]},
+            "step_tflops": head["step_tflops"],
+            "clocks": head.get("clocks"),
+            "e2e": head.get("e2e"),
+            "gpu_launches": head["gpu_launches"],
+            "roofline": head.get("roofline"),
+            "kernels": head.get("kernels"),
+            "eager_profile_ms_per_step": head.get("eager_profile_ms_per_step"),
+            "strict": None if strict is None else {k: strict.get(k) for k in ("value", "ms_per_step", "step_tflops", "steps", "gpu_launches", "roofline")},
+            "workloads": [{k: r.get(k) for k in ("workload", "global_batch", "scaling", "steps", "ms_per_step", "value", "step_tflops", "gpu_launches",
+                                                 "roofline", "eager_profile_ms_per_step")} for r in extras],
+            "dp_check": dpc,
+            "cpu_baseline": cpu,
+        }
+
     if not args.no_extra and world > 1:
-        dpc = dp_check(env)
+        # the checks run behind the measurements; should they ever raise or hang (a lost rank), the bench line still goes out
+        def _give_up():
+            if rank == 0:
+                print(json.dumps(make_line({"error": "dp_check did not finish within 300 s"}, None)))
+                sys.stdout.flush()
+            os._exit(0)
+        wd = threading.Timer(300.0, _give_up)
+        wd.daemon = True
+        wd.start()
+        try:
+            dpc = dp_check(env)
+        except Exception as e:   # noqa: BLE001 -- reported in the line
+            dpc = {"error": f"{type(e).__name__}: {e}"[:400]}
+        wd.cancel()
 
     # every rank has destroyed its contexts (and with them the library's NCCL communicators); ranks != 0 leave before the
     # CPU leg starts, through the normal interpreter exit
@@ -593,30 +632,7 @@ def main():
         return 0
 
     cpu = None if args.no_cpu_baseline else cpu_baseline(args.workload, B)
-    line = {
-        "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
-        "config": make_config(args.workload, cfg, B, world),
-        "run": {"precision": args.precision, "cuda_graph": bool(args.graph), "graph_prime_steps": head.get("graph_prime_steps"),
-                "sync_bn": bool(args.sync_bn), "generator_microbatch": head.get("generator_microbatch"), "control_plane": "gloo (the only NCCL communicators are libdcgansr's)" if world > 1 else "single process",
-                "l2": f"no flush: per-step working set (conv outputs {head['conv_out_mb_per_rank']:.0f} MB fp32 per rank, rotating staged input "
-                      "batches) exceeds the 126 MB L2",
-                "algorithmic_gflop_per_step_per_gpu": head["algorithmic_gflop_per_step_per_gpu"]},
-        "step_tflops": head["step_tflops"],
-        "clocks": head.get("clocks"),
-        "e2e": head.get("e2e"),
-        "gpu_launches": head["gpu_launches"],
-        "roofline": head.get("roofline"),
-        "kernels": head.get("kernels"),
-        "eager_profile_ms_per_step": head.get("eager_profile_ms_per_step"),
-        "strict": None if strict is None else {k: strict.get(k) for k in ("value", "ms_per_step", "step_tflops", "steps", "gpu_launches", "roofline")},
-        "workloads": [{k: r.get(k) for k in ("workload", "global_batch", "scaling", "steps", "ms_per_step", "value", "step_tflops", "gpu_launches",
-                                             "roofline", "eager_profile_ms_per_step")} for r in extras],
-        "dp_check": dpc,
-        "cpu_baseline": cpu,
-    }
-    print(json.dumps(line))
+    print(json.dumps(make_line(dpc, cpu)))
     sys.stdout.flush()
     return 0
 
