@@ -85,6 +85,7 @@ struct HaloParams {
   int stats_row0;                        // [rows][2*Co] doubles receives this CTA's (sum y, sum y^2) per output channel (its cout slice)
   int pair;                              // CTA pairs (cta_group::2): one MMA covers the tiles of both CTAs (M = 256), each CTA holds half of
                                          // every weight block; loads complete on the leader's barriers, commits are multicast
+  int pf_dist;                           // L2 prefetch distance in tiles (0: no prefetch); DCGANSR_HALO_PFDIST overrides the default
   int dbg;                               // DCGANSR_HALO_DBG (timing experiments only): 1 skip MMAs, 2 skip stores, 4 skip the halo TMA loads
 };
 
@@ -328,7 +329,7 @@ __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel
       // plane ring: plane pl of the CTA's it-th tile lives in buffer (it * nplanes + pl) % nring
       int rs = 0;
       uint32_t rph = 0;
-      const int pf_dist = p.nring / p.nplanes + 1;
+      const int pf_dist = p.pf_dist;
       for (int tile = tfirst; tile < tlimit; tile += tstep) {
         int tt = tile;
         const int tx = tt % p.tiles_x; tt /= p.tiles_x;
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(32 * (9 + HALO_MAXGRP), 1) tapconv_halo_kernel
         // most of the shared memory), which alone does not keep enough DRAM reads in flight
         {
           const int ptile = tile + pf_dist * tstep;
-          if (ptile < p.ntiles) {
+          if (pf_dist > 0 && ptile < p.ntiles) {
             int pt = ptile;
             const int ptx = pt % p.tiles_x; pt /= p.tiles_x;
             const int pty = pt % p.tiles_y; pt /= p.tiles_y;
@@ -907,6 +908,13 @@ bool k_tapconv_halo(St st, const TapGeom* classes, int ncls, const float* const*
   HaloParams& p = c.p;
   p.act = act; p.neg = negval;
   p.stats = (stats && p.Npad <= 32) ? stats : nullptr; p.stats_row0 = stats_row0;
+  // L2 prefetch policy (measured on the C3b layers, scripts/exp/halo_pf_ab.py): the prefetch doubles the read requests the L2 serves
+  // (lts__t_sectors of FC 48->24 forward: 71 M sectors of TMA loads + 140 M of prefetches), which costs more than it hides once the
+  // plane ring itself holds more than one tile (C 24->12 dgrad 937 -> 895 us, FC 48->24 dgrad 1046 -> 994, C 24->12 forward 811 ->
+  // 794, FC 48->24 forward unchanged); CTA pairs (big resident weights, starved ring) keep it, one tile ahead (FC 96->48 forward
+  // 677 -> 649 us at distance 1 instead of 2; its dgrad 678 at 1, 732 at 0 or 2)
+  p.pf_dist = p.pair ? 1 : (p.nring > p.nplanes ? 0 : p.nring / p.nplanes + 1);
+  if (const char* d = getenv("DCGANSR_HALO_PFDIST")) p.pf_dist = std::max(0, std::min(8, atoi(d)));      // timing experiments
   if (const char* d = getenv("DCGANSR_HALO_DBG")) p.dbg = atoi(d);
   const TapGeom& g = classes[0];
   EncodeTiledFn enc = tc_encode_fn();
