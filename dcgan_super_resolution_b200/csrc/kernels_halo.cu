@@ -910,10 +910,11 @@ bool k_tapconv_halo(St st, const TapGeom* classes, int ncls, const float* const*
   p.stats = (stats && p.Npad <= 32) ? stats : nullptr; p.stats_row0 = stats_row0;
   // L2 prefetch policy (measured on the C3b layers, scripts/exp/halo_pf_ab.py): the prefetch doubles the read requests the L2 serves
   // (lts__t_sectors of FC 48->24 forward: 71 M sectors of TMA loads + 140 M of prefetches), which costs more than it hides once the
-  // plane ring itself holds more than one tile (C 24->12 dgrad 937 -> 895 us, FC 48->24 dgrad 1046 -> 994, C 24->12 forward 811 ->
+  // plane ring itself holds at least one tile (C 24->12 dgrad 937 -> 895 us, FC 48->24 dgrad 1046 -> 994, C 24->12 forward 811 ->
   // 794, FC 48->24 forward unchanged); CTA pairs (big resident weights, starved ring) keep it, one tile ahead (FC 96->48 forward
   // 677 -> 649 us at distance 1 instead of 2; its dgrad 678 at 1, 732 at 0 or 2)
-  p.pf_dist = p.pair ? 1 : (p.nring > p.nplanes ? 0 : p.nring / p.nplanes + 1);
+  // a ring of exactly one tile (single-CTA form): C2's FC 64->32 dgrad 183 -> 169 us, C4's C 32->64 forward 54.7 -> 50.0 without prefetch
+  p.pf_dist = p.pair ? 1 : (p.nring >= p.nplanes ? 0 : p.nring / p.nplanes + 1);
   if (const char* d = getenv("DCGANSR_HALO_PFDIST")) p.pf_dist = std::max(0, std::min(8, atoi(d)));      // timing experiments
   if (const char* d = getenv("DCGANSR_HALO_DBG")) p.dbg = atoi(d);
   const TapGeom& g = classes[0];

@@ -12,6 +12,10 @@ if len(sys.argv) > 1 and sys.argv[1] == "small":      # the halo launches of C2 
     LAYERS = [("C2 FC 64->32 fwd", (1, 64, 128, 32, 4, 2, 1, 64, 0)), ("C2 FC 64->32 dgrad", (1, 64, 128, 32, 4, 2, 1, 64, 1)),
               ("C2 C 32->16 fwd", (0, 32, 256, 16, 4, 2, 1, 64, 0)), ("C2 C 32->16 dgrad", (0, 32, 256, 16, 4, 2, 1, 64, 1)),
               ("C4 FC 32->16 fwd", (1, 32, 128, 16, 4, 2, 1, 64, 0)), ("C4 C 16->32 fwd", (0, 16, 256, 32, 4, 2, 1, 64, 0))]
+if len(sys.argv) > 1 and sys.argv[1] == "onetile":    # layers whose plane ring holds at most one tile (C2 / C4 / C1b)
+    LAYERS = [("C2 FC 64->32 dgrad", (1, 64, 128, 32, 4, 2, 1, 64, 1)), ("C4 C 32->64 fwd", (0, 32, 128, 64, 4, 2, 1, 64, 0)),
+              ("C1b FC 128->64 fwd", (1, 128, 128, 64, 4, 2, 1, 64, 0)), ("C1b FC 128->64 dgr", (1, 128, 128, 64, 4, 2, 1, 64, 1)),
+              ("C1b C 64->128 fwd", (0, 64, 256, 128, 4, 2, 1, 64, 0)), ("C1b C 64->128 dgr", (0, 64, 256, 128, 4, 2, 1, 64, 1))]
 MODES = [None, "0", "1", "2", "3", "4"]      # unset = the policy of k_tapconv_halo
 for rep in range(2):
     for name, (full, cin, h, cout, k, s, p, n, what) in LAYERS:
