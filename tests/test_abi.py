@@ -212,3 +212,11 @@ def test_build_compiles_every_cuda_source():
     on_disk = sorted(f for f in os.listdir(os.path.join(here, "csrc")) if f.endswith(".cu"))
     assert sorted(b.SOURCES) == on_disk, (sorted(b.SOURCES), on_disk)
     assert "arch=compute_100a,code=sm_100a" in " ".join(b.NVCC_FLAGS) and "-lineinfo" in b.NVCC_FLAGS
+
+
+def test_comm_peer_enabled_is_zero_without_a_communicator():
+    """dcgansr_comm_peer_enabled answers 0 for a NULL context (no device needed): the peer-memory exchange of the sync_bn
+    statistics (kernels_peer.cu) only exists behind dcgansr_comm_init on a multi-rank context."""
+    from dcgan_super_resolution_b200 import _lib as L
+    lib = L.load()
+    assert lib.dcgansr_comm_peer_enabled(None) == 0
