@@ -148,3 +148,49 @@ def test_step_is_data_parallel_decomposable():
         D.backward(xs, g)
         acc += D.get_flat_grads()
     assert torch.allclose(acc, full, atol=1e-12)
+
+
+def test_sync_bn_sums_over_shards_equal_the_big_batch():
+    """What sync_bn=1 exchanges between ranks (kernels_peer.cu / ncclAllReduce): per-shard (sum x, sum x^2) forward and
+    (sum g, sum g*xhat) backward, added in rank order and finalised as var = sum x^2 / n - mean^2 with the GLOBAL n -- the
+    arithmetic of bn_finalize_peer_kernel and bn_bwd_apply -- reproduces SpatialBatchNormalization on the concatenated
+    batch (train.lua:100-109 semantics: biased variance normalises, unbiased n/(n-1) goes to running_var)."""
+    r = rng(11)
+    W, b = 4, 3
+    x = t64(r.standard_normal((W * b, 5, 4, 6)) * 2 + 0.5)
+    dy = t64(r.standard_normal(tuple(x.shape)))
+    g, be = t64(r.standard_normal(5)), t64(r.standard_normal(5))
+    rm0, rv0 = t64(r.standard_normal(5)), t64(r.uniform(0.5, 2.0, 5))
+    y, mean, invstd, rm, rv = ops.bn_fwd_train(x, g, be, rm0, rv0)
+    dx, dg, db = ops.bn_bwd(x, dy, g, mean, invstd)
+    # forward: the ranks' sums, rank order
+    s1, s2 = torch.zeros(5, dtype=torch.float64), torch.zeros(5, dtype=torch.float64)
+    for k in range(W):
+        xs = x[k * b:(k + 1) * b]
+        s1 = s1 + xs.sum(dim=(0, 2, 3))
+        s2 = s2 + (xs * xs).sum(dim=(0, 2, 3))
+    n = float(W * b * 4 * 6)
+    m = s1 / n
+    var = torch.clamp(s2 / n - m * m, min=0.0)
+    inv = 1.0 / torch.sqrt(var + 1e-5)
+    assert torch.allclose(m, mean, atol=1e-12) and torch.allclose(inv, invstd, rtol=1e-10)
+    assert torch.allclose(0.9 * rm0 + 0.1 * m, rm, atol=1e-12)
+    assert torch.allclose(0.9 * rv0 + 0.1 * var * (n / (n - 1.0)), rv, rtol=1e-10)
+    # every rank normalises its shard with the global statistics: the concatenation is the big-batch output
+    ys = torch.cat([(x[k * b:(k + 1) * b] - m[None, :, None, None]) * inv[None, :, None, None] * g[None, :, None, None] + be[None, :, None, None]
+                    for k in range(W)])
+    assert torch.allclose(ys, y, atol=1e-10)
+    # backward: the ranks' (sum g, sum g*xhat); dgamma / dbeta are the LOCAL sums (the gradient all-reduce adds them later)
+    t1, t2 = torch.zeros(5, dtype=torch.float64), torch.zeros(5, dtype=torch.float64)
+    loc = []
+    for k in range(W):
+        xs, ds = x[k * b:(k + 1) * b], dy[k * b:(k + 1) * b]
+        xh = (xs - m[None, :, None, None]) * inv[None, :, None, None]
+        a1, a2 = ds.sum(dim=(0, 2, 3)), (ds * xh).sum(dim=(0, 2, 3))
+        loc.append((a1, a2))
+        t1, t2 = t1 + a1, t2 + a2
+    dxs = torch.cat([(dy[k * b:(k + 1) * b] - (t1 / n)[None, :, None, None]
+                      - (x[k * b:(k + 1) * b] - m[None, :, None, None]) * inv[None, :, None, None] * (t2 / n)[None, :, None, None])
+                     * (g * inv)[None, :, None, None] for k in range(W)])
+    assert torch.allclose(dxs, dx, atol=1e-10)
+    assert torch.allclose(sum(a for a, _ in loc), db, atol=1e-10) and torch.allclose(sum(a for _, a in loc), dg, atol=1e-10)
