@@ -296,15 +296,21 @@ def aggregate_profile(prof, profile_steps, peaks, precision):
     return top, total_ms / max(profile_steps, 1)
 
 
-def roofline_of(top, peaks, precision):
+def roofline_of(top, peaks, precision, workload=None, batch=None):
     if not top:
         return None
     t = top[0]
+    # traffic: dram__bytes_read + dram__bytes_write PER LAUNCH (like `achieved`): the mean over this kernel's launches in the
+    # committed per-launch ncu capture of one step -- which exists for the headline workload at its own batch only
     traffic = None
     tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and workload == HEADLINE and precision == "tf32":
         try:
-            traffic = json.load(open(tp)).get(t["kernel"], {}).get("dram_bytes")
+            from dcgan_super_resolution_b200 import models
+            if batch == models.config(HEADLINE)["batch"]:
+                rows = [r for r in json.load(open(tp)).get("_all", {}).get(t["kernel"], []) if r.get("from") == f"{HEADLINE} step"]
+                if rows:
+                    traffic = sum(r["dram_bytes"] for r in rows) / len(rows)
         except Exception:
             traffic = None
     return {"bound": t["bound"], "achieved": t["achieved"], "peak": t["peak"], "unit": t["unit"], "frac": t["frac"], "traffic": traffic,
@@ -315,8 +321,8 @@ def roofline_of(top, peaks, precision):
                                               "reached -- the pipe's own TF32 ceiling is 1.09-1.16 PFLOP/s at 1.8-1.96 GHz, see sm__pipe_tensor_cycles_active "
                                               "in profiles/r2_ncu_full.csv)" if precision == "tf32"
                                               else " (burst bf16 GEMM; strict mode computes in fp32 FFMA)"),
-            "traffic_note": "dram__bytes_read+write of the heaviest launch of this kernel in profiles/ (ncu --set full); null when that "
-                            "capture was taken on another workload's shapes"}
+            "traffic_note": "mean dram__bytes_read+write per launch of this kernel over one step of this workload (ncu per-launch capture, "
+                            "profiles/r2_step_metrics_c3b.csv -> profiles/traffic.json); null for workloads without a committed capture"}
 
 
 def conv_out_bytes(cfg, B):
@@ -428,7 +434,7 @@ def run_workload(env, ctx, workload, B, steps, warmup, precision, legs=("staged"
         peaks = load_peaks()
         top, eager_ms = aggregate_profile(prof, profile_steps, peaks, precision)
         res["kernels"] = top[:10]
-        res["roofline"] = roofline_of(top, peaks, precision)
+        res["roofline"] = roofline_of(top, peaks, precision, workload, B)
         res["eager_profile_ms_per_step"] = eager_ms
         res["launches_per_step_eager"] = sum(t["launches_per_step"] for t in top)
     res["conv_out_mb_per_rank"] = conv_out_bytes(cfg, B) / 1e6
